@@ -1,0 +1,231 @@
+"""
+Generate tests/golden/*.npz by running the UPSTREAM geosss package
+(oracle tooling; runs only in the build container where /root/reference exists).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Nothing here is imported at test/bench time.  Each fixture stores the inputs
+(parameters, points, initial state, the flat draw tape recorded from the
+reference's own PCG64 run) and the reference's outputs (log-densities,
+trajectories, cumulative rejection counts), all float64.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("GEOSSS_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import geosss as gs  # noqa: E402  (the upstream package)
+from geosss.distributions import CurvedVonMisesFisher  # noqa: E402
+from geosss.pointcloud import PointCloud  # noqa: E402
+from geosss.registration import CoherentPointDrift, GaussianMixtureModel  # noqa: E402
+from geosss.spherical_curve import SlerpCurve, brownian_curve  # noqa: E402
+
+from oracle.tape import TapeRNG  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+README_MUS = np.array([[0.87, -0.37, 0.33], [-0.20, -0.89, -0.40], [0.19, 0.22, -0.96]])
+README_X0 = np.array([-0.86, 0.19, -0.47])
+
+
+def points(d, n, seed, scale_some=True):
+    """Unit points plus a few deliberately un-normalised rows."""
+    x = gs.sample_sphere(d - 1, n, seed=seed)
+    if scale_some:
+        x[::7] *= 0.998
+        x[3::11] *= 1.07
+    return x
+
+
+def vmf_mixture(mus, weights=None):
+    return gs.MixtureModel([gs.VonMisesFisher(m) for m in mus], weights)
+
+
+def record_run(cls, pdf, x0, seed, n_states):
+    """Run the upstream sampler with a recording shim; return tape + trajectory."""
+    smp = cls(pdf, np.array(x0, dtype=float), seed)
+    rec = TapeRNG(source=smp.rng)
+    smp.rng = rec
+    traj = [np.array(smp.state)]
+    cum_rej = [0]
+    while len(traj) < n_states:
+        traj.append(np.copy(next(smp)))
+        cum_rej.append(smp.n_reject)
+    return rec.recorded(), np.array(traj), np.array(cum_rej, dtype=np.int64)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def golden_logprob():
+    out = {}
+    # C1 README mixture, C2 d=10 K=5 at three kappas, a weighted mixture, a lone vMF
+    out["c1_mus"] = 80.0 * README_MUS
+    out["c1_x"] = points(3, 96, 11)
+    out["c1_logp"] = vmf_mixture(out["c1_mus"]).log_prob(out["c1_x"])
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    out["c2_modes"] = modes
+    out["c2_x"] = points(10, 256, 12)
+    for kappa in (50, 100, 500):
+        out[f"c2_logp_k{kappa}"] = vmf_mixture(kappa * modes).log_prob(out["c2_x"])
+    out["wmix_mus"] = np.array([30.0, 5.0, 120.0, 60.0])[:, None] * gs.sample_sphere(5, 4, seed=5)
+    out["wmix_w"] = np.array([0.5, 2.0, 1.0, 0.25])
+    out["wmix_x"] = points(6, 64, 13)
+    out["wmix_logp"] = vmf_mixture(out["wmix_mus"], out["wmix_w"]).log_prob(out["wmix_x"])
+    out["vmf_mu"] = 42.0 * gs.sample_sphere(7, seed=6)
+    out["vmf_x"] = points(8, 64, 14)
+    out["vmf_logp"] = gs.VonMisesFisher(out["vmf_mu"]).log_prob(out["vmf_x"])
+    # overflow quirk: kappa > ~713 -> i0 = inf -> log_prob = -inf
+    with np.errstate(over="ignore"):
+        out["vmf_big_logp"] = vmf_mixture(800.0 * modes).log_prob(out["c2_x"][:8])
+    save("logprob_vmf", **out)
+
+    out = {}
+    # C4 diagonal, its dense variant, a small dense one, Bingham-Fisher
+    for tag, d, vmax, eig, seed in (("c4diag", 50, 300, True, 6982), ("c4dense", 50, 300, False, 6982),
+                                   ("d10", 10, 30, False, 6982)):
+        pdf = gs.random_bingham(d, vmax, 0, eig, seed)
+        x = points(d, 128, 20 + d)
+        out[f"{tag}_A"], out[f"{tag}_x"], out[f"{tag}_logp"] = pdf.A, x, pdf.log_prob(x)
+        out[f"{tag}_mode"] = pdf.mode
+    A = gs.random_bingham(6, 20, 0, False, 3).A
+    b = 4.0 * gs.sample_sphere(5, seed=4)
+    x = points(6, 64, 27)
+    out["bf_A"], out["bf_b"], out["bf_x"] = A, b, x
+    out["bf_logp"] = gs.BinghamFisher(A, b).log_prob(x)
+    save("logprob_bingham", **out)
+
+    out = {}
+    for tag, d in (("c3", 100), ("d10", 10), ("d3", 3)):
+        knots = brownian_curve(10, d, 0.5, seed=4562)
+        pdf = CurvedVonMisesFisher(SlerpCurve(knots), 500.0)
+        x = np.vstack([points(d, 96, 30 + d), knots[:3], gs.sphere.radial_projection(knots[4] + knots[5])])
+        out[f"{tag}_knots"], out[f"{tag}_x"], out[f"{tag}_logp"] = knots, x, pdf.log_prob(x)
+    save("logprob_curved", **out)
+
+    out = {}
+    data = np.load(os.path.join(REF, "data", "protein_registration.npz"))
+    tgt, src = data["target"], data["source"]
+    out["c5_target"], out["c5_source"] = tgt, src
+    out["c5_rotation"], out["c5_sigma"], out["c5_omega"] = data["rotation"], float(data["sigma"]), float(
+        data["prob_outlier"])
+    cpd = CoherentPointDrift(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(len(src)) / len(src)),
+                             sigma=1.0, k=20, omega=0.4)
+    q = points(4, 48, 41)
+    from scipy.spatial.transform import Rotation
+    q = np.vstack([q, Rotation.from_matrix(data["rotation"]).as_quat(), [0, 0, 0, 1.0]])
+    out["c5_q"] = q
+    out["c5_logp"] = np.array([cpd.log_prob(row) for row in q])
+    # cube case in the style of tests/test_cpd.py:16-141 (k=8, sigma=0.5, omega in {0,.2,.4}), seeded
+    gen = np.random.default_rng(77)
+    cube = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dtype=float)
+    cube = np.vstack([cube, gen.uniform(0, 1, (22, 3))])
+    Rtrue = Rotation.from_euler("zyx", [30, -20, 55], degrees=True).as_matrix()
+    tcl = cube @ Rtrue.T + 0.02 * gen.standard_normal(cube.shape)
+    w_s = gen.uniform(0.5, 1.5, len(cube))
+    w_t = gen.uniform(0.5, 1.5, len(cube))
+    out["cube_target"], out["cube_source"], out["cube_ws"], out["cube_wt"] = tcl, cube, w_s, w_t
+    qc = points(4, 32, 43)
+    out["cube_q"] = qc
+    for om in (0.0, 0.2, 0.4):
+        m = CoherentPointDrift(PointCloud(tcl, w_t), PointCloud(cube, w_s), sigma=0.5, k=8, omega=om, beta=1.5)
+        out[f"cube_logp_om{int(om * 10)}"] = np.array([m.log_prob(row) for row in qc])
+    g = GaussianMixtureModel(PointCloud(tcl, w_t), PointCloud(cube, w_s), sigma=0.5, k=8)
+    out["cube_logp_gmm"] = np.array([g.log_prob(row) for row in qc])
+    save("logprob_cpd", **out)
+    return tgt, src
+
+
+def golden_trajectories(tgt, src):
+    shrink, reject = gs.ShrinkageSphericalSliceSampler, gs.RejectionSphericalSliceSampler
+
+    def pack(out, tag, cls, pdf, x0, seed, n_states):
+        tape, traj, rej = record_run(cls, pdf, x0, seed, n_states)
+        out[f"{tag}_x0"], out[f"{tag}_tape"], out[f"{tag}_traj"], out[f"{tag}_cumrej"] = x0, tape, traj, rej
+
+    # C1: the README demo itself (1000 samples + 100 burn-in, seed 3521)
+    out = {"mus": 80.0 * README_MUS}
+    pdf = vmf_mixture(80.0 * README_MUS)
+    pack(out, "shrink", shrink, pdf, README_X0, 3521, 1100)
+    pack(out, "reject", reject, pdf, README_X0, 3521, 1100)
+    # what the documented call returns (burn-in chopped)
+    out["readme_shrink_samples"] = shrink(pdf, README_X0.copy(), 3521).sample(1000, 100)
+    out["readme_reject_samples"] = reject(pdf, README_X0.copy(), 3521).sample(1000, 100)
+    save("traj_c1", **out)
+
+    # C2: d=10 K=5, kappa 100 and 500, distinct init/sampler seeds
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    out = {"modes": modes}
+    for kappa in (100, 500):
+        pdf = vmf_mixture(kappa * modes)
+        for s in (0, 1):
+            x0 = gs.sample_sphere(9, seed=1000 + s)
+            pack(out, f"shrink_k{kappa}_s{s}", shrink, pdf, x0, 2000 + s, 1501)
+        pack(out, f"reject_k{kappa}_s0", reject, pdf, gs.sample_sphere(9, seed=1000), 2000, 201)
+    save("traj_c2", **out)
+
+    # C3: curved vMF d=100 kappa=500
+    knots = brownian_curve(10, 100, 0.5, seed=4562)
+    pdf = CurvedVonMisesFisher(SlerpCurve(knots), 500.0)
+    out = {"knots": knots, "kappa": 500.0}
+    pack(out, "shrink", shrink, pdf, gs.sample_sphere(99, seed=1002), 2002, 201)
+    pack(out, "reject", reject, pdf, gs.sample_sphere(99, seed=1003), 2003, 41)
+    save("traj_c3", **out)
+
+    # C4: Bingham d=50 (diagonal as in scripts/bingham.py:123-134, start at the mode) + dense variant
+    out = {}
+    for tag, eig in (("diag", True), ("dense", False)):
+        pdf = gs.random_bingham(50, 300, 0, eig, 6982)
+        out[f"{tag}_A"] = pdf.A
+        pack(out, f"{tag}_shrink", shrink, pdf, pdf.mode.copy(), 2004, 301)
+        pack(out, f"{tag}_reject", reject, pdf, pdf.mode.copy(), 2005, 61)
+    save("traj_c4", **out)
+
+    # C5: CPD registration on S^3
+    cpd = CoherentPointDrift(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(len(src)) / len(src)),
+                             sigma=1.0, k=20, omega=0.4)
+    out = {}
+    pack(out, "shrink", shrink, cpd, gs.sample_sphere(3, seed=1006), 2006, 41)
+    pack(out, "reject", reject, cpd, gs.sample_sphere(3, seed=1007), 2007, 9)
+    save("traj_c5", **out)
+
+
+def golden_misc():
+    out = {}
+    out["sphere_d9_n5_seed1234"] = gs.sample_sphere(9, 5, seed=1234)
+    out["sphere_d2_seed7"] = gs.sample_sphere(2, seed=7)
+    gen = np.random.default_rng(99)
+    z, v = gen.standard_normal((16, 100)), gen.standard_normal((16, 100))
+    out["proj_z"], out["proj_v"] = z, v
+    out["proj_out"] = np.array([gs.spherical_projection(a, b) for a, b in zip(z, v)])
+    out["radial_out"] = gs.radial_projection(z)
+    out["dist_out"] = gs.distance(gs.radial_projection(z), gs.radial_projection(v))
+    out["bingham_c4_A"] = gs.random_bingham(50, 300, 0, True, 6982).A
+    out["bingham_d10_dense_A"] = gs.random_bingham(10, 30, 0, False, 6982).A
+    out["brownian_c3"] = brownian_curve(10, 100, 0.5, seed=4562)
+    # library ESS helpers on an AR(1) trace
+    ar = np.zeros(4000)
+    e = gen.standard_normal(4000)
+    for i in range(1, 4000):
+        ar[i] = 0.8 * ar[i - 1] + e[i]
+    out["ar1"], out["ar1_acf"] = ar, gs.acf_fft(ar)
+    out["ar1_iat"], out["ar1_neff"] = gs.IAT(ar), gs.n_eff(ar)
+    save("misc", **out)
+
+
+if __name__ == "__main__":
+    with np.errstate(over="ignore", divide="ignore"):
+        t, s = golden_logprob()
+        golden_trajectories(t, s)
+        golden_misc()

@@ -1,0 +1,248 @@
+"""
+Target log-densities on the sphere (oracle; test infrastructure only).
+
+Float64 numpy/scipy restatement of the ``log_prob`` methods on the geosss hot
+path.  Each class cites the reference lines it follows.  The classes are plain
+parameter holders: ``log_prob(x)`` accepts one point ``(d,)`` or rows ``(N, d)``.
+"""
+
+import numpy as np
+from scipy.special import i0, logsumexp
+from scipy.spatial import KDTree
+from scipy.spatial.transform import Rotation
+
+from . import sphere
+
+
+class VMFMixture:
+    """Mixture of von Mises-Fisher "densities".
+
+    Component: ``x @ mu - log(2 pi) - log(i0(|mu|))`` (geosss/distributions.py:156-157;
+    the normaliser uses i0 whatever d is and overflows to inf for |mu| >~ 713).
+    Mixture: per-component values are stacked, ``log w`` added and reduced with
+    scipy's logsumexp (distributions.py:218-221); weights are normalised to sum 1
+    and default to uniform (distributions.py:211-216).
+    """
+
+    def __init__(self, mus, weights=None):
+        self.mus = np.array(mus, dtype=float)
+        if self.mus.ndim == 1:
+            self.mus = self.mus[None, :]
+        K = len(self.mus)
+        w = np.ones(K) if weights is None else np.array(weights, dtype=float)
+        self.weights = w / w.sum()
+
+    @property
+    def d(self):
+        return self.mus.shape[1]
+
+    def component_log_prob(self, k, x):
+        mu = self.mus[k]
+        return x @ mu - np.log(2 * np.pi) - np.log(i0(np.linalg.norm(mu)))
+
+    def log_prob(self, x):
+        x = np.asarray(x, dtype=float)
+        p = np.transpose([self.component_log_prob(k, x) for k in range(len(self.mus))])
+        p = p + np.log(self.weights)
+        return logsumexp(p, axis=-1)
+
+    def log_consts(self):
+        """log w_k - log 2pi - log i0(kappa_k): what the device kernels precompute."""
+        with np.errstate(over="ignore"):
+            kap = np.linalg.norm(self.mus, axis=1)
+            return np.log(self.weights) - np.log(2 * np.pi) - np.log(i0(kap))
+
+
+class SingleVMF(VMFMixture):
+    """A lone VonMisesFisher (distributions.py:117-160): no logsumexp, no weights."""
+
+    def __init__(self, mu):
+        super().__init__(np.asarray(mu, dtype=float)[None, :])
+
+    def log_prob(self, x):
+        return self.component_log_prob(0, np.asarray(x, dtype=float))
+
+
+class Bingham:
+    """log p(x) = x^T A x [+ x.b]  (distributions.py:78-86; Fisher term :113-114)."""
+
+    def __init__(self, A, b=None):
+        A = np.asarray(A, dtype=float)
+        assert np.allclose(A, A.T)  # distributions.py:68
+        self.A = A
+        self.b = None if b is None else np.asarray(b, dtype=float)
+        lam, vec = np.linalg.eigh(A)  # ascending (distributions.py:73-76)
+        self.v, self.U = lam[::-1], vec[:, ::-1]
+
+    @property
+    def d(self):
+        return len(self.A)
+
+    @property
+    def mode(self):
+        return self.U[:, 0]
+
+    def log_prob(self, x):
+        x = np.asarray(x, dtype=float)
+        assert x.ndim in (1, 2) and x.shape[-1] == self.d  # distributions.py:84
+        out = np.sum((x @ self.A) * x, axis=-1)
+        if self.b is not None:
+            out = out + x @ self.b
+        return out
+
+
+def random_bingham_matrix(d=2, vmax=None, vmin=None, eigensystem=False, seed=None):
+    """Precision matrix of ``random_bingham`` (distributions.py:230-258)."""
+    gen = np.random.default_rng(seed)
+    G = gen.standard_normal((d, d))
+    S = G.T @ G
+    lam, vec = np.linalg.eigh(S)
+    if vmin is not None:
+        lam += vmin - lam.min()
+    if vmax is not None:
+        lam *= vmax / lam.max()
+    if eigensystem:
+        vec = np.eye(d)
+    return (vec * lam) @ vec.T
+
+
+def brownian_knots(n_points=100, dimension=6, step_size=0.05, seed=1234):
+    """Knots of ``brownian_curve`` (geosss/spherical_curve.py:105-129)."""
+    gen = np.random.default_rng(seed)
+    pts = np.zeros((n_points, dimension))
+    pts[0] = sphere.unit(gen.standard_normal(dimension))
+    for i in range(1, n_points):
+        pts[i] = sphere.unit(pts[i - 1] + gen.normal(size=dimension) * step_size)
+    return pts
+
+
+class CurvedVMF:
+    """kappa * x . (nearest point on the piecewise-slerp curve through the knots).
+
+    distributions.py:272-275 -> SlerpCurve.find_nearest (spherical_curve.py:95-102)
+    -> distance_slerp (spherical_curve.py:10-32).  Segment loop, ``sin(theta)+1e-10``
+    and first-index argmin are kept literally.
+    """
+
+    def __init__(self, knots, kappa=100.0):
+        self.knots = np.asarray(knots, dtype=float)
+        self.kappa = float(kappa)
+
+    @property
+    def d(self):
+        return self.knots.shape[-1]
+
+    @staticmethod
+    def _nearest_on_segment(x, a, b):
+        ang = sphere.distance(a, b)
+        t = np.arctan2(b @ x - a @ x * np.cos(ang), a @ x * np.sin(ang))
+        t = np.clip(t, 0.0, ang)
+        y = (np.sin(ang - t) * a + np.sin(t) * b) / (np.sin(ang) + 1e-10)
+        return sphere.distance(x, y), y
+
+    def nearest(self, x):
+        best, best_y = None, None
+        for a, b in zip(self.knots, self.knots[1:]):
+            dist, y = self._nearest_on_segment(x, a, b)
+            if best is None or dist < best:  # np.argmin keeps the first minimum
+                best, best_y = dist, y
+        return best_y
+
+    def log_prob(self, x):
+        x = np.asarray(x, dtype=float)
+        if x.ndim == 1:
+            return self.kappa * (x @ self.nearest(x))
+        return np.array([self.log_prob(row) for row in x])
+
+
+def quat_to_matrix(q):
+    """scipy Rotation.from_quat(q).as_matrix(): scalar-last, q normalised first
+    (geosss/pointcloud.py:101-115)."""
+    return Rotation.from_quat(q).as_matrix()
+
+
+def quat_to_matrix_closed_form(q):
+    """Closed form of the same map; what the device kernels evaluate."""
+    x, y, z, w = np.asarray(q, dtype=float) / np.linalg.norm(q)
+    return np.array(
+        [
+            [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+            [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+            [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
+        ]
+    )
+
+
+class CPD:
+    """Coherent-point-drift log-likelihood of a rigid rotation (unit quaternion).
+
+    registration.py:47-53 (quaternion -> R, times beta), :101-109 (kNN query of
+    the rotated source against each target point, KDTree rebuilt per call),
+    :197-259 (Gaussian terms + uniform outlier column, logsumexp per target row,
+    weighted sum over rows).  ``k <= 0`` or ``k >= n_source`` sums all source points.
+    """
+
+    def __init__(self, target, source, sigma=1.0, k=20, beta=1.0, omega=0.0,
+                 target_weights=None, source_weights=None):
+        self.target = np.asarray(target, dtype=float)
+        self.source = np.asarray(source, dtype=float)
+        self.w_t = (np.ones(len(self.target)) if target_weights is None
+                    else np.asarray(target_weights, dtype=float))
+        self.w_s = (np.ones(len(self.source)) if source_weights is None
+                    else np.asarray(source_weights, dtype=float))
+        self.sigma, self.k = float(sigma), int(k)
+        self.beta, self.omega = float(beta), float(omega)
+        self.d = 4
+
+    @property
+    def log_outlier(self):
+        # registration.py:205-209, 237-238
+        with np.errstate(divide="ignore"):
+            return np.log(self.omega + 1e-308) - np.sum(np.log(np.ptp(self.target, 0)))
+
+    @property
+    def log_constant(self):
+        # registration.py:211-215
+        D = self.target.shape[1]
+        with np.errstate(divide="ignore"):
+            return np.log(1 - self.omega) - D / 2 * np.log(2 * np.pi * self.sigma**2)
+
+    def _neighbours(self, moved):
+        k = self.k if 0 < self.k < len(moved) else len(moved)
+        dist, ind = KDTree(moved).query(self.target, k=k)
+        if k == 1:
+            dist, ind = dist[:, None], ind[:, None]
+        return dist, ind
+
+    def log_prob_R(self, R):
+        moved = self.source @ R.T
+        dist, ind = self._neighbours(moved)
+        log_phi = -0.5 * dist**2 / self.sigma**2
+        log_p = np.log(self.w_s[ind]) + log_phi + self.log_constant
+        col = np.full((len(self.target), 1), self.log_outlier)
+        rows = logsumexp(np.hstack((log_p, col)), axis=1)
+        return rows @ self.w_t
+
+    def log_prob(self, q):
+        q = np.asarray(q, dtype=float)
+        if q.ndim == 2 and q.shape != (3, 3):
+            return np.array([self.log_prob(row) for row in q])
+        R = q if q.shape == (3, 3) else quat_to_matrix(q)
+        return self.beta * self.log_prob_R(R)
+
+
+class GMM(CPD):
+    """Parent model without the outlier column / (1-omega) factor
+    (registration.py:111-119)."""
+
+    def __init__(self, target, source, sigma=1.0, k=20, beta=1.0,
+                 target_weights=None, source_weights=None):
+        super().__init__(target, source, sigma, k, beta, 0.0, target_weights, source_weights)
+
+    def log_prob_R(self, R):
+        moved = self.source @ R.T
+        dist, ind = self._neighbours(moved)
+        D = self.target.shape[1]
+        log_phi = -0.5 * dist**2 / self.sigma**2
+        log_p = log_phi - D / 2 * np.log(2 * np.pi * self.sigma**2) + np.log(self.w_s[ind])
+        return logsumexp(log_p, axis=1) @ self.w_t
