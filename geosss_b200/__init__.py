@@ -1,0 +1,40 @@
+"""
+geosss_b200 -- B200-native batched engine for geosss's geodesic slice-sampling hot path.
+
+Import-compatible names for the path (``import geosss_b200 as gs``)::
+
+    pdf = gs.MixtureModel([gs.VonMisesFisher(80.0 * mu) for mu in mus])
+    samples = gs.ShrinkageSphericalSliceSampler(pdf, init_state, seed).sample(n_samples, burnin)
+
+All density evaluation and sampling runs in hand-written sm_100a kernels behind the C ABI of
+``libgeosss_cuda.so`` (include/geosss_cuda.h).  There is no CPU fallback.
+"""
+
+from .distributions import (  # noqa: F401
+    Bingham,
+    BinghamFisher,
+    CurvedVonMisesFisher,
+    Distribution,
+    MixtureModel,
+    VonMisesFisher,
+    random_bingham,
+)
+from .mcmc import (  # noqa: F401
+    RejectionSphericalSliceSampler,
+    ShrinkageSphericalSliceSampler,
+    determine_burnin,
+)
+from .pointcloud import PointCloud, matrix2quat, quat2matrix  # noqa: F401
+from .registration import CoherentPointDrift, GaussianMixtureModel  # noqa: F401
+from .sphere import (  # noqa: F401
+    distance,
+    orthogonal_projection,
+    radial_projection,
+    sample_sphere,
+    sample_subsphere,
+    spherical_projection,
+)
+from .spherical_curve import SlerpCurve, SphericalCurve, brownian_curve  # noqa: F401
+from .utils import SamplerLauncher  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,488 @@
+// C ABI of libgeosss_cuda (see include/geosss_cuda.h): handles, parameter upload, dispatch.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/geosss_cuda.h"
+#include "kernels_fast.cuh"
+#include "kernels_literal.cuh"
+
+using namespace geosss;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(GEOSSS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------ device arrays in both precisions
+struct Arr {
+    float* f = nullptr;
+    double* d = nullptr;
+    size_t n = 0;
+    int upload(const double* h, size_t count) {
+        n = count;
+        if (!count) return 0;
+        std::vector<float> hf(count);
+        for (size_t i = 0; i < count; ++i) hf[i] = (float)h[i];
+        CU(cudaMalloc(&f, count * sizeof(float)));
+        CU(cudaMalloc(&d, count * sizeof(double)));
+        CU(cudaMemcpy(f, hf.data(), count * sizeof(float), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d, h, count * sizeof(double), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release() {
+        if (f) cudaFree(f);
+        if (d) cudaFree(d);
+        f = nullptr; d = nullptr;
+    }
+    template <typename T> const T* get() const;
+};
+template <> const float* Arr::get<float>() const { return f; }
+template <> const double* Arr::get<double>() const { return d; }
+
+struct geosss_target {
+    int kind = 0, d = 0;
+    // vMF mixture
+    int K = 0, single = 0;
+    Arr mu, logw, logi0;
+    std::vector<double> h_mu, h_const;  // host copies for the fast path's parameter block
+    // Bingham
+    Arr A, b;
+    int has_b = 0, diag = 0;
+    // curved vMF
+    int M = 0;
+    double kappa = 0;
+    Arr knots, ang, cosang, sinang;
+    // CPD
+    int nt = 0, ns = 0, k = 0, outlier = 1;
+    double sigma2 = 1, log_const = 0, log_outlier = 0, beta = 1;
+    Arr tgt, wt, src, logws;
+
+    template <typename T> VmfMixP<T> vmf() const { return {mu.get<T>(), logw.get<T>(), logi0.get<T>(), K, d, single}; }
+    template <typename T> BinghamP<T> bingham() const { return {A.get<T>(), has_b ? b.get<T>() : nullptr, d}; }
+    template <typename T> CurvedP<T> curved() const {
+        return {knots.get<T>(), ang.get<T>(), cosang.get<T>(), sinang.get<T>(), (T)kappa, M, d};
+    }
+    template <typename T> CpdP<T> cpd() const {
+        return {tgt.get<T>(), wt.get<T>(), src.get<T>(), logws.get<T>(), (T)sigma2, (T)log_const,
+                (T)log_outlier, (T)beta, nt, ns, k, outlier};
+    }
+    void release() {
+        for (Arr* a : {&mu, &logw, &logi0, &A, &b, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+    }
+};
+
+struct geosss_sampler {
+    geosss_target* t = nullptr;
+    int kind = 0, dtype = 0, path = 0;
+    int64_t N = 0;
+    uint64_t seed = 0, chain0 = 0, step = 0;
+    void* state = nullptr;  // (N, d) dtype
+    void* ws = nullptr;     // literal path scratch (3, d, N)
+    unsigned long long* n_reject = nullptr;
+    size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
+};
+
+extern "C" int geosss_version(void) { return GEOSSS_VERSION; }
+extern "C" const char* geosss_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------ target creation
+extern "C" int geosss_target_create_vmf_mixture(int d, int K, const double* mu, const double* logw,
+                                                const double* log_i0, geosss_target_t* out) {
+    if (!out || !mu || d < 2 || K < 1) return fail(GEOSSS_E_INVALID, "vmf_mixture: need d >= 2, K >= 1, mu");
+    if (!logw && K != 1) return fail(GEOSSS_E_INVALID, "vmf_mixture: logw == NULL means a lone vMF (K == 1)");
+    auto* t = new (std::nothrow) geosss_target();
+    if (!t) return fail(GEOSSS_E_NOMEM, "out of host memory");
+    t->kind = TGT_VMF_MIX; t->d = d; t->K = K; t->single = logw ? 0 : 1;
+    std::vector<double> li(K), lw(K, 0.0);
+    for (int k = 0; k < K; ++k) {
+        if (log_i0) li[k] = log_i0[k];
+        else {
+            double s = 0;
+            for (int j = 0; j < d; ++j) s += mu[(size_t)k * d + j] * mu[(size_t)k * d + j];
+            double kap = std::sqrt(s);
+            // the reference uses scipy.special.i0, which overflows to inf for kappa >~ 713
+            li[k] = kap > 713.0 ? INFINITY : std::log(std::cyl_bessel_i(0.0, kap));
+        }
+        if (logw) lw[k] = logw[k];
+    }
+    t->h_mu.assign(mu, mu + (size_t)K * d);
+    t->h_const.resize(K);
+    for (int k = 0; k < K; ++k) t->h_const[k] = (-1.8378770664093453 - li[k]) + lw[k];
+    int rc = t->mu.upload(mu, (size_t)K * d);
+    if (!rc) rc = t->logw.upload(lw.data(), K);
+    if (!rc) rc = t->logi0.upload(li.data(), K);
+    if (rc) { t->release(); delete t; return rc; }
+    *out = t;
+    return 0;
+}
+
+extern "C" int geosss_target_create_bingham(int d, const double* A, const double* b, geosss_target_t* out) {
+    if (!out || !A || d < 2) return fail(GEOSSS_E_INVALID, "bingham: need d >= 2 and A");
+    bool diag = true;
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) {
+            double a = A[(size_t)i * d + j], at = A[(size_t)j * d + i];
+            // np.allclose(A, A.T) (geosss/distributions.py:68)
+            if (!(std::fabs(a - at) <= 1e-8 + 1e-5 * std::fabs(at))) return fail(GEOSSS_E_INVALID, "bingham: A must be symmetric");
+            if (i != j && a != 0.0) diag = false;
+        }
+    auto* t = new (std::nothrow) geosss_target();
+    if (!t) return fail(GEOSSS_E_NOMEM, "out of host memory");
+    t->kind = TGT_BINGHAM; t->d = d; t->has_b = b ? 1 : 0; t->diag = diag ? 1 : 0;
+    int rc = t->A.upload(A, (size_t)d * d);
+    if (!rc && b) rc = t->b.upload(b, d);
+    if (rc) { t->release(); delete t; return rc; }
+    *out = t;
+    return 0;
+}
+
+extern "C" int geosss_target_create_curved_vmf(int d, int n_knots, const double* knots, double kappa, geosss_target_t* out) {
+    if (!out || !knots || d < 2 || n_knots < 2) return fail(GEOSSS_E_INVALID, "curved_vmf: need d >= 2 and >= 2 knots");
+    auto* t = new (std::nothrow) geosss_target();
+    if (!t) return fail(GEOSSS_E_NOMEM, "out of host memory");
+    t->kind = TGT_CURVED_VMF; t->d = d; t->M = n_knots; t->kappa = kappa;
+    std::vector<double> ang(n_knots - 1), ca(n_knots - 1), sa(n_knots - 1);
+    for (int j = 0; j + 1 < n_knots; ++j) {
+        double dot = 0;
+        for (int i = 0; i < d; ++i) dot += knots[(size_t)j * d + i] * knots[(size_t)(j + 1) * d + i];
+        dot = dot < -1 ? -1 : (dot > 1 ? 1 : dot);
+        ang[j] = std::acos(dot);  // sphere.distance(a, b), spherical_curve.py:29
+        ca[j] = std::cos(ang[j]);
+        sa[j] = std::sin(ang[j]);
+    }
+    int rc = t->knots.upload(knots, (size_t)n_knots * d);
+    if (!rc) rc = t->ang.upload(ang.data(), ang.size());
+    if (!rc) rc = t->cosang.upload(ca.data(), ca.size());
+    if (!rc) rc = t->sinang.upload(sa.data(), sa.size());
+    if (rc) { t->release(); delete t; return rc; }
+    *out = t;
+    return 0;
+}
+
+extern "C" int geosss_target_create_cpd(int n_t, int n_s, const double* target, const double* w_t, const double* source,
+                                        const double* w_s, double sigma, double omega, double beta, int k, int outlier,
+                                        geosss_target_t* out) {
+    if (!out || !target || !source || n_t < 1 || n_s < 1) return fail(GEOSSS_E_INVALID, "cpd: need target and source clouds");
+    if (k > 0 && k < n_s && k > CPD_KMAX) return fail(GEOSSS_E_UNSUPPORTED, "cpd: k-nearest truncation supports k <= %d", CPD_KMAX);
+    if (!(sigma > 0)) return fail(GEOSSS_E_INVALID, "cpd: sigma must be positive");
+    auto* t = new (std::nothrow) geosss_target();
+    if (!t) return fail(GEOSSS_E_NOMEM, "out of host memory");
+    t->kind = TGT_CPD; t->d = 4; t->nt = n_t; t->ns = n_s; t->k = k; t->outlier = outlier ? 1 : 0;
+    t->sigma2 = sigma * sigma; t->beta = beta;
+    const double D = 3.0;
+    const double gauss = D / 2 * std::log(2 * M_PI * sigma * sigma);
+    if (outlier) {
+        // registration.py:205-215, 237-238
+        double vol = 0;
+        for (int a = 0; a < 3; ++a) {
+            double lo = target[a], hi = target[a];
+            for (int l = 1; l < n_t; ++l) { double v = target[(size_t)l * 3 + a]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+            vol += std::log(hi - lo);
+        }
+        t->log_outlier = std::log(omega + 1e-308) - vol;
+        t->log_const = std::log(1 - omega) - gauss;
+    } else {
+        t->log_outlier = -INFINITY;
+        t->log_const = -gauss;  // registration.py:116-118
+    }
+    std::vector<double> wt(n_t, 1.0), lws(n_s, 0.0);
+    if (w_t) wt.assign(w_t, w_t + n_t);
+    if (w_s) for (int i = 0; i < n_s; ++i) lws[i] = std::log(w_s[i]);
+    int rc = t->tgt.upload(target, (size_t)n_t * 3);
+    if (!rc) rc = t->src.upload(source, (size_t)n_s * 3);
+    if (!rc) rc = t->wt.upload(wt.data(), n_t);
+    if (!rc) rc = t->logws.upload(lws.data(), n_s);
+    if (rc) { t->release(); delete t; return rc; }
+    *out = t;
+    return 0;
+}
+
+extern "C" int geosss_target_dim(geosss_target_t t) { return t ? t->d : GEOSSS_E_INVALID; }
+
+extern "C" int geosss_target_destroy(geosss_target_t t) {
+    if (!t) return 0;
+    t->release();
+    delete t;
+    return 0;
+}
+
+// ------------------------------------------------------------------ log_prob
+template <typename T> static int logp_literal(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
+    const T* xi = static_cast<const T*>(x);
+    T* o = static_cast<T*>(out);
+    const unsigned grid = (unsigned)((N + LANE_BLOCK - 1) / LANE_BLOCK);
+    switch (t->kind) {
+        case TGT_VMF_MIX: k_logp_lane<T><<<grid, LANE_BLOCK, 0, st>>>(t->vmf<T>(), xi, o, N); break;
+        case TGT_BINGHAM: k_logp_lane<T><<<grid, LANE_BLOCK, 0, st>>>(t->bingham<T>(), xi, o, N); break;
+        case TGT_CURVED_VMF: k_logp_lane<T><<<grid, LANE_BLOCK, 0, st>>>(t->curved<T>(), xi, o, N); break;
+        case TGT_CPD: {
+            const size_t smem = (size_t)CPD_WARPS * 3 * t->ns * sizeof(T);
+            if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "cpd: source cloud too large for shared memory");
+            CU(cudaFuncSetAttribute(k_logp_cpd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_logp_cpd<T><<<(unsigned)((N + CPD_WARPS - 1) / CPD_WARPS), CPD_WARPS * 32, smem, st>>>(t->cpd<T>(), xi, o, N);
+            break;
+        }
+        default: return fail(GEOSSS_E_INVALID, "unknown target kind");
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int geosss_log_prob(geosss_target_t t, int dtype, int path, const void* x, void* out, int64_t N, void* stream) {
+    if (!t || !x || !out || N < 0) return fail(GEOSSS_E_INVALID, "log_prob: bad arguments");
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (path == GEOSSS_PATH_FAST) {
+        if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: the fast path is float32 only");
+        return fail(GEOSSS_E_UNSUPPORTED, "log_prob: no fast kernel for this target yet");
+    }
+    return dtype == GEOSSS_F64 ? logp_literal<double>(t, x, out, N, st) : logp_literal<float>(t, x, out, N, st);
+}
+
+// ------------------------------------------------------------------ samplers
+extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int path, int64_t N, uint64_t seed,
+                                     uint64_t chain_offset, geosss_sampler_t* out) {
+    if (!t || !out || N < 1) return fail(GEOSSS_E_INVALID, "sampler_create: bad arguments");
+    if (kind != GEOSSS_REJECT && kind != GEOSSS_SHRINK) return fail(GEOSSS_E_INVALID, "sampler_create: kind must be reject or shrink");
+    if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "sampler_create: dtype must be f32 or f64");
+    if (path == GEOSSS_PATH_FAST) {
+        if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the fast path is float32 only");
+        int rc = fast_supported(t->kind, t->d, t->K, t->single);
+        if (rc) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: no fast kernel for this target / shape");
+    } else if (path != GEOSSS_PATH_LITERAL) return fail(GEOSSS_E_INVALID, "sampler_create: unknown path");
+    auto* s = new (std::nothrow) geosss_sampler();
+    if (!s) return fail(GEOSSS_E_NOMEM, "out of host memory");
+    s->t = t; s->kind = kind; s->dtype = dtype; s->path = path; s->N = N; s->seed = seed; s->chain0 = chain_offset;
+    const size_t es = s->esize();
+    cudaError_t e = cudaMalloc(&s->state, (size_t)N * t->d * es);
+    if (e == cudaSuccess) e = cudaMalloc(&s->n_reject, (size_t)N * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(s->n_reject, 0, (size_t)N * sizeof(unsigned long long));
+    if (e == cudaSuccess && path == GEOSSS_PATH_LITERAL && t->kind != TGT_CPD) e = cudaMalloc(&s->ws, (size_t)3 * N * t->d * es);
+    if (e != cudaSuccess) {
+        geosss_sampler_destroy(s);
+        return fail(e == cudaErrorMemoryAllocation ? GEOSSS_E_NOMEM : GEOSSS_E_CUDA, "sampler_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
+    if (!s) return 0;
+    if (s->state) cudaFree(s->state);
+    if (s->ws) cudaFree(s->ws);
+    if (s->n_reject) cudaFree(s->n_reject);
+    delete s;
+    return 0;
+}
+
+extern "C" int geosss_sampler_set_state(geosss_sampler_t s, const void* x, void* stream) {
+    if (!s || !x) return fail(GEOSSS_E_INVALID, "set_state: bad arguments");
+    CU(cudaMemcpyAsync(s->state, x, (size_t)s->N * s->t->d * s->esize(), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+extern "C" int geosss_sampler_get_state(geosss_sampler_t s, void* x, uint64_t* n_reject, void* stream) {
+    if (!s) return fail(GEOSSS_E_INVALID, "get_state: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x) CU(cudaMemcpyAsync(x, s->state, (size_t)s->N * s->t->d * s->esize(), cudaMemcpyDeviceToDevice, st));
+    if (n_reject) CU(cudaMemcpyAsync(n_reject, s->n_reject, (size_t)s->N * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int64_t geosss_sampler_steps_done(geosss_sampler_t s) { return s ? (int64_t)s->step : GEOSSS_E_INVALID; }
+
+template <typename T, int KIND, bool TAPE> static int launch_literal(geosss_sampler* s, const RunArgs& a, cudaStream_t st) {
+    geosss_target* t = s->t;
+    const unsigned grid = (unsigned)((a.N + LANE_BLOCK - 1) / LANE_BLOCK);
+    switch (t->kind) {
+        case TGT_VMF_MIX: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->vmf<T>(), a); break;
+        case TGT_BINGHAM: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->bingham<T>(), a); break;
+        case TGT_CURVED_VMF: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->curved<T>(), a); break;
+        case TGT_CPD: {
+            const size_t smem = (size_t)CPD_WARPS * 3 * t->ns * sizeof(T);
+            if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "cpd: source cloud too large for shared memory");
+            CU(cudaFuncSetAttribute(k_sampler_cpd<T, KIND, TAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sampler_cpd<T, KIND, TAPE><<<(unsigned)((a.N + CPD_WARPS - 1) / CPD_WARPS), CPD_WARPS * 32, smem, st>>>(t->cpd<T>(), a);
+            break;
+        }
+        default: return fail(GEOSSS_E_INVALID, "unknown target kind");
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <bool TAPE> static int dispatch_literal(geosss_sampler* s, const RunArgs& a, cudaStream_t st) {
+    if (s->dtype == GEOSSS_F64)
+        return s->kind == GEOSSS_SHRINK ? launch_literal<double, SHRINK, TAPE>(s, a, st) : launch_literal<double, REJECT, TAPE>(s, a, st);
+    return s->kind == GEOSSS_SHRINK ? launch_literal<float, SHRINK, TAPE>(s, a, st) : launch_literal<float, REJECT, TAPE>(s, a, st);
+}
+
+static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
+    RunArgs a{};
+    a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
+    a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
+    return a;
+}
+
+extern "C" int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* samples_out, void* logp_out,
+                                  uint32_t* nrej_out, void* stream) {
+    if (!s || n_steps < 0 || thin < 1) return fail(GEOSSS_E_INVALID, "run: need n_steps >= 0 and thin >= 1");
+    if (n_steps == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RunArgs a = base_args(s, n_steps, thin);
+    a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
+    int rc = s->path == GEOSSS_PATH_FAST ? launch_fast(s->t->kind, s->kind, s->t->d, s->t->K, s->t->h_mu.data(), s->t->h_const.data(), a, st)
+                                         : dispatch_literal<false>(s, a, st);
+    if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));
+    if (rc) return rc;
+    s->step += (uint64_t)n_steps;
+    return 0;
+}
+
+extern "C" int geosss_sampler_run_tape(geosss_sampler_t s, int64_t n_steps, const double* tape, const int64_t* tape_offsets,
+                                       void* samples_out, uint32_t* nrej_out, int32_t* status, void* stream) {
+    if (!s || n_steps < 0 || !tape || !tape_offsets) return fail(GEOSSS_E_INVALID, "run_tape: bad arguments");
+    if (s->path != GEOSSS_PATH_LITERAL) return fail(GEOSSS_E_UNSUPPORTED, "run_tape: tape mode runs on the literal path");
+    if (n_steps == 0) return 0;
+    RunArgs a = base_args(s, n_steps, 1);
+    a.samples = samples_out; a.nrej = nrej_out; a.tape = tape; a.tape_off = tape_offsets; a.status = status;
+    int rc = dispatch_literal<true>(s, a, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    s->step += (uint64_t)n_steps;
+    return 0;
+}
+
+// ------------------------------------------------------------------ host-buffer entry points
+extern "C" int geosss_sampler_set_state_host(geosss_sampler_t s, const double* x_host) {
+    if (!s || !x_host) return fail(GEOSSS_E_INVALID, "set_state_host: bad arguments");
+    const size_t n = (size_t)s->N * s->t->d;
+    if (s->dtype == GEOSSS_F64) {
+        CU(cudaMemcpy(s->state, x_host, n * 8, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> f(n);
+        for (size_t i = 0; i < n; ++i) f[i] = (float)x_host[i];
+        CU(cudaMemcpy(s->state, f.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int geosss_sampler_get_state_host(geosss_sampler_t s, double* x_host, uint64_t* n_reject_host) {
+    if (!s) return fail(GEOSSS_E_INVALID, "get_state_host: bad arguments");
+    const size_t n = (size_t)s->N * s->t->d;
+    if (x_host) {
+        if (s->dtype == GEOSSS_F64) {
+            CU(cudaMemcpy(x_host, s->state, n * 8, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> f(n);
+            CU(cudaMemcpy(f.data(), s->state, n * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) x_host[i] = (double)f[i];
+        }
+    }
+    if (n_reject_host) CU(cudaMemcpy(n_reject_host, s->n_reject, (size_t)s->N * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+namespace {
+struct HostPipe {
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t filled[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    void* buf[2] = {nullptr, nullptr};
+    ~HostPipe() {
+        for (int i = 0; i < 2; ++i) {
+            if (filled[i]) cudaEventDestroy(filled[i]);
+            if (drained[i]) cudaEventDestroy(drained[i]);
+            if (buf[i]) cudaFree(buf[i]);
+        }
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+}  // namespace
+
+// n_skip transitions without output, then n_keep transitions whose states stream to the host:
+// chunk i is sampled into buf[i & 1] on one stream while chunk i-1 drains over PCIe on another.
+extern "C" int geosss_sampler_run_host(geosss_sampler_t s, int64_t n_skip, int64_t n_keep, void* samples_host) {
+    if (!s || n_skip < 0 || n_keep < 0 || (n_keep > 0 && !samples_host)) return fail(GEOSSS_E_INVALID, "run_host: bad arguments");
+    HostPipe h;
+    CU(cudaDeviceSynchronize());  // earlier work on other streams (set_state, run) must have landed
+    CU(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    int rc = 0;
+    if (n_skip > 0) {
+        rc = geosss_sampler_run(s, n_skip, 1, nullptr, nullptr, nullptr, h.compute);
+        if (rc) return rc;
+    }
+    if (n_keep > 0) {
+        const size_t row = (size_t)s->N * s->t->d * s->esize();  // one retained state of every chain
+        int64_t chunk = (int64_t)((size_t)(64u << 20) / row);
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_keep) chunk = n_keep;
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaMalloc(&h.buf[i], (size_t)chunk * row));
+            CU(cudaEventCreateWithFlags(&h.filled[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h.drained[i], cudaEventDisableTiming));
+        }
+        unsigned char* out = static_cast<unsigned char*>(samples_host);
+        int64_t done = 0;
+        for (int i = 0; done < n_keep; ++i) {
+            const int b = i & 1;
+            const int64_t n = n_keep - done < chunk ? n_keep - done : chunk;
+            if (i >= 2) CU(cudaStreamWaitEvent(h.compute, h.drained[b], 0));
+            rc = geosss_sampler_run(s, n, 1, h.buf[b], nullptr, nullptr, h.compute);
+            if (rc) return rc;
+            CU(cudaEventRecord(h.filled[b], h.compute));
+            CU(cudaStreamWaitEvent(h.copy, h.filled[b], 0));
+            CU(cudaMemcpyAsync(out + (size_t)done * row, h.buf[b], (size_t)n * row, cudaMemcpyDeviceToHost, h.copy));
+            CU(cudaEventRecord(h.drained[b], h.copy));
+            done += n;
+        }
+    }
+    CU(cudaStreamSynchronize(h.compute));
+    CU(cudaStreamSynchronize(h.copy));
+    return 0;
+}
+
+extern "C" int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t N, const double* x0_host,
+                                  uint64_t seed, uint64_t chain_offset, int64_t n_samples, int64_t burnin,
+                                  void* samples_host, uint64_t* n_reject_host) {
+    if (!t || !x0_host || !samples_host || N < 1) return fail(GEOSSS_E_INVALID, "sample_host: bad arguments");
+    if (n_samples < 1) return fail(GEOSSS_E_INVALID, "sample_host: n_samples must be positive");  // mcmc.py:62
+    if (burnin < 0) return fail(GEOSSS_E_INVALID, "sample_host: burnin must be >= 0");            // mcmc.py:18
+    geosss_sampler_t s = nullptr;
+    int rc = geosss_sampler_create(t, kind, dtype, path, N, seed, chain_offset, &s);
+    if (rc) return rc;
+    rc = geosss_sampler_set_state_host(s, x0_host);
+    // the first retained state is the initial state itself when there is no burn-in (mcmc.py:67-77)
+    unsigned char* out = static_cast<unsigned char*>(samples_host);
+    int64_t n_skip = burnin - 1, n_keep = n_samples;
+    if (!rc && burnin == 0) {
+        const size_t n = (size_t)N * t->d;
+        if (dtype == GEOSSS_F64) std::memcpy(out, x0_host, n * 8);
+        else { float* f = reinterpret_cast<float*>(out); for (size_t i = 0; i < n; ++i) f[i] = (float)x0_host[i]; }
+        out += n * s->esize();
+        n_skip = 0;
+        n_keep = n_samples - 1;
+    }
+    if (!rc) rc = geosss_sampler_run_host(s, n_skip, n_keep, out);
+    if (!rc && n_reject_host) rc = geosss_sampler_get_state_host(s, nullptr, n_reject_host);
+    geosss_sampler_destroy(s);
+    return rc;
+}

@@ -1,0 +1,244 @@
+// Float32 throughput kernels ("fast path") for the vMF-mixture target.
+//
+// Same Markov kernel as geosss/mcmc.py:357-401, restructured for the GPU (SURVEY.md section 7,
+// "algebraic shortcuts along the great circle"): for y(theta) = cos(theta) x + sin(theta) u the
+// component scores mu_k . y are linear in (cos, sin), so one transition computes
+// a_k = mu_k.x and b_k = mu_k.u once (2Kd FMAs) and every proposal costs O(K):
+//     accept  <=>  log p(y) > log p(x) + log U  <=>  sum_k 2^(c A_k + s B_k + G_k) > 1
+// with A,B scaled by log2(e) and G_k = C_k - (log2 p(x) + log2 U).  Comparing the SUM with 1
+// never forms "log p(x) + log U", so the level cannot round onto log p(x) (the bracket-collapse
+// hazard of SURVEY.md section 7), and no log is needed per proposal.
+//
+// Deliberate deviations from the literal path, all distribution-preserving: x is renormalised
+// at every transition (the reference lets |x| drift), the bracket is kept in half-turns so
+// sincospif needs no range reduction, log p(x) is not re-evaluated from scratch but from the
+// fresh a_k, and a proposal cap keeps a chain at x instead of looping for ever.
+//
+// One lane per chain; state, direction and the 2K scores live in registers (D, K are template
+// parameters, D padded to a multiple of 4 with zeros); mixture parameters are read from the
+// kernel-parameter constant bank.  Draws come from the per-chain Philox stream of philox.cuh.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels_literal.cuh"  // RunArgs
+#include "philox.cuh"
+
+namespace geosss {
+
+constexpr int FAST_MAX_K = 8;
+constexpr int FAST_MAX_D = 16;
+constexpr int FAST_BLOCK = 64;
+constexpr int FAST_SHRINK_CAP = 200;  // a shrink bracket is far below fp32 resolution long before this
+
+struct VmfFastParams {
+    float mu[FAST_MAX_K * FAST_MAX_D];  // (K, D) zero padded, times log2(e)
+    float c[FAST_MAX_K];                // (log w_k - log 2pi - log i0(kappa_k)) * log2(e)
+    int d;                              // true dimension (<= D)
+};
+
+__device__ __forceinline__ float fast_ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ float fast_sqrt(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// Box-Muller on the MUFU pipe: |error| ~ 1e-6 per normal, irrelevant for a proposal direction.
+__device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float& z0, float& z1) {
+    const float u1 = u01(wa, 0.f), u2 = u01(wb, 0.f);
+    const float r = fast_sqrt(fmaxf(-1.3862943611198906f * fast_lg2(u1), 0.f));  // sqrt(-2 ln u1)
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+template <int K, int D, int KIND>
+__global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__ VmfFastParams P, RunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.N) return;
+    const int d = P.d;
+    constexpr float LN2 = 0.6931471805599453f;
+
+    float x[D];
+    float* st = static_cast<float*>(a.state) + c * d;
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = j < d ? st[j] : 0.0f;
+
+    PhiloxDraws<float> dr;
+    dr.init(a.seed, a.chain0 + (uint64_t)c, d);
+    unsigned long long rej_total = a.n_reject[c];
+    unsigned int rej_window = 0;
+    float* samples = static_cast<float*>(a.samples);
+    float* lpo = static_cast<float*>(a.logp);
+    int64_t since_keep = 0, kept = 0;
+
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+        dr.begin_step(a.step0 + (uint64_t)t);
+
+        // pole: x <- x / |x|
+        float xx = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) xx = fmaf(x[j], x[j], xx);
+        const float inx = rsqrtf(xx);
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] *= inx;
+
+        // direction: u = unit(z - (z.x) x)
+        float u[D];
+#pragma unroll
+        for (int b = 0; b < D / 4; ++b) {
+            U4 r = dr.block(b);
+            box_muller_fast(r.x, r.y, u[4 * b], u[4 * b + 1]);
+            box_muller_fast(r.z, r.w, u[4 * b + 2], u[4 * b + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) if (j >= d) u[j] = 0.f;
+        float zx = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) zx = fmaf(u[j], x[j], zx);
+        float pp = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) { u[j] = fmaf(-zx, x[j], u[j]); pp = fmaf(u[j], u[j], pp); }
+        const float inp = rsqrtf(pp);
+#pragma unroll
+        for (int j = 0; j < D; ++j) u[j] *= inp;
+
+        // scores along the great circle (log2 units)
+        float A[K], B[K], G[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) { sa = fmaf(P.mu[k * D + j], x[j], sa); sb = fmaf(P.mu[k * D + j], u[j], sb); }
+            A[k] = sa; B[k] = sb;
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) m = fmaxf(m, A[k] + P.c[k]);
+        float s0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - m);
+        const float lp2 = m + fast_lg2(s0);
+        const float level2 = lp2 + fast_lg2(dr.level_uniform());
+#pragma unroll
+        for (int k = 0; k < K; ++k) G[k] = P.c[k] - level2;
+
+        // bracket in half-turns: theta = pi * tt
+        float lo, hi;
+        if (KIND == SHRINK) { hi = 2.0f * dr.bracket_uniform(); lo = hi - 2.0f; }
+        else { lo = 0.f; hi = 2.0f; }
+
+        const int cap = (lp2 > -INFINITY) ? (KIND == SHRINK ? FAST_SHRINK_CAP : MAX_PROPOSALS) : 0;
+        float sn = 0.f, cs = 1.f, S = 0.f;
+        int r = 0;
+        bool moved = false;
+        for (; r < cap; ++r) {
+            const float tt = fmaf(hi - lo, dr.proposal_uniform(r), lo);
+            sincospif(tt, &sn, &cs);
+            S = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) S += fast_ex2(fmaf(cs, A[k], fmaf(sn, B[k], G[k])));
+            if (S > 1.0f) { moved = true; break; }
+            if (KIND == SHRINK) { if (tt < 0.f) lo = tt; else hi = tt; }
+        }
+        if (moved) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+        }
+        rej_total += (unsigned)r;
+        rej_window += (unsigned)r;
+
+        if (++since_keep == a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (samples) {
+                float* o = samples + (k * a.N + c) * d;
+#pragma unroll
+                for (int j = 0; j < D; ++j) if (j < d) o[j] = x[j];
+            }
+            if (lpo) {
+                // log p of the kept state, natural log; level2 + log2(S) is exact for the accepted point
+                float l2 = moved ? level2 + fast_lg2(S) : lp2;
+                if (!(l2 < INFINITY)) {  // S overflowed: evaluate directly
+                    float mm = -INFINITY, e[K];
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) { e[kk] = fmaf(cs, A[kk], sn * B[kk]) + P.c[kk]; mm = fmaxf(mm, e[kk]); }
+                    float ss = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < K; ++kk) ss += fast_ex2(e[kk] - mm);
+                    l2 = mm + fast_lg2(ss);
+                }
+                lpo[k * a.N + c] = l2 * LN2;
+            }
+            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            rej_window = 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) if (j < d) st[j] = x[j];
+    a.n_reject[c] = rej_total;
+}
+
+// ------------------------------------------------------------------ host-side dispatch
+inline int fast_supported(int target_kind, int d, int K, int single) {
+    (void)single;
+    if (target_kind != TGT_VMF_MIX) return -1;
+    if (d > FAST_MAX_D || K > FAST_MAX_K || K < 1) return -1;
+    return 0;
+}
+
+template <int K, int D> static int launch_vmf_fast_kd(int kind, const VmfFastParams& P, const RunArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.N + FAST_BLOCK - 1) / FAST_BLOCK);
+    if (kind == SHRINK) k_vmf_fast<K, D, SHRINK><<<grid, FAST_BLOCK, 0, st>>>(P, a);
+    else k_vmf_fast<K, D, REJECT><<<grid, FAST_BLOCK, 0, st>>>(P, a);
+    return (int)cudaGetLastError();
+}
+
+template <int K> static int launch_vmf_fast_k(int kind, int Dp, const VmfFastParams& P, const RunArgs& a, cudaStream_t st) {
+    switch (Dp) {
+        case 4: return launch_vmf_fast_kd<K, 4>(kind, P, a, st);
+        case 8: return launch_vmf_fast_kd<K, 8>(kind, P, a, st);
+        case 12: return launch_vmf_fast_kd<K, 12>(kind, P, a, st);
+        default: return launch_vmf_fast_kd<K, 16>(kind, P, a, st);
+    }
+}
+
+// returns 0, a negative GEOSSS_E_* code, or a positive cudaError_t
+inline int launch_fast(int target_kind, int kind, int d, int K, const double* mu, const double* consts, const RunArgs& a, cudaStream_t st) {
+    if (fast_supported(target_kind, d, K, 0)) return -3;
+    const int Dp = (d + 3) / 4 * 4;
+    VmfFastParams P;
+    const double L2E = 1.4426950408889634;
+    for (int k = 0; k < FAST_MAX_K; ++k) {
+        for (int j = 0; j < FAST_MAX_D; ++j) P.mu[k * FAST_MAX_D + j] = 0.f;
+        P.c[k] = 0.f;
+    }
+    for (int k = 0; k < K; ++k) {
+        for (int j = 0; j < d; ++j) P.mu[k * Dp + j] = (float)(mu[(size_t)k * d + j] * L2E);
+        P.c[k] = (float)(consts[k] * L2E);
+    }
+    P.d = d;
+    switch (K) {
+        case 1: return launch_vmf_fast_k<1>(kind, Dp, P, a, st);
+        case 2: return launch_vmf_fast_k<2>(kind, Dp, P, a, st);
+        case 3: return launch_vmf_fast_k<3>(kind, Dp, P, a, st);
+        case 4: return launch_vmf_fast_k<4>(kind, Dp, P, a, st);
+        case 5: return launch_vmf_fast_k<5>(kind, Dp, P, a, st);
+        case 6: return launch_vmf_fast_k<6>(kind, Dp, P, a, st);
+        case 7: return launch_vmf_fast_k<7>(kind, Dp, P, a, st);
+        default: return launch_vmf_fast_k<8>(kind, Dp, P, a, st);
+    }
+}
+
+}  // namespace geosss

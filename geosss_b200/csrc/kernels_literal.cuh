@@ -1,0 +1,197 @@
+// Kernels of the literal path: batched log_prob and lane-per-chain / warp-per-chain samplers
+// that follow the reference operation for operation, in float64 (parity) or float32.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+#include "targets.cuh"
+#include "transition.cuh"
+
+namespace geosss {
+
+constexpr int LANE_BLOCK = 128;  // threads per block, lane-per-chain kernels
+constexpr int CPD_WARPS = 4;     // warps (= chains or points) per block, CPD kernels
+
+// ------------------------------------------------------------------ batched log_prob
+// x: (N, d) row-major.  One lane per row; parameters are read through L1 as warp broadcasts.
+template <typename T, class P>
+__global__ void __launch_bounds__(LANE_BLOCK) k_logp_lane(P p, const T* __restrict__ x, T* __restrict__ out, int64_t N) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    SVec<const T> v{x + i * p.d, 1};
+    out[i] = p.logp(v);
+}
+
+// Warp-cooperative CPD log-likelihood: every lane passes the same quaternion and receives the
+// same value.  moved: per-warp shared scratch, 3*ns elements.
+template <typename T> struct CpdWarpLogP {
+    CpdP<T> p;
+    T* moved;
+    template <class Vec> __device__ __forceinline__ T operator()(Vec q) const {
+        const int lane = threadIdx.x & 31;
+        T R[9];
+        quat_to_matrix<T>(q[0], q[1], q[2], q[3], R);
+        __syncwarp();
+        cpd_move_source(p, R, moved, lane, 32);
+        __syncwarp();
+        double acc = 0.0;
+        for (int l = lane; l < p.nt; l += 32) acc += (double)cpd_row(p, moved, l);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = __shfl_sync(0xffffffffu, acc, 0);
+        return p.beta * (T)acc;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(CPD_WARPS * 32) k_logp_cpd(CpdP<T> p, const T* __restrict__ q, T* __restrict__ out, int64_t N) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    T* moved = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 3 * p.ns;
+    int64_t i = (int64_t)blockIdx.x * CPD_WARPS + warp;
+    if (i >= N) return;  // whole warp leaves together
+    CpdWarpLogP<T> f{p, moved};
+    SVec<const T> v{q + i * 4, 1};
+    T val = f(v);
+    if ((threadIdx.x & 31) == 0) out[i] = val;
+}
+
+// ------------------------------------------------------------------ sampler drivers
+struct RunArgs {
+    int64_t N;            // chains owned by this sampler
+    int64_t n_steps;      // transitions to run
+    int64_t thin;         // keep every thin-th state
+    uint64_t seed;        // Philox key
+    uint64_t chain0;      // global id of chain 0
+    uint64_t step0;       // transitions already done
+    const double* tape;   // tape mode: flat draws ...
+    const int64_t* tape_off;  // ... and (N+1) offsets into it
+    void* state;          // (N, d) row-major, in/out
+    void* ws;             // (3, d, N) column-major scratch
+    void* samples;        // (n_keep, N, d) or null
+    void* logp;           // (n_keep, N) or null
+    uint32_t* nrej;       // (n_keep, N) rejections of each kept transition (thin == 1) or null
+    unsigned long long* n_reject;  // (N) running totals
+    int* status;          // (N) tape mode: 0 ok, 1 tape exhausted; may be null
+};
+
+template <typename T, int KIND, bool TAPE> struct DrawsOf;
+template <typename T, int KIND> struct DrawsOf<T, KIND, false> {
+    using type = PhiloxDraws<T>;
+    static __device__ __forceinline__ void init(type& dr, const RunArgs& a, int64_t c, int d) { dr.init(a.seed, a.chain0 + (uint64_t)c, d); }
+};
+template <typename T, int KIND> struct DrawsOf<T, KIND, true> {
+    using type = TapeDraws<T>;
+    static __device__ __forceinline__ void init(type& dr, const RunArgs& a, int64_t c, int) { dr.init(a.tape, a.tape_off[c], a.tape_off[c + 1]); }
+};
+
+template <class P> struct LaneLogP {
+    P p;
+    template <class Vec> __device__ __forceinline__ auto operator()(Vec v) const { return p.logp(v); }
+};
+
+// lane-per-chain; all n_steps transitions of a chain run inside one launch
+template <typename T, int KIND, bool TAPE, class P>
+__global__ void __launch_bounds__(LANE_BLOCK) k_sampler_lane(P p, RunArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.N) return;
+    const int d = p.d;
+    T* ws = static_cast<T*>(a.ws);
+    SVec<T> x{ws + c, a.N}, u{ws + (int64_t)d * a.N + c, a.N}, y{ws + 2 * (int64_t)d * a.N + c, a.N};
+    T* st = static_cast<T*>(a.state) + c * d;
+    for (int j = 0; j < d; ++j) x[j] = st[j];
+
+    using D = DrawsOf<T, KIND, TAPE>;
+    typename D::type dr;
+    D::init(dr, a, c, d);
+    LaneLogP<P> f{p};
+    unsigned long long rej_total = a.n_reject[c];
+    unsigned int rej_window = 0;
+    T* samples = static_cast<T*>(a.samples);
+    T* lpo = static_cast<T*>(a.logp);
+    bool good = true;
+    int64_t since_keep = 0, kept = 0;
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+        dr.begin_step(a.step0 + (uint64_t)t);
+        T lp;
+        int r = transition_literal<T, KIND>(d, x, u, y, dr, f, &lp);
+        if (!dr.ok()) { good = false; break; }
+        rej_total += (unsigned)r;
+        rej_window += (unsigned)r;
+        if (++since_keep == a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (samples) {
+                T* o = samples + (k * a.N + c) * d;
+                for (int j = 0; j < d; ++j) o[j] = x[j];
+            }
+            if (lpo) lpo[k * a.N + c] = lp;
+            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            rej_window = 0;
+        }
+    }
+    for (int j = 0; j < d; ++j) st[j] = x[j];
+    a.n_reject[c] = rej_total;
+    if (a.status) a.status[c] = good ? 0 : 1;
+}
+
+// warp-per-chain CPD sampler: all lanes carry the same 4-vector state and the same draws, the
+// log-likelihood is evaluated cooperatively (target rows over lanes).
+template <typename T> struct Reg4 {
+    T* v;
+    __device__ __forceinline__ T& operator[](int j) const { return v[j]; }
+};
+
+template <typename T, int KIND, bool TAPE>
+__global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd(CpdP<T> p, RunArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* moved = reinterpret_cast<T*>(smem_raw) + (size_t)warp * 3 * p.ns;
+    const int64_t c = (int64_t)blockIdx.x * CPD_WARPS + warp;
+    if (c >= a.N) return;
+    T xs[4], us[4], ys[4];
+    Reg4<T> x{xs}, u{us}, y{ys};
+    T* st = static_cast<T*>(a.state) + c * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = st[j];
+
+    using D = DrawsOf<T, KIND, TAPE>;
+    typename D::type dr;
+    D::init(dr, a, c, 4);
+    CpdWarpLogP<T> f{p, moved};
+    unsigned long long rej_total = a.n_reject[c];
+    unsigned int rej_window = 0;
+    T* samples = static_cast<T*>(a.samples);
+    T* lpo = static_cast<T*>(a.logp);
+    bool good = true;
+    int64_t since_keep = 0, kept = 0;
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+        dr.begin_step(a.step0 + (uint64_t)t);
+        T lp;
+        int r = transition_literal<T, KIND>(4, x, u, y, dr, f, &lp);
+        if (!dr.ok()) { good = false; break; }
+        rej_total += (unsigned)r;
+        rej_window += (unsigned)r;
+        if (++since_keep == a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (lane == 0) {
+                if (samples) {
+                    T* o = samples + (k * a.N + c) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = xs[j];
+                }
+                if (lpo) lpo[k * a.N + c] = lp;
+                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            }
+            rej_window = 0;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st[j] = xs[j];
+        a.n_reject[c] = rej_total;
+        if (a.status) a.status[c] = good ? 0 : 1;
+    }
+}
+
+}  // namespace geosss

@@ -1,0 +1,206 @@
+// Target log-densities, "literal" form: same operations and operation order as the reference
+// (float64 gives <= 1e-12 relative agreement, the float32 instantiation is the plain fp32
+// version of the same code).  One chain's point is read through a strided view (SVec) so the
+// same functions serve the batched log_prob kernels and the lane-per-chain samplers.
+//
+//   VmfMixP   geosss/distributions.py:156-157 (component), :218-221 (mixture + scipy logsumexp)
+//   BinghamP  geosss/distributions.py:78-86, Fisher term :113-114
+//   CurvedP   geosss/distributions.py:272-275 -> spherical_curve.py:95-102 -> :10-32
+//   CpdP      geosss/registration.py:47-53, :101-109, :211-259 (+ GMM parent :111-119)
+#pragma once
+#include "common.cuh"
+
+namespace geosss {
+
+// scipy.special.logsumexp (>= 1.15) separates the maximal elements: with m maxima and
+// s = sum over the others of exp(a - a_max),  out = log1p(s / m) + log(m) + a_max.
+template <typename T> GEOSSS_HD T lse_finish(T a_max, T s_others, int n_max) {
+    if (!(a_max > Const<T>::neg_inf())) return a_max;  // all -inf (or NaN) stays what it is
+    if (a_max == INFINITY) return a_max;
+    T m = (T)n_max;
+    T s = (s_others == T(0)) ? s_others : s_others / m;
+    return m_log1p(s) + m_log(m) + a_max;
+}
+
+// ------------------------------------------------------------------ vMF mixture
+template <typename T> struct VmfMixP {
+    const T* mu;     // (K, d) row-major
+    const T* logw;   // (K)  log of the normalised weights
+    const T* logi0;  // (K)  log(i0(|mu_k|)), +inf when i0 overflows, as in the reference
+    int K, d, single;
+
+    template <class Vec> GEOSSS_HD T comp(int k, Vec v) const {
+        T dot = 0;
+        const T* m = mu + (int64_t)k * d;
+        for (int j = 0; j < d; ++j) dot += v[j] * m[j];
+        return (dot - Const<T>::log_two_pi()) - logi0[k];
+    }
+    template <class Vec> GEOSSS_HD T logp(Vec v) const {
+        if (single) return comp(0, v);
+        T a_max = Const<T>::neg_inf();
+        int n_max = 0;
+        for (int k = 0; k < K; ++k) {
+            T a = comp(k, v) + logw[k];
+            if (a > a_max) { a_max = a; n_max = 1; }
+            else if (a == a_max) ++n_max;
+            else if (a != a) return a;  // NaN propagates
+        }
+        if (n_max == 0) n_max = 1;
+        T s = 0;
+        if (a_max > Const<T>::neg_inf() && a_max < INFINITY)
+            for (int k = 0; k < K; ++k) {
+                T a = comp(k, v) + logw[k];
+                if (a != a_max) s += m_exp(a - a_max);
+            }
+        return lse_finish(a_max, s, n_max);
+    }
+};
+
+// ------------------------------------------------------------------ Bingham (+ Fisher term)
+template <typename T> struct BinghamP {
+    const T* A;  // (d, d) row-major, symmetric
+    const T* b;  // (d) or nullptr
+    int d;
+
+    template <class Vec> GEOSSS_HD T logp(Vec v) const {
+        T tot = 0;
+        for (int j = 0; j < d; ++j) {
+            T col = 0;
+            for (int i = 0; i < d; ++i) col += v[i] * A[(int64_t)i * d + j];  // (x @ A)_j
+            tot += col * v[j];
+        }
+        if (b) {
+            T lin = 0;
+            for (int j = 0; j < d; ++j) lin += v[j] * b[j];
+            tot += lin;
+        }
+        return tot;
+    }
+};
+
+// ------------------------------------------------------------------ curved vMF
+// x . y_seg depends on x only through G = knots @ x; per segment
+//   t = clip(atan2(G_b - G_a cos(ang), G_a sin(ang)), 0, ang)
+//   x.y = (sin(ang - t) G_a + sin(t) G_b) / (sin(ang) + 1e-10)
+// and the segment with the smallest arccos(clip(x.y)) wins, first index on ties.
+template <typename T> struct CurvedP {
+    const T* knots;   // (M, d)
+    const T* ang;     // (M-1) arccos(clip(a.b))
+    const T* cosang;  // (M-1)
+    const T* sinang;  // (M-1)
+    T kappa;
+    int M, d;
+
+    template <class Vec> GEOSSS_HD T knot_dot(int m, Vec v) const {
+        T g = 0;
+        const T* kn = knots + (int64_t)m * d;
+        for (int j = 0; j < d; ++j) g += kn[j] * v[j];
+        return g;
+    }
+    GEOSSS_HD void segment(int j, T ga, T gb, T& dot, T& dist) const {
+        T t = m_atan2(gb - ga * cosang[j], ga * sinang[j]);
+        t = m_clip(t, T(0), ang[j]);
+        dot = (m_sin(ang[j] - t) * ga + m_sin(t) * gb) / (sinang[j] + T(1e-10));
+        dist = m_acos(m_clip(dot, T(-1), T(1)));
+    }
+    template <class Vec> GEOSSS_HD T logp(Vec v) const {
+        T ga = knot_dot(0, v);
+        T best_dot = 0, best_dist = 0;
+        for (int j = 0; j + 1 < M; ++j) {
+            T gb = knot_dot(j + 1, v);
+            T dot, dist;
+            segment(j, ga, gb, dot, dist);
+            if (j == 0 || dist < best_dist) { best_dist = dist; best_dot = dot; }
+            ga = gb;
+        }
+        return kappa * best_dot;
+    }
+};
+
+// ------------------------------------------------------------------ CPD registration on S^3
+constexpr int CPD_KMAX = 64;  // largest k of the k-nearest-neighbour truncation
+
+template <typename T> struct CpdP {
+    const T* tgt;    // (nt, 3)
+    const T* wt;     // (nt)
+    const T* src;    // (ns, 3)
+    const T* logws;  // (ns) log source weights
+    T sigma2, log_const, log_outlier, beta;
+    int nt, ns, k, outlier;  // k <= 0 or k >= ns: all source points; outlier 0: GMM parent
+};
+
+// scipy Rotation.from_quat(q).as_matrix(): scalar-last, q normalised first (pointcloud.py:115)
+template <typename T> GEOSSS_HD void quat_to_matrix(T qx, T qy, T qz, T qw, T R[9]) {
+    T n = m_sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    T x = qx / n, y = qy / n, z = qz / n, w = qw / n;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// moved_k = R s_k  (positions @ R.T, pointcloud.py:258-262), k = first, first+step, ...
+template <typename T> GEOSSS_HD void cpd_move_source(const CpdP<T>& p, const T R[9], T* moved, int first, int step) {
+    for (int k = first; k < p.ns; k += step) {
+        T s0 = p.src[3 * k], s1 = p.src[3 * k + 1], s2 = p.src[3 * k + 2];
+        moved[3 * k]     = s0 * R[0] + s1 * R[1] + s2 * R[2];
+        moved[3 * k + 1] = s0 * R[3] + s1 * R[4] + s2 * R[5];
+        moved[3 * k + 2] = s0 * R[6] + s1 * R[7] + s2 * R[8];
+    }
+}
+
+template <typename T> GEOSSS_HD T cpd_term(const CpdP<T>& p, T d2, T lw) {
+    T log_phi = (T(-0.5) * d2) / p.sigma2;
+    return p.outlier ? (lw + log_phi) + p.log_const : (log_phi + p.log_const) + lw;
+}
+
+// log-likelihood of target row l given the moved source cloud, times the row weight
+template <typename T> GEOSSS_HD T cpd_row(const CpdP<T>& p, const T* moved, int l) {
+    const T t0 = p.tgt[3 * l], t1 = p.tgt[3 * l + 1], t2 = p.tgt[3 * l + 2];
+    const bool dense = p.k <= 0 || p.k >= p.ns;
+    T a_max = p.outlier ? p.log_outlier : Const<T>::neg_inf();
+    int n_max = p.outlier ? 1 : 0;
+    T s = 0;
+    if (dense) {
+        for (int k = 0; k < p.ns; ++k) {
+            T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+            T a = cpd_term(p, e0 * e0 + e1 * e1 + e2 * e2, p.logws[k]);
+            if (a > a_max) { a_max = a; n_max = 1; } else if (a == a_max) ++n_max;
+        }
+        if (a_max > Const<T>::neg_inf() && a_max < INFINITY) {
+            for (int k = 0; k < p.ns; ++k) {
+                T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+                T a = cpd_term(p, e0 * e0 + e1 * e1 + e2 * e2, p.logws[k]);
+                if (a != a_max) s += m_exp(a - a_max);
+            }
+            if (p.outlier && p.log_outlier != a_max) s += m_exp(p.log_outlier - a_max);
+        }
+    } else {
+        // k nearest moved source points (scipy KDTree.query, registration.py:107-108)
+        T bd[CPD_KMAX], bl[CPD_KMAX];
+        int cnt = 0;
+        const int kk = p.k;
+        for (int k = 0; k < p.ns; ++k) {
+            T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+            T d2 = e0 * e0 + e1 * e1 + e2 * e2;
+            if (cnt < kk || d2 < bd[cnt - 1]) {
+                int i = cnt < kk ? cnt++ : kk - 1;
+                while (i > 0 && bd[i - 1] > d2) { bd[i] = bd[i - 1]; bl[i] = bl[i - 1]; --i; }
+                bd[i] = d2; bl[i] = p.logws[k];
+            }
+        }
+        for (int i = 0; i < cnt; ++i) {
+            T a = cpd_term(p, bd[i], bl[i]);
+            bd[i] = a;
+            if (a > a_max) { a_max = a; n_max = 1; } else if (a == a_max) ++n_max;
+        }
+        if (a_max > Const<T>::neg_inf() && a_max < INFINITY) {
+            for (int i = 0; i < cnt; ++i)
+                if (bd[i] != a_max) s += m_exp(bd[i] - a_max);
+            if (p.outlier && p.log_outlier != a_max) s += m_exp(p.log_outlier - a_max);
+        }
+    }
+    if (n_max == 0) n_max = 1;
+    return lse_finish(a_max, s, n_max) * p.wt[l];
+}
+
+}  // namespace geosss

@@ -1,0 +1,258 @@
+"""
+Geodesic slice samplers with the reference's interface, running N chains at once on a B200.
+
+    determine_burnin                       geosss/mcmc.py:13-19
+    Sampler.__init__/__next__/sample       geosss/mcmc.py:28-77
+    RejectionSphericalSliceSampler         geosss/mcmc.py:335-374
+    ShrinkageSphericalSliceSampler         geosss/mcmc.py:377-401
+
+Drop-in use is unchanged::
+
+    samples = ShrinkageSphericalSliceSampler(pdf, init_state, seed).sample(n_samples, burnin)
+
+with ``init_state`` of shape ``(d,)`` -> ``(n, d)`` exactly as upstream.  Extension: an
+``init_state`` of shape ``(N, d)`` runs N independent chains and returns ``(N, n, d)`` (the
+``(chain, draw, dim)`` layout the upstream scripts stack, scripts/protein_reg3d3d.py:346-349).
+
+Same semantics as upstream: the first retained sample is the current state, so
+``n_samples + burnin - 1`` transitions run; a float burn-in is a fraction of ``n_samples``;
+calling ``sample`` again continues the chain.  Differences, by construction: draws come from a
+per-chain Philox4x32-10 stream keyed by ``seed`` and the global chain id (numpy's PCG64 sequence
+is not reproduced, so results agree with upstream in distribution, and exactly when both are fed
+the same draws -- see ``run_tape``); ``dtype='float32'`` (default) uses the throughput kernels,
+``dtype='float64'`` the literal ones.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _device, _lib
+
+
+def determine_burnin(n_samples, burnin):
+    """Float in [0, 1]: fraction of n_samples; anything else: a count  (mcmc.py:13-19)."""
+    if isinstance(burnin, float):
+        assert 0 <= burnin <= 1.0
+        return int(burnin * n_samples)
+    assert burnin >= 0
+    return int(burnin)
+
+
+class PhiloxStream:
+    """What ``sampler.rng`` holds here: the key and position of the counter-based stream."""
+
+    def __init__(self, seed, chain_offset):
+        self.seed, self.chain_offset, self.steps_done = seed, chain_offset, 0
+
+    def __repr__(self):
+        return f"PhiloxStream(seed={self.seed:#x}, chain_offset={self.chain_offset}, steps_done={self.steps_done})"
+
+
+class Sampler:
+    """Base class: state handling and the ``sample`` driver (mcmc.py:22-77)."""
+
+    KIND = None
+
+    def __init__(self, distribution, initial_state, seed=None, *, dtype="float32", path="auto", device=None,
+                 chain_offset=0):
+        self.target = distribution
+        self._torch_io = isinstance(initial_state, torch.Tensor)
+        x0 = initial_state.detach().cpu().numpy() if self._torch_io else np.asarray(initial_state)
+        if x0.ndim not in (1, 2):
+            raise ValueError("initial_state must have shape (d,) or (N, d)")
+        self._single = x0.ndim == 1
+        self._host_state = np.array(x0, dtype=float).reshape(-1, x0.shape[-1])
+        self.N, self.d = self._host_state.shape
+        if distribution.d is not None and self.d != distribution.d:
+            raise ValueError(f"initial_state has dimension {self.d}, target has {distribution.d}")
+        self._code, self._tdtype, self._npdtype = _device.dtype_code(dtype)
+        if path not in ("auto", "fast", "literal"):
+            raise ValueError("path must be 'auto', 'fast' or 'literal'")
+        self._path_req = path
+        self._device_req = device if device is not None else (initial_state.device if self._torch_io and initial_state.is_cuda else None)
+        self.rng = PhiloxStream(_device.seed_to_u64(seed), int(chain_offset))
+        self._h = None
+        self._n_reject = 0
+        self._rej_seen = 0
+        self._steps_counted = 0
+
+    # ---- device sampler ------------------------------------------------------------------
+    def _sampler(self):
+        if self._h is None:
+            self.device = _device.resolve_device(self._device_req)
+            lib = _lib.lib()
+            tgt = self.target._handle(self.device)
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                want_fast = self._path_req in ("auto", "fast") and self._code == _lib.F32
+                rc = _lib.E_UNSUPPORTED
+                if want_fast:
+                    rc = lib.geosss_sampler_create(tgt, self.KIND, self._code, _lib.PATH_FAST, self.N, self.rng.seed,
+                                                   self.rng.chain_offset, C.byref(h))
+                    self.path = "fast"
+                if rc == _lib.E_UNSUPPORTED and self._path_req != "fast":
+                    rc = lib.geosss_sampler_create(tgt, self.KIND, self._code, _lib.PATH_LITERAL, self.N, self.rng.seed,
+                                                   self.rng.chain_offset, C.byref(h))
+                    self.path = "literal"
+                _lib.check(rc)
+                self._h = h
+                _lib.check(lib.geosss_sampler_set_state_host(h, _lib.dptr(np.ascontiguousarray(self._host_state))))
+        return self._h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None:
+            try:
+                with torch.cuda.device(self.device):
+                    _lib.lib().geosss_sampler_destroy(h)
+            except Exception:
+                pass
+
+    # ---- reference attributes --------------------------------------------------------------
+    @property
+    def state(self):
+        """Current state(s), float64 on the host: (d,) for one chain, (N, d) otherwise."""
+        if self._h is not None:
+            buf = np.empty((self.N, self.d))
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_get_state_host(self._h, _lib.dptr(buf), None))
+            self._host_state = buf
+        return self._host_state[0] if self._single else self._host_state
+
+    @state.setter
+    def state(self, value):
+        value = np.array(value, dtype=float).reshape(self.N, self.d)
+        self._host_state = value
+        if self._h is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_set_state_host(self._h, _lib.dptr(np.ascontiguousarray(value))))
+
+    @property
+    def n_reject_per_chain(self):
+        if self._h is None:
+            return np.zeros(self.N, dtype=np.uint64)
+        buf = np.empty(self.N, dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_get_state_host(self._h, None, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    @property
+    def n_reject(self):
+        """Rejected proposals so far, summed over chains (mcmc.py:355,374,401)."""
+        self._sync_counters()
+        return self._n_reject
+
+    def _sync_counters(self):
+        if self._h is None:
+            return
+        total = int(self.n_reject_per_chain.sum())
+        steps = self.rng.steps_done
+        # the reference evaluates log_prob 2 + r times per transition (mcmc.py:364-371,389-397)
+        calls = 2 * (steps - self._steps_counted) * self.N + (total - self._rej_seen)
+        lp = getattr(self.target, "log_prob", None)
+        if calls and hasattr(lp, "add_calls"):
+            lp.add_calls(calls)
+        self._n_reject, self._rej_seen, self._steps_counted = total, total, steps
+
+    # ---- iteration -------------------------------------------------------------------------
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        """One transition of every chain; returns the new state(s)."""
+        self._run_device(1, None)
+        return self.state.copy()
+
+    def _run_device(self, n_steps, samples, thin=1, logp=None, nrej=None):
+        h = self._sampler()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_run(
+                h, n_steps, thin, None if samples is None else samples.data_ptr(),
+                None if logp is None else logp.data_ptr(), None if nrej is None else nrej.data_ptr(),
+                _device.stream_ptr(self.device)))
+        self.rng.steps_done += n_steps
+
+    def sample(self, n_samples, burnin=0, return_all_samples=False, *, out=None):
+        """Markov chain(s) of the requested length (mcmc.py:55-77).
+
+        Returns float arrays of the sampler's dtype: ``(n, d)`` for one chain, ``(N, n, d)`` for N
+        chains (a transposed view of the step-major ``(n, N, d)`` buffer the kernels write).
+        numpy in -> numpy out through pinned host memory, with device->host copies overlapped
+        with sampling; a CUDA tensor as ``initial_state`` -> CUDA tensor out, no host copy.
+        ``out``: optional preallocated ``(n, N, d)`` pinned tensor / CUDA tensor to fill.
+        """
+        assert n_samples > 0
+        burnin = determine_burnin(n_samples, burnin)
+        n_out = n_samples + burnin if return_all_samples else n_samples
+        keeps_current = return_all_samples or burnin == 0
+        n_skip = 0 if keeps_current else burnin - 1
+        n_new = n_out - 1 if keeps_current else n_out
+        h = self._sampler()
+        lib = _lib.lib()
+        on_device = self._torch_io and self._device_req is not None
+        shape = (n_out, self.N, self.d)
+        if out is not None:
+            if tuple(out.shape) != shape or out.dtype != self._tdtype or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous {self._tdtype} tensor of shape {shape}")
+            on_device = out.is_cuda
+        if on_device:
+            buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, device=self.device)
+            if keeps_current:
+                buf[0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype, device=self.device)
+            if n_skip:
+                self._run_device(n_skip, None)
+            if n_new:
+                self._run_device(n_new, buf[1:] if keeps_current else buf)
+            res = buf.permute(1, 0, 2)
+        else:
+            buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
+            if keeps_current:
+                buf[0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype)
+            dst = buf[1:] if keeps_current else buf
+            with torch.cuda.device(self.device):
+                _lib.check(lib.geosss_sampler_run_host(h, n_skip, n_new, dst.data_ptr() if n_new else None))
+            self.rng.steps_done += n_skip + n_new
+            res = buf.numpy().transpose(1, 0, 2) if not self._torch_io else buf.permute(1, 0, 2)
+        self._sync_counters()
+        return res[0] if self._single else res
+
+    # ---- parity mode ---------------------------------------------------------------------
+    def run_tape(self, tapes, n_steps):
+        """Run ``n_steps`` transitions with the draws taken from ``tapes`` (one flat float64
+        array per chain, in the reference's consumption order -- see oracle/tape.py).  Literal
+        path only.  Returns (samples (N, n_steps, d), rejections (N, n_steps), status (N,))."""
+        if self._path_req == "auto":
+            self._path_req = "literal"
+        h = self._sampler()
+        if self.path != "literal":
+            raise ValueError("tape mode needs path='literal'")
+        if self._single and not isinstance(tapes, (list, tuple)):
+            tapes = [tapes]
+        assert len(tapes) == self.N
+        offs = np.zeros(self.N + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(t) for t in tapes])
+        flat = torch.as_tensor(np.concatenate([np.asarray(t, dtype=float) for t in tapes])).to(self.device)
+        offs_d = torch.as_tensor(offs).to(self.device)
+        samples = torch.empty((n_steps, self.N, self.d), dtype=self._tdtype, device=self.device)
+        nrej = torch.zeros((n_steps, self.N), dtype=torch.int32, device=self.device)
+        status = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_run_tape(h, n_steps, flat.data_ptr(), offs_d.data_ptr(), samples.data_ptr(),
+                                                          nrej.data_ptr(), status.data_ptr(), _device.stream_ptr(self.device)))
+            torch.cuda.synchronize(self.device)
+        self.rng.steps_done += n_steps
+        return (samples.permute(1, 0, 2).cpu().numpy(), nrej.t().cpu().numpy(), status.cpu().numpy())
+
+
+class RejectionSphericalSliceSampler(Sampler):
+    """GeoSSS-reject: proposals uniform on the whole great circle until one falls in the slice."""
+
+    KIND = _lib.REJECT
+
+
+class ShrinkageSphericalSliceSampler(RejectionSphericalSliceSampler):
+    """GeoSSS-shrink: the proposal bracket shrinks towards the current state on rejections."""
+
+    KIND = _lib.SHRINK

@@ -1,0 +1,138 @@
+/*
+ * libgeosss_cuda -- C ABI of the B200 (sm_100a) engine for geosss's geodesic slice-sampling
+ * hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference (microscopic-image-analysis/geosss v0.3.5) is pure Python and has no FFI; the
+ * entry points below are what a binding for the path would need, one per reference interface:
+ *
+ *   geosss_target_create_vmf_mixture   VonMisesFisher.__init__ / MixtureModel.__init__
+ *                                      (geosss/distributions.py:126-127, :211-216)
+ *   geosss_target_create_bingham       Bingham.__init__ / BinghamFisher.__init__ (:67-76, :108-111)
+ *   geosss_target_create_curved_vmf    CurvedVonMisesFisher.__init__ + SlerpCurve.__init__
+ *                                      (distributions.py:263-265, spherical_curve.py:79-85)
+ *   geosss_target_create_cpd           CoherentPointDrift.__init__ / GaussianMixtureModel.__init__
+ *                                      (geosss/registration.py:69-99, :172-203)
+ *   geosss_log_prob                    Distribution.log_prob(x) for x of shape (N, d)
+ *                                      (distributions.py:78-86, :156-157, :218-221, :272-275,
+ *                                       registration.py:47-53)
+ *   geosss_sampler_create              Sampler.__init__ (geosss/mcmc.py:28-45, :340-355)
+ *   geosss_sampler_set_state/get_state Sampler.state, .n_reject (mcmc.py:44, :355)
+ *   geosss_sampler_run                 repeated __next__ inside Sampler.sample (mcmc.py:55-77,
+ *                                      :357-374 reject, :382-401 shrink), own Philox stream
+ *   geosss_sampler_run_tape            the same transitions fed with recorded draws (parity mode)
+ *   geosss_sample_host                 Sampler(pdf, x0, seed).sample(n, burnin) with HOST buffers
+ *
+ * Conventions: every function returns 0 on success or a negative GEOSSS_E_* code, with a
+ * message available from geosss_last_error() (thread-local).  Unless the name ends in _host,
+ * data pointers are DEVICE pointers owned by the caller; work is enqueued on the given
+ * cudaStream_t (passed as void*; NULL = default stream) and is asynchronous -- no hidden
+ * synchronisation or allocation in log_prob / run.  Handles are opaque and belong to the
+ * device that was current when they were created; a handle must not be used from two threads
+ * at once.  Row-major everywhere; "dtype" selects float32 (fast) or float64 (parity).
+ */
+#ifndef GEOSSS_CUDA_H
+#define GEOSSS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEOSSS_VERSION 100 /* 0.1.0 */
+
+enum { GEOSSS_F32 = 0, GEOSSS_F64 = 1 };
+enum { GEOSSS_REJECT = 0, GEOSSS_SHRINK = 1 };
+/* LITERAL: reference operation order (any target, either dtype).
+ * FAST:    float32 throughput kernels that use the great-circle algebra. */
+enum { GEOSSS_PATH_LITERAL = 0, GEOSSS_PATH_FAST = 1 };
+
+enum {
+    GEOSSS_OK = 0,
+    GEOSSS_E_INVALID = -1,     /* bad argument (the reference would assert / raise ValueError) */
+    GEOSSS_E_CUDA = -2,        /* a CUDA runtime call failed */
+    GEOSSS_E_UNSUPPORTED = -3, /* combination not available (e.g. FAST path in float64) */
+    GEOSSS_E_NOMEM = -4
+};
+
+typedef struct geosss_target* geosss_target_t;
+typedef struct geosss_sampler* geosss_sampler_t;
+
+int geosss_version(void);
+const char* geosss_last_error(void);
+
+/* ---- targets (host parameter arrays, float64; copied to the device in both precisions) ---- */
+
+/* mu: (K, d).  logw: (K) log of NORMALISED weights, or NULL for a lone VonMisesFisher (no
+ * logsumexp).  log_i0: (K) log(i0(|mu_k|)) as the reference computes it (scipy), may hold +inf;
+ * NULL lets the library compute it with std::cyl_bessel_i. */
+int geosss_target_create_vmf_mixture(int d, int K, const double* mu, const double* logw,
+                                     const double* log_i0, geosss_target_t* out);
+/* A: (d, d) symmetric.  b: (d) Fisher term or NULL. */
+int geosss_target_create_bingham(int d, const double* A, const double* b, geosss_target_t* out);
+/* knots: (n_knots, d), consecutive knots are joined by slerps. */
+int geosss_target_create_curved_vmf(int d, int n_knots, const double* knots, double kappa,
+                                    geosss_target_t* out);
+/* target: (n_t, 3), w_t: (n_t); source: (n_s, 3), w_s: (n_s).  k <= 0 or k >= n_s sums every
+ * source point, else the k nearest (k <= 64).  outlier = 0 selects the GaussianMixtureModel
+ * parent (no outlier column, omega ignored). */
+int geosss_target_create_cpd(int n_t, int n_s, const double* target, const double* w_t,
+                             const double* source, const double* w_s, double sigma, double omega,
+                             double beta, int k, int outlier, geosss_target_t* out);
+int geosss_target_dim(geosss_target_t t); /* ambient dimension d of the state */
+int geosss_target_destroy(geosss_target_t t);
+
+/* x: (N, d) device, out: (N) device, both of `dtype`. */
+int geosss_log_prob(geosss_target_t t, int dtype, int path, const void* x, void* out, int64_t N,
+                    void* stream);
+
+/* ---- samplers: N independent chains ------------------------------------------------------ */
+
+/* chain_offset: global id of this sampler's chain 0; the Philox counter uses the global id, so
+ * results do not depend on how chains are split over samplers / GPUs. */
+int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int path, int64_t N,
+                          uint64_t seed, uint64_t chain_offset, geosss_sampler_t* out);
+int geosss_sampler_set_state(geosss_sampler_t s, const void* x /* (N, d) dtype */, void* stream);
+/* x: (N, d) or NULL; n_reject: (N) running totals or NULL. */
+int geosss_sampler_get_state(geosss_sampler_t s, void* x, uint64_t* n_reject, void* stream);
+/* Runs n_steps transitions of every chain.  Every thin-th state is kept:
+ * samples_out (n_steps / thin, N, d), logp_out (n_steps / thin, N), nrej_out (n_steps / thin, N)
+ * rejections accumulated since the previous kept state; any of them may be NULL. */
+int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* samples_out,
+                       void* logp_out, uint32_t* nrej_out, void* stream);
+/* Parity mode: draws come from a flat float64 tape per chain, in the order the reference consumes
+ * them (d normals, level uniform, [bracket uniform,] one uniform per proposal; next transition).
+ * tape_offsets: (N + 1) int64.  status: (N) 0 ok / 1 tape exhausted early, or NULL. */
+int geosss_sampler_run_tape(geosss_sampler_t s, int64_t n_steps, const double* tape,
+                            const int64_t* tape_offsets, void* samples_out, uint32_t* nrej_out,
+                            int32_t* status, void* stream);
+/* transitions done so far (the Philox step counter) */
+int64_t geosss_sampler_steps_done(geosss_sampler_t s);
+int geosss_sampler_destroy(geosss_sampler_t s);
+
+/* ---- HOST-buffer entry points (synchronous; copies are part of the call) ------------------- */
+
+/* x_host: (N, d) float64 on the host, converted to the sampler's dtype. */
+int geosss_sampler_set_state_host(geosss_sampler_t s, const double* x_host);
+/* x_host: (N, d) float64 or NULL; n_reject_host: (N) or NULL. */
+int geosss_sampler_get_state_host(geosss_sampler_t s, double* x_host, uint64_t* n_reject_host);
+/* n_skip transitions without output, then n_keep transitions whose states are written to
+ * samples_host (n_keep, N, d) of the sampler's dtype (pinned memory recommended).  Sampling of
+ * chunk i overlaps the device->host copy of chunk i-1 (two streams, double buffering). */
+int geosss_sampler_run_host(geosss_sampler_t s, int64_t n_skip, int64_t n_keep, void* samples_host);
+
+/* Sampler(pdf, x0, seed).sample(n_samples, burnin) for N chains: x0_host (N, d) float64 on the
+ * host; samples_host (n_samples, N, d) of `dtype` on the host (pinned memory recommended).
+ * Reference semantics per chain (mcmc.py:55-77): the first retained state is the initial state,
+ * n_samples + burnin - 1 transitions run, the first `burnin` states are dropped.  The device
+ * work is chunked and the device->host copies are overlapped with sampling on two streams.
+ * n_reject_host: (N) or NULL. */
+int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t N,
+                       const double* x0_host, uint64_t seed, uint64_t chain_offset,
+                       int64_t n_samples, int64_t burnin, void* samples_host,
+                       uint64_t* n_reject_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOSSS_CUDA_H */
