@@ -1,0 +1,276 @@
+"""
+bench.py -- GeoSSS samples/sec on the BASELINE.json workload.
+
+    python bench.py [--gpus N --steps K --warmup W]            # our CUDA path
+    python bench.py --impl reference [...]                      # CPU arm: oracle port on all host cores
+
+Workload (BASELINE.json configs[1], scripts/mixture_vMF.py): mixture of K=5 von Mises-Fisher
+components on S^9 (d=10), modes = sample_sphere(9, 5, seed=1234), kappa=100, GeoSSS-shrink,
+65,536 chains PER GPU (weak scaling: each rank owns a disjoint block of global chain ids).
+One "step" = --transitions Markov transitions of every chain, every state retained in HBM
+(step-major (T, N, d) float32), exactly what ``sampler.sample()`` returns.  One step is one
+launch of the sampler kernel; its output (T*N*40 B >> L2) is larger than L2.
+
+value  = transitions of all chains of all ranks / device time (CUDA events, max over ranks)
+e2e    = same metric through the public Python API with HOST buffers: initial states numpy ->
+         device, all samples device -> pinned host, inside the timed region
+roofline: retained-sample bytes written per second by the sampler kernel against the measured
+         HBM copy bandwidth (the kernel is issue/MUFU-bound, not HBM-bound)
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GeoSSS-shrink samples/sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=65536, help="chains per GPU")
+    ap.add_argument("--transitions", type=int, default=500, help="transitions per step")
+    ap.add_argument("--kappa", type=float, default=100.0)
+    ap.add_argument("--sampler", default="shrink", choices=["shrink", "reject"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-transitions", type=int, default=2500, help="transitions per host core in the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_dict(a):
+    return {"name": "vmf_mixture", "d": 10, "K": 5, "kappa": a.kappa}
+
+
+def config_dict(a, n_gpus):
+    return {"workload": f"C2 vMF mixture d=10 K=5 kappa={a.kappa:g} (scripts/mixture_vMF.py), sss-{a.sampler}",
+            "chains_per_gpu": a.chains, "chains_total": a.chains * n_gpus, "transitions_per_step": a.transitions,
+            "retention": "every state, (T,N,d) float32 in HBM", "l2": "outputs_larger_than_L2",
+            "sharding": f"chains x{n_gpus}"}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 8 or not (t0 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_arm(a, n_transitions):
+    from oracle import cpu_bench
+    kind = 1 if a.sampler == "shrink" else 0
+    return cpu_bench.run_all_cores(workload_dict(a), kind, n_transitions)
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_core = max(200, a.cpu_transitions // 5)
+    for _ in range(a.warmup):
+        cpu_arm(a, 50)
+    total, cores, rej, wall = 0, 1, 0.0, 0.0
+    for _ in range(a.steps):
+        r = cpu_arm(a, per_core)
+        total += r["transitions"]
+        wall += r["wall_s"]  # process start-up and imports are outside the timed region
+        cores = r["cores"]
+        rej = r["mean_rejections"]
+    value = total / wall
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(a, a.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"oracle port of the reference samplers, {cores} independent chains x {per_core} transitions per step, "
+                                       f"mean rejections/transition {rej:.2f}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import geosss_b200 as gs
+    from geosss_b200 import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N, T, d = a.chains, a.transitions, 10
+    modes = gs.sample_sphere(d - 1, 5, seed=1234)
+    pdf = gs.MixtureModel([gs.VonMisesFisher(a.kappa * m) for m in modes])
+    cls = gs.ShrinkageSphericalSliceSampler if a.sampler == "shrink" else gs.RejectionSphericalSliceSampler
+    x0 = gs.sample_sphere(d - 1, N, seed=np.random.SeedSequence(48485).spawn(world)[rank])
+    smp = cls(pdf, torch.as_tensor(x0).to(dev), 48385, chain_offset=rank * N)
+    buf = torch.empty((T, N, d), dtype=torch.float32, device=dev)
+
+    # burn-in + warm-up
+    smp._run_device(200, None)
+    for _ in range(max(a.warmup, 3)):
+        smp._run_device(T, buf)
+    rej0 = int(smp.n_reject_per_chain.sum())
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    t_host0 = time.perf_counter()
+    for s, e in ev:
+        s.record()
+        smp._run_device(T, buf)  # one kernel launch: T transitions of N chains, all states retained
+        e.record()
+    barrier()
+    t_host1 = time.perf_counter()
+    total_ms = ev[0][0].elapsed_time(ev[-1][1])
+    launch_ms = [s.elapsed_time(e) for s, e in ev]
+    clk = clocks.stop(t_host0, t_host1)
+    total_ms = max_over_ranks(total_ms)
+    rej = (int(smp.n_reject_per_chain.sum()) - rej0) / (a.steps * T * N)
+
+    samples_per_step = N * T * world
+    value = samples_per_step * a.steps / (total_ms * 1e-3)
+
+    # roofline of the sampler kernel: retained bytes written / launch duration vs measured HBM copy bandwidth
+    peak, peak_src = measured_peak_hbm()
+    avg_launch_s = statistics.mean(launch_ms) * 1e-3
+    algo_bytes = N * T * d * 4
+    achieved = algo_bytes / avg_launch_s / 1e9
+
+    # ESS of the first coordinate over the last retained step (64 chains, oracle estimator; diagnostics only)
+    ess = None
+    if rank == 0:
+        try:
+            from oracle import ess as ess_mod
+            tr = buf[:, :64, 0].t().contiguous().cpu().numpy().astype(np.float64)
+            rel = ess_mod.ess_multichain(tr, min(T // 2, 400)) / tr.size
+            ess = {"relative_ess_x0": rel, "ess_per_sec": rel * value, "chains_used": 64, "draws": T}
+        except Exception as exc:  # diagnostics must not break the bench line
+            ess = {"error": str(exc)}
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    x0_host = np.ascontiguousarray(x0)
+    out_host = torch.empty((T + 1, N, d), dtype=torch.float32, pin_memory=True)
+    def e2e_step(seed):
+        s = cls(pdf, x0_host, seed, chain_offset=rank * N)
+        s.sample(T + 1, 0, out=out_host)  # H2D of the initial states, T transitions, D2H of every state
+        return s
+    e2e_step(1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.e2e_steps):
+        e2e_step(2 + i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = N * T * world * a.e2e_steps / e2e_s
+    h2d = N * d * 4
+    d2h = T * N * d * 4 + N * 8
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_arm(a, a.cpu_transitions)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"oracle port of the reference sampler (float64 numpy/scipy), {r['cores']} independent chains x "
+                         f"{a.cpu_transitions} transitions, mean rejections/transition {r['mean_rejections']:.2f}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": a.e2e_steps, "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
+                "gpu_launches": a.steps,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<5,12,SHRINK>",
+                             "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
+                             "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
+                "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
+                "samples_per_sec_per_gpu": value / world}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

@@ -19,4 +19,4 @@ build container only) and writes ``tests/golden/*.npz``; ``tests/test_oracle_gol
 checks every oracle function against those vectors.
 """
 
-from . import sphere, targets, samplers, tape, philox, ess  # noqa: F401
+from . import sphere, targets, samplers, tape, philox, ess, exact  # noqa: F401

@@ -1,0 +1,316 @@
+"""
+GPU parity tests: the CUDA path, called through the Python mirror -> ctypes -> C ABI of
+libgeosss_cuda.so, against the golden vectors recorded from the upstream package and against
+the float64 oracle fed the same draws.  Nothing here reads /root/reference.
+
+Stated tolerances:
+  float64  log_prob <= 1e-12 * max(1, |logp|);  CPD <= 5e-12 abs;  tape trajectories <= 1e-12
+           abs with identical per-step rejection counts
+  float32  log_prob <= 1e-5 * max(1, |logp|) (curved vMF 2e-5);  CPD <= 1e-3 abs;  trajectories
+           <= 1e-4 abs up to the first accept/reject flip
+  own-RNG marginals: Kolmogorov-Smirnov against exact draws at alpha = 1e-3
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import geosss_b200 as gs
+from geosss_b200 import _lib
+from oracle import exact, philox, samplers, targets
+
+pytestmark = pytest.mark.gpu
+
+F32, F64 = np.float32, np.float64
+
+
+def rel_err(got, want):
+    return np.max(np.abs(np.asarray(got, float) - want) / np.maximum(1.0, np.abs(want)))
+
+
+def mixture(mus, weights=None):
+    return gs.MixtureModel([gs.VonMisesFisher(m) for m in mus], weights)
+
+
+def c5_target(golden, k=20):
+    c = golden("logprob_cpd")
+    n = len(c["c5_source"])
+    return gs.CoherentPointDrift(gs.PointCloud(c["c5_target"], np.ones(len(c["c5_target"]))),
+                                 gs.PointCloud(c["c5_source"], np.ones(n) / n), sigma=1.0, k=k, omega=0.4)
+
+
+# ------------------------------------------------------------------ log_prob
+@pytest.mark.parametrize("dtype,tol", [(F64, 1e-12), (F32, 1e-5)])
+def test_logprob_vmf(golden, dtype, tol):
+    g = golden("logprob_vmf")
+    assert rel_err(mixture(g["c1_mus"]).log_prob(g["c1_x"].astype(dtype)), g["c1_logp"]) <= tol
+    for kappa in (50, 100, 500):
+        got = mixture(kappa * g["c2_modes"]).log_prob(g["c2_x"].astype(dtype))
+        assert got.dtype == dtype and got.shape == (256,)
+        assert rel_err(got, g[f"c2_logp_k{kappa}"]) <= tol
+    assert rel_err(mixture(g["wmix_mus"], g["wmix_w"]).log_prob(g["wmix_x"].astype(dtype)), g["wmix_logp"]) <= tol
+    assert rel_err(gs.VonMisesFisher(g["vmf_mu"]).log_prob(g["vmf_x"].astype(dtype)), g["vmf_logp"]) <= tol
+    # single point -> scalar; torch tensor in -> torch tensor out
+    one = mixture(g["c1_mus"]).log_prob(g["c1_x"][5].astype(dtype))
+    assert np.ndim(one) == 0 and abs(one - g["c1_logp"][5]) <= tol * max(1, abs(g["c1_logp"][5]))
+    tt = mixture(g["c1_mus"]).log_prob(torch.as_tensor(g["c1_x"].astype(dtype)).cuda())
+    assert isinstance(tt, torch.Tensor) and tt.is_cuda and rel_err(tt.cpu().numpy(), g["c1_logp"]) <= tol
+    # i0 overflow quirk: kappa > ~713 gives -inf like the reference
+    assert np.all(np.isneginf(mixture(800.0 * g["c2_modes"]).log_prob(g["c2_x"][:8].astype(dtype))))
+
+
+@pytest.mark.parametrize("dtype,tol", [(F64, 1e-12), (F32, 1e-5)])
+def test_logprob_bingham_curved(golden, dtype, tol):
+    g = golden("logprob_bingham")
+    for tag in ("c4diag", "c4dense", "d10"):
+        pdf = gs.Bingham(g[f"{tag}_A"])
+        assert rel_err(pdf.log_prob(g[f"{tag}_x"].astype(dtype)), g[f"{tag}_logp"]) <= tol
+    assert rel_err(gs.BinghamFisher(g["bf_A"], g["bf_b"]).log_prob(g["bf_x"].astype(dtype)), g["bf_logp"]) <= tol
+    with pytest.raises(AssertionError):
+        gs.Bingham(g["d10_A"]).log_prob(np.ones(9))
+    g = golden("logprob_curved")
+    for tag in ("c3", "d10", "d3"):
+        pdf = gs.CurvedVonMisesFisher(gs.SlerpCurve(g[f"{tag}_knots"]), 500.0)
+        assert rel_err(pdf.log_prob(g[f"{tag}_x"].astype(dtype)), g[f"{tag}_logp"]) <= (tol if dtype == F64 else 2e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(F64, 5e-12), (F32, 1e-3)])
+def test_logprob_cpd(golden, dtype, tol):
+    g = golden("logprob_cpd")
+    for k in (20, 0):
+        assert np.max(np.abs(c5_target(golden, k).log_prob(g["c5_q"].astype(dtype)) - g["c5_logp"])) <= tol
+    # rotation matrix input (registration.py:47-53)
+    want = g["c5_logp"][-2]  # the quaternion of the true rotation
+    assert abs(c5_target(golden).log_prob(g["c5_rotation"]) - want) <= 1e-9
+    rtol = 1e-12 if dtype == F64 else 1e-5
+    for om in (0, 2, 4):
+        m = gs.CoherentPointDrift(gs.PointCloud(g["cube_target"], g["cube_wt"]), gs.PointCloud(g["cube_source"], g["cube_ws"]),
+                                  sigma=0.5, k=8, omega=om / 10, beta=1.5)
+        assert rel_err(m.log_prob(g["cube_q"].astype(dtype)), g[f"cube_logp_om{om}"]) <= rtol
+    gm = gs.GaussianMixtureModel(gs.PointCloud(g["cube_target"], g["cube_wt"]), gs.PointCloud(g["cube_source"], g["cube_ws"]),
+                                 sigma=0.5, k=8)
+    assert rel_err(gm.log_prob(g["cube_q"].astype(dtype)), g["cube_logp_gmm"]) <= rtol
+
+
+def test_logprob_empty_and_ragged(golden):
+    g = golden("logprob_vmf")
+    pdf = mixture(g["c1_mus"])
+    assert pdf.log_prob(np.zeros((0, 3))).shape == (0,)
+    for n in (1, 31, 33, 129):
+        assert rel_err(pdf.log_prob(g["c1_x"][:n] if n <= 96 else np.tile(g["c1_x"], (2, 1))[:n]),
+                       (g["c1_logp"][:n] if n <= 96 else np.tile(g["c1_logp"], 2)[:n])) <= 1e-12
+    with pytest.raises(ValueError):
+        pdf.log_prob(np.zeros(4))
+
+
+# ------------------------------------------------------------------ trajectories under the reference's draws
+def tape_cases(golden):
+    g = golden("traj_c1")
+    pdf = mixture(g["mus"])
+    yield pdf, gs.ShrinkageSphericalSliceSampler, g, "shrink"
+    yield pdf, gs.RejectionSphericalSliceSampler, g, "reject"
+    g = golden("traj_c2")
+    for kappa in (100, 500):
+        pdf = mixture(kappa * g["modes"])
+        yield pdf, gs.ShrinkageSphericalSliceSampler, g, f"shrink_k{kappa}_s0"
+        yield pdf, gs.ShrinkageSphericalSliceSampler, g, f"shrink_k{kappa}_s1"
+        yield pdf, gs.RejectionSphericalSliceSampler, g, f"reject_k{kappa}_s0"
+    g = golden("traj_c3")
+    pdf = gs.CurvedVonMisesFisher(gs.SlerpCurve(g["knots"]), float(g["kappa"]))
+    yield pdf, gs.ShrinkageSphericalSliceSampler, g, "shrink"
+    yield pdf, gs.RejectionSphericalSliceSampler, g, "reject"
+    g = golden("traj_c4")
+    for tag in ("diag", "dense"):
+        pdf = gs.Bingham(g[f"{tag}_A"])
+        yield pdf, gs.ShrinkageSphericalSliceSampler, g, f"{tag}_shrink"
+        yield pdf, gs.RejectionSphericalSliceSampler, g, f"{tag}_reject"
+    g = golden("traj_c5")
+    pdf = c5_target(golden)
+    yield pdf, gs.ShrinkageSphericalSliceSampler, g, "shrink"
+    yield pdf, gs.RejectionSphericalSliceSampler, g, "reject"
+
+
+def test_tape_trajectories_float64(golden):
+    for pdf, cls, g, tag in tape_cases(golden):
+        want, cum = g[f"{tag}_traj"], g[f"{tag}_cumrej"]
+        smp = cls(pdf, g[f"{tag}_x0"], 0, dtype="float64", path="literal")
+        got, nrej, status = smp.run_tape(g[f"{tag}_tape"], len(want) - 1)
+        assert status[0] == 0, tag
+        assert np.array_equal(nrej[0], np.diff(cum)), tag
+        assert np.max(np.abs(got[0] - want[1:])) <= 1e-12, tag
+        assert smp.n_reject == cum[-1]
+
+
+def test_tape_trajectories_float32(golden):
+    total = clean = 0
+    for pdf, cls, g, tag in tape_cases(golden):
+        want, rej_want = g[f"{tag}_traj"], np.diff(g[f"{tag}_cumrej"])
+        got, nrej, _ = cls(pdf, g[f"{tag}_x0"], 0, dtype="float32", path="literal").run_tape(g[f"{tag}_tape"], len(want) - 1)
+        flips = np.nonzero(nrej[0] != rej_want)[0]
+        upto = flips[0] if len(flips) else len(rej_want)
+        assert np.max(np.abs(got[0][:upto] - want[1:1 + upto])) <= 1e-4, tag
+        total += len(rej_want)
+        clean += upto
+    assert clean >= 0.8 * total, (clean, total)
+
+
+def test_tape_many_chains_ragged_block(golden):
+    """The same tape on 130 chains (not a multiple of the block size) gives 130 identical chains."""
+    g = golden("traj_c2")
+    pdf = mixture(100 * g["modes"])
+    tag = "shrink_k100_s0"
+    n = 200
+    N = 130
+    x0 = np.tile(g[f"{tag}_x0"], (N, 1))
+    got, nrej, status = gs.ShrinkageSphericalSliceSampler(pdf, x0, 0, dtype="float64", path="literal").run_tape(
+        [g[f"{tag}_tape"]] * N, n)
+    assert np.all(status == 0)
+    assert np.max(np.abs(got - g[f"{tag}_traj"][None, 1:n + 1])) <= 1e-12
+    assert np.all(nrej == np.diff(g[f"{tag}_cumrej"])[None, :n])
+    # a tape that is too short is reported, not read past its end
+    _, _, status = gs.ShrinkageSphericalSliceSampler(pdf, x0[:2], 0, dtype="float64", path="literal").run_tape(
+        [g[f"{tag}_tape"][:100]] * 2, 50)
+    assert np.all(status == 1)
+
+
+# ------------------------------------------------------------------ own Philox stream
+def oracle_chain(pdf_oracle, kind, x0, seed, chain, n, d, dtype, first_step=0):
+    rng = philox.PhiloxChainRNG(seed=seed, chain=chain, kind=kind, d=d, dtype=dtype, first_step=first_step)
+    smp = samplers.SliceSampler(kind, pdf_oracle.log_prob, np.array(x0, float), rng)
+    return smp.sample(n + 1)[1:], np.array(smp.rejects_per_step)
+
+
+@pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
+                                      (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
+def test_free_running_literal_float64_matches_oracle(golden, cls, kind):
+    """Literal float64 kernel + device Philox == reference algorithm fed oracle/philox.py's draws."""
+    g = golden("traj_c2")
+    mus = 100.0 * g["modes"]
+    x0 = gs.sample_sphere(9, 6, seed=5)
+    n = 60 if kind == samplers.SHRINK else 25
+    seed, off = 0xABCDEF0123456789, 2**32 - 3  # chain ids straddle the 32-bit boundary
+    smp = cls(mixture(mus), x0, seed, dtype="float64", path="literal", chain_offset=off)
+    got = smp.sample(n + 1)
+    assert got.shape == (6, n + 1, 10) and np.array_equal(got[:, 0], x0)
+    for c in range(6):
+        want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, off + c, n, 10, F64)
+        assert np.max(np.abs(got[c, 1:] - want)) <= 1e-11
+    assert smp.n_reject == sum(oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, off + c, n, 10, F64)[1].sum() for c in range(6))
+
+
+@pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
+                                      (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
+@pytest.mark.parametrize("cfg", ["c1", "c2_k100", "c2_k500"])
+def test_fast_path_follows_reference_under_shared_draws(golden, cls, kind, cfg):
+    """fp32 throughput kernel vs the float64 reference algorithm fed the same Philox draws:
+    <= 1e-4 until the first accept/reject flip; at most a small fraction of chains flip early."""
+    if cfg == "c1":
+        mus, d = golden("traj_c1")["mus"], 3
+    else:
+        mus, d = float(cfg.split("k")[1]) * golden("traj_c2")["modes"], 10
+    N, n = 24, (40 if kind == samplers.SHRINK else 15)
+    x0 = gs.sample_sphere(d - 1, N, seed=11)
+    seed = 20240607
+    smp = cls(mixture(mus), x0, seed, dtype="float32", path="fast")
+    got = smp.sample(n + 1)
+    assert smp.path == "fast" and got.dtype == F32
+    clean = 0
+    for c in range(N):
+        want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, c, n, d, F32)
+        err = np.max(np.abs(got[c, 1:] - want), axis=1)
+        bad = np.nonzero(err > 1e-4)[0]
+        upto = bad[0] if len(bad) else n
+        clean += upto
+    assert clean >= 0.9 * N * n, (clean, N * n)
+
+
+def test_shard_invariance_and_continuation(golden):
+    """Chains depend on (seed, global chain id, step) only: splitting chains over samplers or
+    steps over calls does not change them (what makes 1/2/4/8-GPU runs identical)."""
+    g = golden("traj_c2")
+    pdf = mixture(100.0 * g["modes"])
+    x0 = gs.sample_sphere(9, 200, seed=3)
+    for path in ("fast", "literal"):
+        whole = gs.ShrinkageSphericalSliceSampler(pdf, x0, 99, path=path).sample(30)
+        a = gs.ShrinkageSphericalSliceSampler(pdf, x0[:77], 99, path=path).sample(30)
+        b = gs.ShrinkageSphericalSliceSampler(pdf, x0[77:], 99, path=path, chain_offset=77).sample(30)
+        assert np.array_equal(whole, np.concatenate([a, b]))
+        s = gs.ShrinkageSphericalSliceSampler(pdf, x0, 99, path=path)
+        first = s.sample(12).copy()
+        second = s.sample(19)  # starts from the current state: 18 new transitions
+        assert np.array_equal(second[:, 0], first[:, -1])
+        assert np.array_equal(np.concatenate([first, second[:, 1:]], axis=1), whole)
+
+
+def test_sample_semantics(golden):
+    g = golden("traj_c1")
+    pdf = mixture(g["mus"])
+    x0 = np.array([-0.86, 0.19, -0.47])
+    s = gs.ShrinkageSphericalSliceSampler(pdf, x0, 3521, dtype="float64")
+    out = s.sample(1000, 100)
+    assert out.shape == (1000, 3) and out.dtype == F64
+    assert s.rng.steps_done == 1099  # n + burnin - 1 transitions (mcmc.py:67-68)
+    allout = gs.ShrinkageSphericalSliceSampler(pdf, x0, 3521, dtype="float64").sample(1000, 100, return_all_samples=True)
+    assert allout.shape == (1100, 3) and np.array_equal(allout[0], x0) and np.array_equal(allout[100:], out)
+    frac = gs.ShrinkageSphericalSliceSampler(pdf, x0, 3521, dtype="float64").sample(1000, 0.1)
+    assert np.array_equal(frac, out)
+    # norms relax towards 1 but the initial state is not normalised (README.md:52)
+    assert abs(np.linalg.norm(allout[0]) - 1) > 1e-3 and np.all(np.abs(np.linalg.norm(out, axis=1) - 1) < 0.05)
+    # iterator protocol + counters
+    it = gs.RejectionSphericalSliceSampler(pdf, x0, 1, dtype="float64")
+    gs.MixtureModel.log_prob.reset_counters()
+    y = next(it)
+    assert y.shape == (3,) and np.array_equal(y, it.state)
+    rejected = it.n_reject  # reading it folds the device counters into log_prob.num_calls
+    assert gs.MixtureModel.log_prob.num_calls == 2 + rejected
+    with pytest.raises(AssertionError):
+        it.sample(0)
+    # torch in -> torch out, on the device
+    xt = torch.as_tensor(gs.sample_sphere(2, 64, seed=1)).cuda()
+    tt = gs.ShrinkageSphericalSliceSampler(pdf, xt, 7).sample(50, 10)
+    assert isinstance(tt, torch.Tensor) and tt.is_cuda and tuple(tt.shape) == (64, 50, 3)
+
+
+def test_host_entry_point_equals_device_run(golden):
+    import ctypes as C
+    g = golden("traj_c2")
+    pdf = mixture(100.0 * g["modes"])
+    N, n, burn = 300, 40, 7
+    x0 = np.ascontiguousarray(gs.sample_sphere(9, N, seed=8))
+    want = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5).sample(n, burn)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty((n, N, 10), dtype=torch.float32, pin_memory=True)
+    nrej = np.zeros(N, dtype=np.uint64)
+    _lib.check(_lib.lib().geosss_sample_host(pdf._handle(dev), _lib.SHRINK, _lib.F32, _lib.PATH_FAST, N, _lib.dptr(x0), 5, 0,
+                                             n, burn, out.data_ptr(), nrej.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(out.numpy().transpose(1, 0, 2), want)
+    assert nrej.sum() > 0
+    out0 = torch.empty((n, N, 10), dtype=torch.float32, pin_memory=True)
+    _lib.check(_lib.lib().geosss_sample_host(pdf._handle(dev), _lib.SHRINK, _lib.F32, _lib.PATH_FAST, N, _lib.dptr(x0), 5, 0,
+                                             n, 0, out0.data_ptr(), None))
+    assert np.array_equal(out0.numpy()[0], x0.astype(F32))
+
+
+# ------------------------------------------------------------------ statistical agreement under own RNG
+def ks_2samp_p(a, b):
+    from scipy.stats import ks_2samp
+    return ks_2samp(a, b).pvalue
+
+
+@pytest.mark.parametrize("cls", [gs.ShrinkageSphericalSliceSampler, gs.RejectionSphericalSliceSampler])
+@pytest.mark.parametrize("path", ["fast", "literal"])
+def test_marginals_match_exact_vmf_mixture(cls, path):
+    """Final states of many independent chains are i.i.d.; compare with exact Wood draws."""
+    mus = np.array([[6.0, 0, 0, 0, 0], [0, -4.0, 3.0, 0, 0], [0, 0, 0, 5.0, -2.0]])
+    w = np.array([0.5, 0.3, 0.2])
+    pdf = mixture(mus, w)
+    N = 8192
+    x0 = gs.sample_sphere(4, N, seed=21)
+    burn = 150 if cls is gs.ShrinkageSphericalSliceSampler else 40
+    got = cls(pdf, x0, 77, path=path).sample(1, burn)[:, 0].astype(float)
+    ref = exact.wood_vmf_mixture(mus, w, N, seed=5)
+    assert np.allclose(np.linalg.norm(got, axis=1), 1, atol=1e-4)
+    for j in range(5):
+        assert ks_2samp_p(got[:, j], ref[:, j]) > 1e-3, j
+    for m in mus:
+        assert ks_2samp_p(got @ m, ref @ m) > 1e-3

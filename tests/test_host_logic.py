@@ -1,0 +1,106 @@
+"""CPU tests of the host-side mirror and of the C-ABI surface (no compute calls: no GPU here)."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import geosss_b200 as gs
+from geosss_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "geosss_cuda.h")).read()
+    declared = set(re.findall(r"\b(geosss_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().geosss_version() == 100
+
+
+def test_bad_arguments_are_rejected_before_touching_the_gpu():
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.geosss_target_create_vmf_mixture(1, 1, None, None, None, C.byref(h)) == _lib.E_INVALID
+    assert b"vmf_mixture" in lib.geosss_last_error()
+    A = np.array([[1.0, 2.0], [0.0, 1.0]])
+    assert lib.geosss_target_create_bingham(2, _lib.dptr(A), None, C.byref(h)) == _lib.E_INVALID
+    assert b"symmetric" in lib.geosss_last_error()
+    assert lib.geosss_sampler_create(None, 1, 0, 0, 10, 0, 0, C.byref(h)) == _lib.E_INVALID
+    assert lib.geosss_log_prob(None, 0, 0, None, None, 1, None) == _lib.E_INVALID
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pdf = gs.MixtureModel([gs.VonMisesFisher(np.array([3.0, 0, 0]))])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pdf.log_prob(np.array([1.0, 0, 0]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gs.ShrinkageSphericalSliceSampler(pdf, np.array([1.0, 0, 0]), 1).sample(3)
+
+
+def test_burnin_rule_and_constructor_checks():
+    assert gs.determine_burnin(1000, 100) == 100 and gs.determine_burnin(1000, 0.2) == 200
+    with pytest.raises(AssertionError):
+        gs.determine_burnin(10, 2.0)
+    pdf = gs.VonMisesFisher(np.array([3.0, 0, 0]))
+    with pytest.raises(ValueError):
+        gs.ShrinkageSphericalSliceSampler(pdf, np.zeros(4), 1)
+    with pytest.raises(ValueError):
+        gs.ShrinkageSphericalSliceSampler(pdf, np.zeros((2, 2, 3)), 1)
+    with pytest.raises(ValueError):
+        gs.SamplerLauncher(pdf, np.zeros(3), 10).run("nope")
+    with pytest.raises(AssertionError):
+        gs.Bingham(np.array([[1.0, 2.0], [0.0, 1.0]]))
+    with pytest.raises(ValueError):
+        gs.PointCloud(np.zeros((3, 4)))
+    s = gs.ShrinkageSphericalSliceSampler(pdf, np.array([0.998, 0, 0]), np.random.SeedSequence(5))
+    assert s.N == 1 and s.d == 3 and np.array_equal(s.state, [0.998, 0, 0])  # not normalised, not copied semantics aside
+    assert s.rng.seed == gs.ShrinkageSphericalSliceSampler(pdf, np.zeros(3), np.random.SeedSequence(5)).rng.seed
+
+
+def test_host_helpers_match_reference_vectors(golden):
+    g = golden("misc")
+    assert np.array_equal(gs.sample_sphere(9, 5, seed=1234), g["sphere_d9_n5_seed1234"])
+    assert np.array_equal(gs.sample_sphere(2, seed=7), g["sphere_d2_seed7"])
+    got = np.array([gs.spherical_projection(a, b) for a, b in zip(g["proj_z"], g["proj_v"])])
+    assert np.array_equal(got, g["proj_out"])
+    assert np.array_equal(gs.radial_projection(g["proj_z"]), g["radial_out"])
+    assert np.array_equal(gs.random_bingham(50, 300, 0, True, 6982).A, g["bingham_c4_A"])
+    assert np.array_equal(gs.random_bingham(10, 30, 0, False, 6982).A, g["bingham_d10_dense_A"])
+    assert np.array_equal(gs.brownian_curve(10, 100, 0.5, seed=4562), g["brownian_c3"])
+    pdf = gs.random_bingham(10, 30, 0, False, 6982)
+    assert np.isclose(pdf.mode @ pdf.A @ pdf.mode, pdf.max_log_prob)
+
+
+def test_slerp_curve_and_quaternions(golden):
+    from oracle import targets
+    g = golden("logprob_curved")
+    curve = gs.SlerpCurve(g["d10_knots"])
+    ora = targets.CurvedVMF(g["d10_knots"], 1.0)
+    for x in g["d10_x"][:20]:
+        assert np.allclose(curve.find_nearest(x), ora.nearest(x), atol=1e-12)
+    assert np.allclose(curve(np.array([0.0, 1.0])), g["d10_knots"][[0, -1]], atol=1e-12)
+    q = golden("logprob_cpd")["c5_q"]
+    for row in q[:10]:
+        R = gs.quat2matrix(row)
+        assert np.allclose(R, targets.quat_to_matrix(row), atol=1e-15)
+        q2 = gs.matrix2quat(R)
+        assert np.allclose(gs.quat2matrix(q2), R, atol=1e-14)
+
+
+def test_counters_are_class_level_like_upstream():
+    gs.VonMisesFisher.log_prob.reset_counters()
+    a, b = gs.VonMisesFisher(np.ones(3)), gs.VonMisesFisher(np.ones(3))
+    a.log_prob.add_calls(3)
+    assert b.log_prob.num_calls == 3 and gs.VonMisesFisher.log_prob.num_calls == 3
+    b.log_prob.reset_counters()
+    assert a.log_prob.num_calls == 0
