@@ -22,7 +22,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -64,44 +63,53 @@ def config_dict(a, n_gpus):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons through NVML every few ms while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.gpu, self.samples, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:
+            self.error = str(exc)
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+        def loop():
+            while not self.stop_flag:
+                try:
+                    self.samples.append((time.perf_counter(), pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                         pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.lines:
-            f = [v.strip() for v in line.split(",")]
-            if len(f) < 8 or not (t0 <= t <= t1 + 0.15):
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "error", "?")]}
+        self.thread.join(timeout=1.0)
+        inside = [(c, r) for t, c, r in self.samples if t0 <= t <= t1]
+        reasons = set()
+        for _, r in inside:
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median([c for c, _ in inside]) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(inside)}
 
 
 def measured_peak_hbm():

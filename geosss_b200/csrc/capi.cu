@@ -247,8 +247,9 @@ template <typename T> static int logp_literal(geosss_target* t, const void* x, v
 }
 
 extern "C" int geosss_log_prob(geosss_target_t t, int dtype, int path, const void* x, void* out, int64_t N, void* stream) {
-    if (!t || !x || !out || N < 0) return fail(GEOSSS_E_INVALID, "log_prob: bad arguments");
+    if (!t || N < 0) return fail(GEOSSS_E_INVALID, "log_prob: bad arguments");
     if (N == 0) return 0;
+    if (!x || !out) return fail(GEOSSS_E_INVALID, "log_prob: null buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (path == GEOSSS_PATH_FAST) {
         if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: the fast path is float32 only");

@@ -63,12 +63,39 @@ __device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float&
     z1 = r * sn;
 }
 
+// Stores the first d of x[0..D) to o, vectorised when d allows (o is 8- resp. 16-byte aligned
+// whenever d is even resp. a multiple of 4, because rows are d floats apart).
+template <int D> __device__ __forceinline__ void store_row(float* __restrict__ o, const float (&x)[D], int d) {
+    if (d == D) {
+#pragma unroll
+        for (int j = 0; j < D; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    } else if (d == D - 2) {
+#pragma unroll
+        for (int j = 0; j < D - 2; j += 2) *reinterpret_cast<float2*>(o + j) = make_float2(x[j], x[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) if (j < d) o[j] = x[j];
+    }
+}
+
+constexpr int FAST_BATCH = 4;  // proposals evaluated together = words of one Philox block
+
+// One transition =
+//   prologue (converged): renormalise x, d normals -> direction u, scores A_k = mu_k.x, B_k = mu_k.u,
+//                         level;
+//   bracket loop (lock-step over the warp): batches of four proposals.  The angles of a batch
+//   depend only on the uniforms and on the SIGNS of earlier angles (mcmc.py:400), never on the
+//   density, so all four are known up front; their densities are evaluated with four-way ILP and
+//   the first accepted one wins -- identical to evaluating them one after the other.
 template <int K, int D, int KIND>
 __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__ VmfFastParams P, RunArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.N) return;
     const int d = P.d;
     constexpr float LN2 = 0.6931471805599453f;
+    const bool aux_in_last = philox_aux_in_last(d);
+    const int nbn = D / 4;                       // normal blocks (D = 4 ceil(d/4))
+    const int pb = aux_in_last ? nbn : nbn + 1;  // first proposal block
 
     float x[D];
     float* st = static_cast<float*>(a.state) + c * d;
@@ -84,7 +111,9 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
     int64_t since_keep = 0, kept = 0;
 
     for (int64_t t = 0; t < a.n_steps; ++t) {
-        dr.begin_step(a.step0 + (uint64_t)t);
+        const uint64_t step = a.step0 + (uint64_t)t;
+        dr.s_lo = (uint32_t)step;
+        dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
 
         // pole: x <- x / |x|
         float xx = 0.f;
@@ -94,14 +123,17 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < D; ++j) x[j] *= inx;
 
-        // direction: u = unit(z - (z.x) x)
+        // direction: u = unit(z - (z.x) x); the level / bracket words ride along (philox.cuh)
         float u[D];
+        uint32_t aux0 = 0, aux1 = 0;
 #pragma unroll
         for (int b = 0; b < D / 4; ++b) {
             U4 r = dr.block(b);
             box_muller_fast(r.x, r.y, u[4 * b], u[4 * b + 1]);
             box_muller_fast(r.z, r.w, u[4 * b + 2], u[4 * b + 3]);
+            if (b == D / 4 - 1) { aux0 = r.z; aux1 = r.w; }
         }
+        if (!aux_in_last) { U4 r = dr.block(nbn); aux0 = r.x; aux1 = r.y; }
 #pragma unroll
         for (int j = 0; j < D; ++j) if (j >= d) u[j] = 0.f;
         float zx = 0.f;
@@ -130,27 +162,49 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - m);
         const float lp2 = m + fast_lg2(s0);
-        const float level2 = lp2 + fast_lg2(dr.level_uniform());
+        const float level2 = lp2 + fast_lg2(u01(aux0, 0.f));
 #pragma unroll
         for (int k = 0; k < K; ++k) G[k] = P.c[k] - level2;
 
         // bracket in half-turns: theta = pi * tt
         float lo, hi;
-        if (KIND == SHRINK) { hi = 2.0f * dr.bracket_uniform(); lo = hi - 2.0f; }
+        if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }
         else { lo = 0.f; hi = 2.0f; }
 
         const int cap = (lp2 > -INFINITY) ? (KIND == SHRINK ? FAST_SHRINK_CAP : MAX_PROPOSALS) : 0;
         float sn = 0.f, cs = 1.f, S = 0.f;
         int r = 0;
         bool moved = false;
-        for (; r < cap; ++r) {
-            const float tt = fmaf(hi - lo, dr.proposal_uniform(r), lo);
-            sincospif(tt, &sn, &cs);
-            S = 0.f;
+        for (int batch = 0; r < cap; ++batch) {
+            const U4 w = dr.block(pb + batch);
+            const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
+            float tt[FAST_BATCH], sb_[FAST_BATCH], cb_[FAST_BATCH], Sb[FAST_BATCH];
+            float lo_ = lo, hi_ = hi;
 #pragma unroll
-            for (int k = 0; k < K; ++k) S += fast_ex2(fmaf(cs, A[k], fmaf(sn, B[k], G[k])));
-            if (S > 1.0f) { moved = true; break; }
-            if (KIND == SHRINK) { if (tt < 0.f) lo = tt; else hi = tt; }
+            for (int i = 0; i < FAST_BATCH; ++i) {
+                tt[i] = fmaf(hi_ - lo_, u01(wi[i], 0.f), lo_);
+                if (KIND == SHRINK) { if (tt[i] < 0.f) lo_ = tt[i]; else hi_ = tt[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < FAST_BATCH; ++i) {
+                sincospif(tt[i], &sb_[i], &cb_[i]);
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc += fast_ex2(fmaf(cb_[i], A[k], fmaf(sb_[i], B[k], G[k])));
+                Sb[i] = acc;
+            }
+            int first = FAST_BATCH;
+#pragma unroll
+            for (int i = FAST_BATCH - 1; i >= 0; --i) if (Sb[i] > 1.0f) first = i;
+            if (first < FAST_BATCH) {
+#pragma unroll
+                for (int i = 0; i < FAST_BATCH; ++i) if (i == first) { sn = sb_[i]; cs = cb_[i]; S = Sb[i]; }
+                r += first;
+                moved = true;
+                break;
+            }
+            r += FAST_BATCH;
+            lo = lo_; hi = hi_;
         }
         if (moved) {
 #pragma unroll
@@ -162,11 +216,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
         if (++since_keep == a.thin) {
             const int64_t k = kept++;
             since_keep = 0;
-            if (samples) {
-                float* o = samples + (k * a.N + c) * d;
-#pragma unroll
-                for (int j = 0; j < D; ++j) if (j < d) o[j] = x[j];
-            }
+            if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
             if (lpo) {
                 // log p of the kept state, natural log; level2 + log2(S) is exact for the accepted point
                 float l2 = moved ? level2 + fast_lg2(S) : lp2;

@@ -10,8 +10,10 @@
 //   key     = (seed lo, seed hi)
 //   counter = (chain lo, chain hi, step lo, (step hi16 << 16) | block)
 //   block b < nb = ceil(d/4): normals 4b..4b+3 (Box-Muller on words (0,1) and (2,3))
-//   block nb   : word0 slice-level uniform, word1 shrink-bracket uniform, word2/3 proposals 0,1
-//   block nb+1+j: proposals 2+4j .. 5+4j
+//   aux words (slice-level uniform, shrink-bracket uniform): words 2,3 of block nb-1 when
+//     d % 4 is 1 or 2 (that Box-Muller pair would be unused), else words 0,1 of block nb
+//   proposals start at block pb (= nb, resp. nb+1): proposal j = word j%4 of block pb + j/4,
+//     so one Philox block feeds one batch of four proposals
 // chain is the GLOBAL chain id, so a chain's trajectory does not depend on how chains are
 // split over GPUs, blocks or launches.
 #pragma once
@@ -58,44 +60,50 @@ template <typename T> GEOSSS_HD void box_muller(uint32_t wa, uint32_t wb, T& z0,
 }
 
 // ------------------------------------------------------------------------------------------
+GEOSSS_HD bool philox_aux_in_last(int d) { return (d & 3) == 1 || (d & 3) == 2; }
+
 template <typename T> struct PhiloxDraws {
     uint32_t k0, k1, c0, c1, s_lo, s_hi;
-    int nb;
+    uint32_t aux0, aux1;  // level / bracket words of the current transition
+    int nb, pb, d_;
     int cached;  // index of the proposal block held in w (-1: none)
     U4 w;
 
     GEOSSS_HD void init(uint64_t seed, uint64_t chain, int d) {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
         c0 = (uint32_t)chain; c1 = (uint32_t)(chain >> 32);
+        d_ = d;
         nb = (d + 3) >> 2;
+        pb = philox_aux_in_last(d) ? nb : nb + 1;
         cached = -1;
     }
     GEOSSS_HD U4 block(int b) const { return philox4x32_10(U4{c0, c1, s_lo, (s_hi << 16) | (uint32_t)b}, k0, k1); }
     GEOSSS_HD void begin_step(uint64_t step) {
         s_lo = (uint32_t)step; s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
-        w = block(nb);
-        cached = nb;
+        cached = -1;
+        if (!philox_aux_in_last(d_)) { U4 a = block(nb); aux0 = a.x; aux1 = a.y; }
     }
     template <class Vec> GEOSSS_HD void fill_normals(Vec z, int d) {
         for (int b = 0; b < nb; ++b) {
             U4 r = block(b);
             T n0, n1, n2, n3;
             box_muller<T>(r.x, r.y, n0, n1);
-            box_muller<T>(r.z, r.w, n2, n3);
             int j = 4 * b;
             z[j] = n0;
             if (j + 1 < d) z[j + 1] = n1;
-            if (j + 2 < d) z[j + 2] = n2;
-            if (j + 3 < d) z[j + 3] = n3;
+            if (j + 2 < d) {
+                box_muller<T>(r.z, r.w, n2, n3);
+                z[j + 2] = n2;
+                if (j + 3 < d) z[j + 3] = n3;
+            } else { aux0 = r.z; aux1 = r.w; }
         }
     }
-    GEOSSS_HD T level_uniform() { return u01(w.x, T(0)); }
-    GEOSSS_HD T bracket_uniform() { return u01(w.y, T(0)); }
+    GEOSSS_HD T level_uniform() { return u01(aux0, T(0)); }
+    GEOSSS_HD T bracket_uniform() { return u01(aux1, T(0)); }
     GEOSSS_HD T proposal_uniform(int j) {
-        if (j < 2) return u01(j == 0 ? w.z : w.w, T(0));
-        int b = nb + 1 + ((j - 2) >> 2);
+        int b = pb + (j >> 2);
         if (b != cached) { w = block(b); cached = b; }
-        int i = (j - 2) & 3;
+        int i = j & 3;
         return u01(i == 0 ? w.x : i == 1 ? w.y : i == 2 ? w.z : w.w, T(0));
     }
     GEOSSS_HD bool ok() const { return true; }

@@ -85,6 +85,8 @@ class Distribution(ABC):
         xd = _device.to_device(x, tdt, dev).reshape(-1, self.d)
         out = torch.empty(xd.shape[0], dtype=tdt, device=dev)
         with torch.cuda.device(dev):
+            if xd.shape[0] == 0:
+                return out if is_torch else out.cpu().numpy()
             _lib.check(_lib.lib().geosss_log_prob(self._handle(dev), code, _lib.PATH_LITERAL, xd.data_ptr(),
                                                    out.data_ptr(), xd.shape[0], _device.stream_ptr(dev)))
         if is_torch:

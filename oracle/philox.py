@@ -10,10 +10,11 @@ call, exactly what chain ``chain`` of the CUDA kernels consumes.
 
 Layout (DESIGN.md "RNG"): key = (seed lo, seed hi); counter =
 (chain lo, chain hi, step lo, (step hi16 << 16) | block).  Within one transition
-blocks 0..ceil(d/4)-1 give the d normals (Box-Muller on word pairs (0,1) and
-(2,3)); block nb = ceil(d/4) gives word0 -> slice-level uniform, word1 -> shrink
-bracket uniform (skipped by the reject sampler), word2/3 -> proposals 0,1; block
-nb+1+j gives proposals 2+4j..5+4j.
+blocks 0..nb-1, nb = ceil(d/4), give the d normals (Box-Muller on word pairs (0,1)
+and (2,3)).  The slice-level and shrink-bracket uniforms ("aux") are words 2,3 of
+block nb-1 when d % 4 is 1 or 2 (that pair would be unused), else words 0,1 of
+block nb.  Proposals start at block pb (= nb, resp. nb + 1): proposal j is word
+j % 4 of block pb + j // 4.  The reject sampler skips the bracket word.
 """
 
 import numpy as np
@@ -67,6 +68,8 @@ class PhiloxChainRNG:
         self.dtype = np.dtype(dtype)
         self.step = first_step - 1
         self.nb = (d + 3) // 4
+        self.aux_in_last = d % 4 in (1, 2)
+        self.pb = self.nb if self.aux_in_last else self.nb + 1
         self._cache = {}
         self.prop = 0
         self.bracket_pending = False
@@ -79,6 +82,9 @@ class PhiloxChainRNG:
                    self.step & 0xFFFFFFFF, ((self.step >> 32) << 16) | b)
             got = self._cache[b] = philox4x32_10(ctr, self.key)
         return got
+
+    def _aux(self, i):
+        return self._block(self.nb - 1)[2 + i] if self.aux_in_last else self._block(self.nb)[i]
 
     def standard_normal(self, n):
         assert n == self.d
@@ -94,17 +100,15 @@ class PhiloxChainRNG:
         return z[:n]
 
     def random(self):
-        return u01(self._block(self.nb)[0], self.dtype)
+        return u01(self._aux(0), self.dtype)
 
     def _next_uniform(self):
         if self.bracket_pending:
             self.bracket_pending = False
-            return u01(self._block(self.nb)[1], self.dtype)
+            return u01(self._aux(1), self.dtype)
         j = self.prop
         self.prop += 1
-        if j < 2:
-            return u01(self._block(self.nb)[2 + j], self.dtype)
-        return u01(self._block(self.nb + 1 + (j - 2) // 4)[(j - 2) % 4], self.dtype)
+        return u01(self._block(self.pb + j // 4)[j % 4], self.dtype)
 
     def uniform(self, a, b):
         return a + (b - a) * self._next_uniform()

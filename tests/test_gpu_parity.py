@@ -301,14 +301,19 @@ def ks_2samp_p(a, b):
 @pytest.mark.parametrize("path", ["fast", "literal"])
 def test_marginals_match_exact_vmf_mixture(cls, path):
     """Final states of many independent chains are i.i.d.; compare with exact Wood draws."""
+    from scipy.special import i0, iv
     mus = np.array([[6.0, 0, 0, 0, 0], [0, -4.0, 3.0, 0, 0], [0, 0, 0, 5.0, -2.0]])
     w = np.array([0.5, 0.3, 0.2])
     pdf = mixture(mus, w)
+    # The reference's component "normaliser" is 2 pi i0(kappa) whatever d is (distributions.py:157), so
+    # with unequal kappas the mixture's true component masses are w_k Z_d(kappa_k) / (2 pi i0(kappa_k)).
+    kap = np.linalg.norm(mus, axis=1)
+    w_eff = w * ((2 * np.pi) ** 2.5 * iv(1.5, kap) / kap**1.5) / (2 * np.pi * i0(kap))
     N = 8192
     x0 = gs.sample_sphere(4, N, seed=21)
     burn = 150 if cls is gs.ShrinkageSphericalSliceSampler else 40
     got = cls(pdf, x0, 77, path=path).sample(1, burn)[:, 0].astype(float)
-    ref = exact.wood_vmf_mixture(mus, w, N, seed=5)
+    ref = exact.wood_vmf_mixture(mus, w_eff, N, seed=5)
     assert np.allclose(np.linalg.norm(got, axis=1), 1, atol=1e-4)
     for j in range(5):
         assert ks_2samp_p(got[:, j], ref[:, j]) > 1e-3, j

@@ -188,20 +188,28 @@ def test_philox_known_answers():
 
 
 def test_philox_chain_rng_layout():
+    # d = 10: aux words ride in the last normal block, proposals start at block 3
     rng = philox.PhiloxChainRNG(seed=12345, chain=7, kind=samplers.SHRINK, d=10, dtype=np.float32)
     z = rng.standard_normal(10)
     assert z.shape == (10,) and np.all(np.isfinite(z))
     u = rng.random()
-    assert 0 < u < 1
     t0 = rng.uniform(0, 1)
     p = [rng.uniform(0, 1) for _ in range(7)]
+    last = philox.philox4x32_10((7, 0, 0, 2), (12345, 0))
+    assert u == philox.u01(last[2], np.float32) and t0 == philox.u01(last[3], np.float32)
     blk = philox.philox4x32_10((7, 0, 0, 3), (12345, 0))
-    assert u == philox.u01(blk[0], np.float32) and t0 == philox.u01(blk[1], np.float32)
-    assert p[0] == philox.u01(blk[2], np.float32) and p[1] == philox.u01(blk[3], np.float32)
+    assert p[:4] == [philox.u01(w, np.float32) for w in blk]
     blk2 = philox.philox4x32_10((7, 0, 0, 4), (12345, 0))
-    assert p[2:6] == [philox.u01(w, np.float32) for w in blk2]
+    assert p[4:7] == [philox.u01(w, np.float32) for w in blk2[:3]]
     # reject sampler skips the bracket word
     rj = philox.PhiloxChainRNG(seed=12345, chain=7, kind=samplers.REJECT, d=10, dtype=np.float32)
     rj.standard_normal(10)
     rj.random()
     assert rj.uniform(0, 1) == p[0]
+    # d = 4: dedicated aux block 1, proposals from block 2; second transition uses step 1
+    r4 = philox.PhiloxChainRNG(seed=1, chain=0, kind=samplers.SHRINK, d=4, dtype=np.float64)
+    r4.standard_normal(4)
+    r4.standard_normal(4)
+    aux = philox.philox4x32_10((0, 0, 1, 1), (1, 0))
+    assert r4.random() == philox.u01(aux[0], np.float64) and r4.uniform(0, 1) == philox.u01(aux[1], np.float64)
+    assert r4.uniform(0, 1) == philox.u01(philox.philox4x32_10((0, 0, 1, 2), (1, 0))[0], np.float64)
