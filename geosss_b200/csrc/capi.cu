@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -340,6 +341,9 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     RunArgs a{};
     a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
     a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
+    // quorum of the persistent bracket loop (kernels_fast.cuh); tuned on B200, see DESIGN.md
+    a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 14;
+    if (const char* q = std::getenv("GEOSSS_QUORUM")) { int v = std::atoi(q); if (v >= 1 && v <= 32) a.quorum = v; }
     return a;
 }
 

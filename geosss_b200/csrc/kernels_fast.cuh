@@ -80,102 +80,162 @@ template <int D> __device__ __forceinline__ void store_row(float* __restrict__ o
 
 constexpr int FAST_BATCH = 4;  // proposals evaluated together = words of one Philox block
 
-// One transition =
-//   prologue (converged): renormalise x, d normals -> direction u, scores A_k = mu_k.x, B_k = mu_k.u,
-//                         level;
-//   bracket loop (lock-step over the warp): batches of four proposals.  The angles of a batch
-//   depend only on the uniforms and on the SIGNS of earlier angles (mcmc.py:400), never on the
-//   density, so all four are known up front; their densities are evaluated with four-way ILP and
-//   the first accepted one wins -- identical to evaluating them one after the other.
+// log2 p at the accepted point: level2 + log2(S) is exact for it; when S overflowed fp32 the
+// mixture is evaluated directly with a max shift.
+template <int K>
+__device__ __forceinline__ float kept_log2p(bool moved, float level2, float S, float lp2, float cs, float sn,
+                                            const float (&A)[K], const float (&B)[K], const float* cst) {
+    float l2 = moved ? level2 + fast_lg2(S) : lp2;
+    if (!(l2 < INFINITY)) {
+        float mm = -INFINITY, e[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { e[k] = fmaf(cs, A[k], sn * B[k]) + cst[k]; mm = fmaxf(mm, e[k]); }
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) ss += fast_ex2(e[k] - mm);
+        l2 = mm + fast_lg2(ss);
+    }
+    return l2;
+}
+
+// Persistent bracket loop with quorum scheduling.
+//
+// A transition has two parts with very different shapes: a fixed-cost PROLOGUE (renormalise x,
+// d normals -> direction u, scores A_k = mu_k.x, B_k = mu_k.u, level) and a BRACKET LOOP whose
+// trip count differs from chain to chain (geosss/mcmc.py:394-401; p99/mean of the rejection count
+// is ~3 for shrink and ~7 for reject).  Run in lock-step, the 32 chains of a
+// warp would all wait for the slowest one.  Here every lane owns its chain's step counter and the
+// warp keeps iterating
+//     vote;  if >= quorum lanes wait for a new transition (or nobody is in a loop): those lanes
+//            apply their accepted move, store the sample and run the prologue;
+//            lanes inside a bracket loop evaluate their next batch of proposals;
+// so that lanes drift apart by a few transitions instead of idling.  The quorum trades idle lanes
+// in the prologue against idle lanes in the loop (quorum 32 = lock-step).  Per-chain results do not
+// depend on the schedule: every draw is addressed by (seed, chain, step, block).
+//
+// A batch is four proposals.  The angles of a batch depend only on the uniforms and on the SIGNS
+// of the earlier angles (mcmc.py:400), never on the density, so all four are known up front; their
+// densities are evaluated with four-way ILP and the first accepted one wins -- identical to
+// evaluating them one after the other.
 template <int K, int D, int KIND>
 __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__ VmfFastParams P, RunArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.N) return;
+    const bool live = c < a.N;  // lanes past the end still vote
     const int d = P.d;
     constexpr float LN2 = 0.6931471805599453f;
     const bool aux_in_last = philox_aux_in_last(d);
     const int nbn = D / 4;                       // normal blocks (D = 4 ceil(d/4))
     const int pb = aux_in_last ? nbn : nbn + 1;  // first proposal block
+    const int quorum = a.quorum;
+    const int n_steps = (int)a.n_steps;
 
-    float x[D];
-    float* st = static_cast<float*>(a.state) + c * d;
+    float x[D], u[D];
+    float* st = static_cast<float*>(a.state) + (live ? c : 0) * d;
 #pragma unroll
-    for (int j = 0; j < D; ++j) x[j] = j < d ? st[j] : 0.0f;
+    for (int j = 0; j < D; ++j) { x[j] = (live && j < d) ? st[j] : 0.0f; u[j] = 0.f; }
 
     PhiloxDraws<float> dr;
     dr.init(a.seed, a.chain0 + (uint64_t)c, d);
-    unsigned long long rej_total = a.n_reject[c];
+    unsigned long long rej_total = live ? a.n_reject[c] : 0ull;
     unsigned int rej_window = 0;
     float* samples = static_cast<float*>(a.samples);
     float* lpo = static_cast<float*>(a.logp);
-    int64_t since_keep = 0, kept = 0;
+    int since_keep = 0;
+    int64_t kept = 0;
 
-    for (int64_t t = 0; t < a.n_steps; ++t) {
-        const uint64_t step = a.step0 + (uint64_t)t;
-        dr.s_lo = (uint32_t)step;
-        dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
+    float A[K], B[K], G[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { A[k] = 0.f; B[k] = 0.f; G[k] = 0.f; }
+    float lo = 0.f, hi = 2.f, level2 = 0.f, lp2 = 0.f;
+    float sn = 0.f, cs = 1.f, S = 0.f;  // the accepted proposal, applied at the next prologue
+    int t = live ? 0 : n_steps;         // transitions started by this lane
+    int r = 0, batch = 0, cap = 0;
+    bool inloop = false, pending = false, moved = false;
 
-        // pole: x <- x / |x|
-        float xx = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) xx = fmaf(x[j], x[j], xx);
-        const float inx = rsqrtf(xx);
-#pragma unroll
-        for (int j = 0; j < D; ++j) x[j] *= inx;
+    while (true) {
+        const bool need = !inloop && t < n_steps;
+        const unsigned m_need = __ballot_sync(0xffffffffu, need);
+        const unsigned m_loop = __ballot_sync(0xffffffffu, inloop);
+        if ((m_need | m_loop) == 0u) break;
 
-        // direction: u = unit(z - (z.x) x); the level / bracket words ride along (philox.cuh)
-        float u[D];
-        uint32_t aux0 = 0, aux1 = 0;
+        if (m_loop == 0u || __popc(m_need) >= quorum) {
+            if (need) {
+                // ---- finish the previous transition: move, store ----
+                if (pending) {
+                    if (moved) {
 #pragma unroll
-        for (int b = 0; b < D / 4; ++b) {
-            U4 r = dr.block(b);
-            box_muller_fast(r.x, r.y, u[4 * b], u[4 * b + 1]);
-            box_muller_fast(r.z, r.w, u[4 * b + 2], u[4 * b + 3]);
-            if (b == D / 4 - 1) { aux0 = r.z; aux1 = r.w; }
+                        for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+                    }
+                    rej_total += (unsigned)r;
+                    rej_window += (unsigned)r;
+                    if (++since_keep == (int)a.thin) {
+                        const int64_t k = kept++;
+                        since_keep = 0;
+                        if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
+                        if (lpo) lpo[k * a.N + c] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                        if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+                        rej_window = 0;
+                    }
+                    pending = false;
+                }
+                // ---- prologue of transition t ----
+                const uint64_t step = a.step0 + (uint64_t)t;
+                dr.s_lo = (uint32_t)step;
+                dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
+                float xx = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) xx = fmaf(x[j], x[j], xx);
+                const float inx = rsqrtf(xx);
+#pragma unroll
+                for (int j = 0; j < D; ++j) x[j] *= inx;
+
+                uint32_t aux0 = 0, aux1 = 0;
+#pragma unroll
+                for (int b = 0; b < D / 4; ++b) {
+                    U4 w = dr.block(b);
+                    box_muller_fast(w.x, w.y, u[4 * b], u[4 * b + 1]);
+                    box_muller_fast(w.z, w.w, u[4 * b + 2], u[4 * b + 3]);
+                    if (b == D / 4 - 1) { aux0 = w.z; aux1 = w.w; }
+                }
+                if (!aux_in_last) { U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
+#pragma unroll
+                for (int j = 0; j < D; ++j) if (j >= d) u[j] = 0.f;
+                float zx = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) zx = fmaf(u[j], x[j], zx);
+                float pp = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) { u[j] = fmaf(-zx, x[j], u[j]); pp = fmaf(u[j], u[j], pp); }
+                const float inp = rsqrtf(pp);
+#pragma unroll
+                for (int j = 0; j < D; ++j) u[j] *= inp;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float sa = 0.f, sb = 0.f;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) { sa = fmaf(P.mu[k * D + j], x[j], sa); sb = fmaf(P.mu[k * D + j], u[j], sb); }
+                    A[k] = sa; B[k] = sb;
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < K; ++k) mx = fmaxf(mx, A[k] + P.c[k]);
+                float s0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - mx);
+                lp2 = mx + fast_lg2(s0);
+                level2 = lp2 + fast_lg2(u01(aux0, 0.f));
+#pragma unroll
+                for (int k = 0; k < K; ++k) G[k] = P.c[k] - level2;
+                if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }  // half-turns: theta = pi * tt
+                else { lo = 0.f; hi = 2.0f; }
+                cap = (lp2 > -INFINITY) ? (KIND == SHRINK ? FAST_SHRINK_CAP : MAX_PROPOSALS) : 0;
+                r = 0; batch = 0; moved = false;
+                ++t;
+                if (cap > 0) inloop = true; else pending = true;  // density is -inf/NaN everywhere: stay
+            }
         }
-        if (!aux_in_last) { U4 r = dr.block(nbn); aux0 = r.x; aux1 = r.y; }
-#pragma unroll
-        for (int j = 0; j < D; ++j) if (j >= d) u[j] = 0.f;
-        float zx = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) zx = fmaf(u[j], x[j], zx);
-        float pp = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) { u[j] = fmaf(-zx, x[j], u[j]); pp = fmaf(u[j], u[j], pp); }
-        const float inp = rsqrtf(pp);
-#pragma unroll
-        for (int j = 0; j < D; ++j) u[j] *= inp;
 
-        // scores along the great circle (log2 units)
-        float A[K], B[K], G[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            float sa = 0.f, sb = 0.f;
-#pragma unroll
-            for (int j = 0; j < D; ++j) { sa = fmaf(P.mu[k * D + j], x[j], sa); sb = fmaf(P.mu[k * D + j], u[j], sb); }
-            A[k] = sa; B[k] = sb;
-        }
-        float m = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < K; ++k) m = fmaxf(m, A[k] + P.c[k]);
-        float s0 = 0.f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - m);
-        const float lp2 = m + fast_lg2(s0);
-        const float level2 = lp2 + fast_lg2(u01(aux0, 0.f));
-#pragma unroll
-        for (int k = 0; k < K; ++k) G[k] = P.c[k] - level2;
-
-        // bracket in half-turns: theta = pi * tt
-        float lo, hi;
-        if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }
-        else { lo = 0.f; hi = 2.0f; }
-
-        const int cap = (lp2 > -INFINITY) ? (KIND == SHRINK ? FAST_SHRINK_CAP : MAX_PROPOSALS) : 0;
-        float sn = 0.f, cs = 1.f, S = 0.f;
-        int r = 0;
-        bool moved = false;
-        for (int batch = 0; r < cap; ++batch) {
+        if (inloop) {
             const U4 w = dr.block(pb + batch);
             const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
             float tt[FAST_BATCH], sb_[FAST_BATCH], cb_[FAST_BATCH], Sb[FAST_BATCH];
@@ -200,44 +260,36 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < FAST_BATCH; ++i) if (i == first) { sn = sb_[i]; cs = cb_[i]; S = Sb[i]; }
                 r += first;
-                moved = true;
-                break;
+                moved = true; inloop = false; pending = true;
+            } else {
+                r += FAST_BATCH;
+                lo = lo_; hi = hi_;
+                ++batch;
+                if (r >= cap) { inloop = false; pending = true; }  // cap reached: stay at x
             }
-            r += FAST_BATCH;
-            lo = lo_; hi = hi_;
-        }
-        if (moved) {
-#pragma unroll
-            for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
-        }
-        rej_total += (unsigned)r;
-        rej_window += (unsigned)r;
-
-        if (++since_keep == a.thin) {
-            const int64_t k = kept++;
-            since_keep = 0;
-            if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
-            if (lpo) {
-                // log p of the kept state, natural log; level2 + log2(S) is exact for the accepted point
-                float l2 = moved ? level2 + fast_lg2(S) : lp2;
-                if (!(l2 < INFINITY)) {  // S overflowed: evaluate directly
-                    float mm = -INFINITY, e[K];
-#pragma unroll
-                    for (int kk = 0; kk < K; ++kk) { e[kk] = fmaf(cs, A[kk], sn * B[kk]) + P.c[kk]; mm = fmaxf(mm, e[kk]); }
-                    float ss = 0.f;
-#pragma unroll
-                    for (int kk = 0; kk < K; ++kk) ss += fast_ex2(e[kk] - mm);
-                    l2 = mm + fast_lg2(ss);
-                }
-                lpo[k * a.N + c] = l2 * LN2;
-            }
-            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
-            rej_window = 0;
         }
     }
+
+    // flush the last transition of every lane (converged)
+    if (live) {
+        if (pending) {
+            if (moved) {
 #pragma unroll
-    for (int j = 0; j < D; ++j) if (j < d) st[j] = x[j];
-    a.n_reject[c] = rej_total;
+                for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+            }
+            rej_total += (unsigned)r;
+            rej_window += (unsigned)r;
+            if (++since_keep == (int)a.thin) {
+                const int64_t k = kept++;
+                if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
+                if (lpo) lpo[k * a.N + c] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) if (j < d) st[j] = x[j];
+        a.n_reject[c] = rej_total;
+    }
 }
 
 // ------------------------------------------------------------------ host-side dispatch
@@ -250,6 +302,7 @@ inline int fast_supported(int target_kind, int d, int K, int single) {
 
 template <int K, int D> static int launch_vmf_fast_kd(int kind, const VmfFastParams& P, const RunArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.N + FAST_BLOCK - 1) / FAST_BLOCK);
+    if (a.n_steps > 0x7fffffff) return -1;
     if (kind == SHRINK) k_vmf_fast<K, D, SHRINK><<<grid, FAST_BLOCK, 0, st>>>(P, a);
     else k_vmf_fast<K, D, REJECT><<<grid, FAST_BLOCK, 0, st>>>(P, a);
     return (int)cudaGetLastError();

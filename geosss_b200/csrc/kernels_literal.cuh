@@ -72,6 +72,7 @@ struct RunArgs {
     uint32_t* nrej;       // (n_keep, N) rejections of each kept transition (thin == 1) or null
     unsigned long long* n_reject;  // (N) running totals
     int* status;          // (N) tape mode: 0 ok, 1 tape exhausted; may be null
+    int quorum;           // fast path: lanes that must wait before a warp runs the prologue (32 = lock-step)
 };
 
 template <typename T, int KIND, bool TAPE> struct DrawsOf;
