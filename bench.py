@@ -222,16 +222,16 @@ def main_ours(a):
     algo_bytes = N * T * d * 4
     achieved = algo_bytes / avg_launch_s / 1e9
 
-    # ESS of the first coordinate over the last retained step (64 chains, oracle estimator; diagnostics only)
+    # ESS of the first coordinate (scripts/ess_mixture_vMF.py:233) over the last retained step, all chains of
+    # all ranks: autocovariances on the GPU (csrc/diag.cuh), max_lag+2 doubles all-reduced, Geyer cut on the host
+    from geosss_b200 import diagnostics
     ess = None
-    if rank == 0:
-        try:
-            from oracle import ess as ess_mod
-            tr = buf[:, :64, 0].t().contiguous().cpu().numpy().astype(np.float64)
-            rel = ess_mod.ess_multichain(tr, min(T // 2, 400)) / tr.size
-            ess = {"relative_ess_x0": rel, "ess_per_sec": rel * value, "chains_used": 64, "draws": T}
-        except Exception as exc:  # diagnostics must not break the bench line
-            ess = {"error": str(exc)}
+    try:
+        n_ess, rel = diagnostics.ess(buf, None, min(T // 2, 400))
+        ess = {"relative_ess_x0": rel, "ess_per_sec": rel * value, "chains_used": N * world, "draws": T,
+               "estimator": "multi-chain autocovariance ESS (Vehtari et al. 2021), device partial sums"}
+    except Exception as exc:  # diagnostics must not break the bench line
+        ess = {"error": str(exc)}
 
     # ---- end to end through the public API with host buffers ---------------------------------
     x0_host = np.ascontiguousarray(x0)
@@ -241,6 +241,16 @@ def main_ours(a):
         s.sample(T + 1, 0, out=out_host)  # H2D of the initial states, T transitions, D2H of every state
         return s
     e2e_step(1)
+    # raw pinned device->host bandwidth of this box, for context (the e2e number is PCIe-bound)
+    probe = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    host_probe = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+    host_probe.copy_(probe)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    for _ in range(4):
+        host_probe.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = 4 * (64 << 20) / (time.perf_counter() - tp) / 1e9
     barrier()
     t0 = time.perf_counter()
     for i in range(a.e2e_steps):
@@ -263,10 +273,10 @@ def main_ours(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": a.e2e_steps, "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
+                        "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs, "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
                 "gpu_launches": a.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<5,12,SHRINK>",
+                             "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
                              "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
                              "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
                 "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,

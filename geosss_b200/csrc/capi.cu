@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/geosss_cuda.h"
+#include "diag.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_literal.cuh"
 
@@ -490,4 +491,26 @@ extern "C" int geosss_sample_host(geosss_target_t t, int kind, int dtype, int pa
     if (!rc && n_reject_host) rc = geosss_sampler_get_state_host(s, nullptr, n_reject_host);
     geosss_sampler_destroy(s);
     return rc;
+}
+
+// ------------------------------------------------------------------ diagnostics
+extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int64_t n_draws, int64_t n_chains, int d,
+                                        const void* direction, int max_lag, double* out, void* stream) {
+    if (!samples || !direction || !out || n_draws < 2 || n_chains < 1 || d < 1 || max_lag < 1 || max_lag > n_draws)
+        return fail(GEOSSS_E_INVALID, "diag_ess_partials: bad arguments");
+    const size_t smem = (size_t)n_draws * sizeof(float);
+    if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "diag_ess_partials: at most 51200 draws per chain per call");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemsetAsync(out, 0, (size_t)(max_lag + 2) * sizeof(double), st));
+    if (dtype == GEOSSS_F64) {
+        CU(cudaFuncSetAttribute(k_ess_partials<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ess_partials<double><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const double*>(samples), n_draws, n_chains, d,
+                                                                             static_cast<const double*>(direction), max_lag, out);
+    } else {
+        CU(cudaFuncSetAttribute(k_ess_partials<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ess_partials<float><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const float*>(samples), n_draws, n_chains, d,
+                                                                            static_cast<const float*>(direction), max_lag, out);
+    }
+    CU(cudaGetLastError());
+    return 0;
 }

@@ -1,0 +1,58 @@
+// Device diagnostics: partial sums for the multi-chain effective sample size of a scalar test
+// function f(x) = x . v (v = e_0 gives the first coordinate the upstream scripts use,
+// scripts/ess_mixture_vMF.py:233; v = mode gives scripts/bingham.py:50-52).
+//
+// Restates the autocovariance step of geosss/utils.py:109-112 (acf) per chain, in the direct
+// (non-circular, biased 1/n) form that the multi-chain estimator of Vehtari et al. (2021) uses
+// (oracle/ess.py:ess_multichain).  One block per chain: the chain's centred trace is staged in
+// shared memory, lags are spread over the threads, and the block adds its chain's
+// autocovariances into global double accumulators -- O(L) doubles leave the GPU, which is what
+// gets all-reduced over NVLink when chains are sharded over GPUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace geosss {
+
+constexpr int DIAG_BLOCK = 256;
+
+// samples: (n, N, d) step-major float; out: max_lag + 2 doubles, zeroed by the caller:
+//   out[l] += acov_c(l) for l < max_lag;  out[max_lag] += mean_c;  out[max_lag+1] += mean_c^2
+template <typename T>
+__global__ void __launch_bounds__(DIAG_BLOCK) k_ess_partials(const T* __restrict__ samples, int64_t n, int64_t N, int d,
+                                                             const T* __restrict__ v, int max_lag, double* __restrict__ out) {
+    extern __shared__ float trace[];  // n floats
+    __shared__ double red[DIAG_BLOCK / 32];
+    __shared__ double mean_s;
+    const int64_t c = blockIdx.x;
+    double part = 0.0;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const T* row = samples + (t * N + c) * d;
+        double f = 0.0;
+        for (int j = 0; j < d; ++j) f += (double)row[j] * (double)v[j];
+        trace[t] = (float)f;
+        part += f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < DIAG_BLOCK / 32; ++w) s += red[w];
+        mean_s = s / (double)n;
+        atomicAdd(out + max_lag, mean_s);
+        atomicAdd(out + max_lag + 1, mean_s * mean_s);
+    }
+    __syncthreads();
+    const float mean = (float)mean_s;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) trace[t] -= mean;
+    __syncthreads();
+    for (int l = threadIdx.x; l < max_lag; l += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t t = 0; t + l < n; ++t) acc += (double)(trace[t] * trace[t + l]);
+        atomicAdd(out + l, acc / (double)n);
+    }
+}
+
+}  // namespace geosss

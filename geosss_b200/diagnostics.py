@@ -1,0 +1,81 @@
+"""
+Diagnostics on retained samples: multi-chain effective sample size and moments.
+
+The upstream scripts compute relative ESS with ``arviz.ess`` over ``(chains, draws)`` traces of
+the first coordinate (scripts/ess_mixture_vMF.py:233-268) or of ``x . mode``
+(scripts/bingham.py:50-52); the library's own helpers are ``acf`` / ``IAT`` / ``n_eff``
+(geosss/utils.py:91-134).  Here the per-chain autocovariances are accumulated on the GPU
+(csrc/diag.cuh); only ``max_lag + 2`` doubles per GPU are all-reduced when chains are sharded,
+and the Geyer truncation (Vehtari et al. 2021, as restated in oracle/ess.py) runs on the host.
+"""
+
+import math
+
+import numpy as np
+import torch
+
+from . import _device, _lib
+
+
+def ess_from_partials(partials, n_draws, n_chains):
+    """Finish the estimator from summed partials (max_lag autocovariance sums, sum of chain means,
+    sum of squared chain means).  Returns (ess, relative_ess)."""
+    partials = np.asarray(partials, dtype=float)
+    L = len(partials) - 2
+    n, m = float(n_draws), float(n_chains)
+    acov = partials[:L] / m
+    mean_var = acov[0] * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n
+    if n_chains > 1:
+        s1, s2 = partials[L], partials[L + 1]
+        var_plus += (s2 - s1 * s1 / m) / (m - 1.0)
+    rho = 1.0 - (mean_var - acov) / var_plus
+    rho[0] = 1.0
+    tau, prev, t = -1.0, math.inf, 0
+    while t + 1 < L:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        pair = min(pair, prev)
+        prev = pair
+        tau += 2.0 * pair
+        t += 2
+    tau = max(tau, 1.0 / math.log10(m * n))
+    ess = m * n / tau
+    return ess, ess / (m * n)
+
+
+def ess_partials(samples, direction=None, max_lag=None):
+    """Device partial sums for samples of shape (n_draws, n_chains, d) (the step-major layout the
+    kernels write; pass ``result.permute(1, 0, 2)`` of a ``sample()`` output).  CUDA tensor in,
+    CUDA float64 tensor of length max_lag + 2 out."""
+    if not (isinstance(samples, torch.Tensor) and samples.is_cuda):
+        raise ValueError("ess_partials needs a CUDA tensor; there is no CPU fallback")
+    samples = samples.contiguous()
+    n, N, d = samples.shape
+    code, tdt, _ = _device.dtype_code(samples.dtype)
+    max_lag = int(min(n, max_lag if max_lag is not None else n // 2))
+    v = torch.zeros(d, dtype=tdt, device=samples.device)
+    if direction is None:
+        v[0] = 1.0
+    else:
+        v.copy_(torch.as_tensor(np.asarray(direction, dtype=float)))
+    out = torch.empty(max_lag + 2, dtype=torch.float64, device=samples.device)
+    with torch.cuda.device(samples.device):
+        _lib.check(_lib.lib().geosss_diag_ess_partials(samples.data_ptr(), code, n, N, d, v.data_ptr(), max_lag,
+                                                       out.data_ptr(), _device.stream_ptr(samples.device)))
+    return out
+
+
+def ess(samples, direction=None, max_lag=None, group=None):
+    """Multi-chain ESS of x . direction (default: first coordinate).  With a torch.distributed
+    ``group`` (or the default group when initialised) the partial sums are all-reduced, so every
+    rank returns the ESS of ALL chains of all ranks."""
+    import torch.distributed as dist
+    part = ess_partials(samples, direction, max_lag)
+    n, N, _ = samples.shape
+    total = torch.tensor([float(N)], dtype=torch.float64, device=samples.device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(part, group=group)
+        dist.all_reduce(total, group=group)
+    return ess_from_partials(part.cpu().numpy(), n, int(total.item()))

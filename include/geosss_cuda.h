@@ -132,6 +132,16 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
                        int64_t n_samples, int64_t burnin, void* samples_host,
                        uint64_t* n_reject_host);
 
+/* ---- diagnostics ("next" row of the scope table: ESS half of the metric) --------------------- */
+
+/* Partial sums for the multi-chain ESS of f(x) = x . direction over samples (n_draws, n_chains, d)
+ * (step-major, device, `dtype`); direction: (d) device, `dtype`.  out: (max_lag + 2) doubles on the
+ * device: out[l] = sum over chains of the biased autocovariance at lag l (geosss/utils.py:91-112
+ * per chain), out[max_lag] = sum of chain means, out[max_lag + 1] = sum of squared chain means.
+ * The sums are additive over chain shards, so ranks all-reduce `out` and finish on the host. */
+int geosss_diag_ess_partials(const void* samples, int dtype, int64_t n_draws, int64_t n_chains, int d,
+                             const void* direction, int max_lag, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
