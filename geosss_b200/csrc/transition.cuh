@@ -56,6 +56,11 @@ GEOSSS_HD int transition_literal(int d, Vec x, Vec u, Vec y, Draws& dr, const Lo
         }
         if (KIND == SHRINK) {
             if (theta < T(0)) lo = theta; else hi = theta;
+            // Bracket collapsed onto theta = 0: every further proposal IS x, and log p(x) > level can
+            // only fail because "log p(x) + log U" rounded onto log p(x) (in
+            // fp32 with |log p| ~ 2400 this happens once per ~1e4 transitions).  The reference would
+            // spin for ever; the chain stays at x, which is always inside the slice.
+            if (!(hi - lo > Const<T>::bracket_floor())) { *lp_new = level; return r + 1; }
         }
         if (!dr.ok()) break;
     }
