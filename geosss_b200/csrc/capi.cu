@@ -12,6 +12,7 @@
 #include "../../include/geosss_cuda.h"
 #include "diag.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_gc.cuh"
 #include "kernels_literal.cuh"
 
 using namespace geosss;
@@ -66,7 +67,7 @@ struct geosss_target {
     Arr mu, logw, logi0;
     std::vector<double> h_mu, h_const;  // host copies for the fast path's parameter block
     // Bingham
-    Arr A, b;
+    Arr A, b, Adiag;
     int has_b = 0, diag = 0;
     // curved vMF
     int M = 0;
@@ -87,7 +88,7 @@ struct geosss_target {
                 (T)log_outlier, (T)beta, nt, ns, k, outlier};
     }
     void release() {
-        for (Arr* a : {&mu, &logw, &logi0, &A, &b, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (Arr* a : {&mu, &logw, &logi0, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
     }
 };
 
@@ -101,6 +102,64 @@ struct geosss_sampler {
     unsigned long long* n_reject = nullptr;
     size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
 };
+
+// ------------------------------------------------------------------ fast-path dispatch
+static size_t gc_smem_bytes(const geosss_target* t, const GcParams& p) {
+    const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p) : CurvedGc::smem_floats(p);
+    return (2 * (size_t)t->d * GC_BLOCK + pol) * sizeof(float);
+}
+
+static GcParams gc_params(const geosss_target* t) {
+    GcParams p{};
+    p.d = t->d;
+    if (t->kind == TGT_BINGHAM) {
+        p.diag = t->diag;
+        p.a0 = t->diag ? t->Adiag.f : t->A.f;
+        p.a1 = t->has_b ? t->b.f : nullptr;
+    } else {
+        p.M = t->M; p.kappa = (float)t->kappa;
+        p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
+    }
+    return p;
+}
+
+// 0 when a float32 throughput kernel exists for this target / shape
+static int target_fast_supported(const geosss_target* t) {
+    if (t->kind == TGT_VMF_MIX) return fast_supported(t->kind, t->d, t->K, t->single);
+    if (t->kind == TGT_BINGHAM || t->kind == TGT_CURVED_VMF) {
+        if (t->kind == TGT_CURVED_VMF && t->M > GC_MAX_KNOTS) return -1;
+        return gc_smem_bytes(t, gc_params(t)) <= 200 * 1024 ? 0 : -1;
+    }
+    return -1;
+}
+
+template <class Policy> static int launch_gc(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {
+    const GcParams p = gc_params(t);
+    const size_t smem = gc_smem_bytes(t, p);
+    const unsigned grid = (unsigned)((a.N + GC_BLOCK - 1) / GC_BLOCK);
+    if (a.n_steps > 0x7fffffff) return fail(GEOSSS_E_INVALID, "run: at most 2^31-1 transitions per call");
+    if (kind == SHRINK) {
+        CU(cudaFuncSetAttribute(k_gc_fast<Policy, SHRINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gc_fast<Policy, SHRINK><<<grid, GC_BLOCK, smem, st>>>(p, a);
+    } else {
+        CU(cudaFuncSetAttribute(k_gc_fast<Policy, REJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gc_fast<Policy, REJECT><<<grid, GC_BLOCK, smem, st>>>(p, a);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {
+    if (t->kind == TGT_VMF_MIX) {
+        int rc = launch_fast(t->kind, kind, t->d, t->K, t->h_mu.data(), t->h_const.data(), a, st);
+        if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));
+        if (rc < 0) return fail(GEOSSS_E_UNSUPPORTED, "run: fast kernel unavailable for this shape");
+        return 0;
+    }
+    if (t->kind == TGT_BINGHAM) return launch_gc<BinghamGc>(t, kind, a, st);
+    if (t->kind == TGT_CURVED_VMF) return launch_gc<CurvedGc>(t, kind, a, st);
+    return fail(GEOSSS_E_UNSUPPORTED, "run: no fast kernel for this target");
+}
 
 extern "C" int geosss_version(void) { return GEOSSS_VERSION; }
 extern "C" const char* geosss_last_error(void) { return g_err; }
@@ -151,6 +210,11 @@ extern "C" int geosss_target_create_bingham(int d, const double* A, const double
     t->kind = TGT_BINGHAM; t->d = d; t->has_b = b ? 1 : 0; t->diag = diag ? 1 : 0;
     int rc = t->A.upload(A, (size_t)d * d);
     if (!rc && b) rc = t->b.upload(b, d);
+    if (!rc && diag) {
+        std::vector<double> dg(d);
+        for (int i = 0; i < d; ++i) dg[i] = A[(size_t)i * d + i];
+        rc = t->Adiag.upload(dg.data(), d);
+    }
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
     return 0;
@@ -268,8 +332,7 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "sampler_create: dtype must be f32 or f64");
     if (path == GEOSSS_PATH_FAST) {
         if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the fast path is float32 only");
-        int rc = fast_supported(t->kind, t->d, t->K, t->single);
-        if (rc) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: no fast kernel for this target / shape");
+        if (target_fast_supported(t)) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: no fast kernel for this target / shape");
     } else if (path != GEOSSS_PATH_LITERAL) return fail(GEOSSS_E_INVALID, "sampler_create: unknown path");
     auto* s = new (std::nothrow) geosss_sampler();
     if (!s) return fail(GEOSSS_E_NOMEM, "out of host memory");
@@ -355,9 +418,7 @@ extern "C" int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RunArgs a = base_args(s, n_steps, thin);
     a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
-    int rc = s->path == GEOSSS_PATH_FAST ? launch_fast(s->t->kind, s->kind, s->t->d, s->t->K, s->t->h_mu.data(), s->t->h_const.data(), a, st)
-                                         : dispatch_literal<false>(s, a, st);
-    if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));
+    int rc = s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
     if (rc) return rc;
     s->step += (uint64_t)n_steps;
     return 0;

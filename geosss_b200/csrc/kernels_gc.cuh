@@ -1,0 +1,295 @@
+// Float32 throughput kernels for targets whose log-density along a great circle has a cheap
+// closed form: Bingham(-Fisher) and the curved vMF.  Same persistent, quorum-scheduled bracket
+// loop as k_vmf_fast (kernels_fast.cuh), but for runtime d up to a few hundred: the chain state x
+// and the direction u live in shared memory in column layout (element j of lane t at
+// [j * BLOCK + t], conflict-free), target parameters are staged into shared memory once per block.
+//
+// With y(theta) = c x + s u (x, u orthonormal):
+//   Bingham   geosss/distributions.py:78-86,113-114
+//             y^T A y - x^T A x = s (s (Quu - Qxx) + 2 c Qxu),   b.y - b.x = (c - 1) bx + s bu
+//             with Qxx = x^T A x, Qxu = x^T A u, Quu = u^T A u: O(1) per proposal, and the slice test
+//             "log p(y) - log p(x) > log U" is cancellation-free.
+//   curved vMF distributions.py:272-275, spherical_curve.py:10-32,95-102
+//             knots.y = c (knots.x) + s (knots.u); per segment (a, b) with angle ang the nearest
+//             point on the arc has x.y = hypot(p1, p2) when its angle t* = atan2(p2, p1) lies in
+//             [0, ang] (p1 = G_a, p2 = (G_b - G_a cos ang) / sin ang), else G_a (t* < 0) or G_b: the
+//             clip(atan2) / sin / arccos chain of the reference reduces to two sign tests and a sqrt.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels_fast.cuh"
+#include "kernels_literal.cuh"
+#include "philox.cuh"
+
+namespace geosss {
+
+constexpr int GC_BLOCK = 64;
+constexpr int GC_MAX_KNOTS = 16;
+
+struct GcParams {
+    const float* a0;  // Bingham: A (d,d) or its diagonal (d);  curved: knots (M,d)
+    const float* a1;  // Bingham: b (d) or null;                 curved: cos(ang) (M-1)
+    const float* a2;  //                                         curved: sin(ang) (M-1)
+    float kappa;
+    int d, M, diag;
+};
+
+// ------------------------------------------------------------------ policies
+struct BinghamGc {
+    struct Coef { float qxx, qxu, quu, bx, bu; };
+    const float* A;  // shared: diagonal (d) or dense (d, d)
+    const float* b;  // shared or null
+    int d, diag;
+
+    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)(p.diag ? p.d : p.d * p.d) + (p.a1 ? p.d : 0); }
+    __device__ void stage(const GcParams& p, float* sm) {
+        d = p.d; diag = p.diag;
+        const int nA = diag ? d : d * d;
+        for (int i = threadIdx.x; i < nA; i += blockDim.x) sm[i] = p.a0[i];
+        if (p.a1) for (int i = threadIdx.x; i < d; i += blockDim.x) sm[nA + i] = p.a1[i];
+        A = sm;
+        b = p.a1 ? sm + nA : nullptr;
+    }
+    __device__ __forceinline__ void begin(Coef& c) const { c.qxx = c.qxu = c.quu = c.bx = c.bu = 0.f; }
+    __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
+        if (diag) {
+            const float l = A[j];
+            c.qxx = fmaf(l * xj, xj, c.qxx); c.qxu = fmaf(l * xj, uj, c.qxu); c.quu = fmaf(l * uj, uj, c.quu);
+        }
+        if (b) { c.bx = fmaf(b[j], xj, c.bx); c.bu = fmaf(b[j], uj, c.bu); }
+    }
+    template <class V> __device__ __forceinline__ void finish(Coef& c, V xs, V us) const {
+        if (diag) return;
+        for (int i = 0; i < d; ++i) {
+            const float* row = A + i * d;
+            float ax = 0.f, au = 0.f;
+            for (int j = 0; j < d; ++j) { const float aij = row[j]; ax = fmaf(aij, xs[j], ax); au = fmaf(aij, us[j], au); }
+            const float xi = xs[i], ui = us[i];
+            c.qxx = fmaf(xi, ax, c.qxx); c.qxu = fmaf(xi, au, c.qxu); c.quu = fmaf(ui, au, c.quu);
+        }
+    }
+    __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const {
+        float dlt = sn * fmaf(sn, c.quu - c.qxx, 2.f * cs * c.qxu);
+        if (b) dlt += fmaf(cs - 1.f, c.bx, sn * c.bu);
+        return dlt;
+    }
+    __device__ __forceinline__ float logp_x(const Coef& c) const { return c.qxx + c.bx; }
+};
+
+struct CurvedGc {
+    struct Coef { float gx[GC_MAX_KNOTS], gu[GC_MAX_KNOTS], best0; };
+    const float* knotsT;  // shared (d, M): knotsT[j * M + m]
+    const float* ca;      // shared (M-1)
+    const float* isa;     // shared (M-1) 1 / (sin(ang) + 1e-10)
+    const float* sa;      // shared (M-1)
+    float kappa;
+    int d, M;
+
+    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)p.M * p.d + 3 * (size_t)(p.M - 1); }
+    __device__ void stage(const GcParams& p, float* sm) {
+        d = p.d; M = p.M; kappa = p.kappa;
+        for (int i = threadIdx.x; i < M * d; i += blockDim.x) { const int m = i / d, j = i - m * d; sm[j * M + m] = p.a0[i]; }
+        float* c_ = sm + M * d;
+        float* is_ = c_ + (M - 1);
+        float* s_ = is_ + (M - 1);
+        for (int i = threadIdx.x; i < M - 1; i += blockDim.x) { c_[i] = p.a1[i]; s_[i] = p.a2[i]; is_[i] = 1.f / (p.a2[i] + 1e-10f); }
+        knotsT = sm; ca = c_; isa = is_; sa = s_;
+    }
+    __device__ __forceinline__ void begin(Coef& c) const {
+#pragma unroll
+        for (int m = 0; m < GC_MAX_KNOTS; ++m) { c.gx[m] = 0.f; c.gu[m] = 0.f; }
+    }
+    __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
+        const float* col = knotsT + j * M;
+#pragma unroll
+        for (int m = 0; m < GC_MAX_KNOTS; ++m) if (m < M) { const float k = col[m]; c.gx[m] = fmaf(k, xj, c.gx[m]); c.gu[m] = fmaf(k, uj, c.gu[m]); }
+    }
+    // max over segments of x(theta) . nearest-point, first segment wins ties (argmin of arccos)
+    __device__ __forceinline__ float best_dot(const Coef& c, float cs, float sn) const {
+        float ga = fmaf(cs, c.gx[0], sn * c.gu[0]);
+        float best = -INFINITY;
+#pragma unroll
+        for (int m = 1; m < GC_MAX_KNOTS; ++m) if (m < M) {
+            const float gb = fmaf(cs, c.gx[m], sn * c.gu[m]);
+            const float p2 = (gb - ga * ca[m - 1]) * isa[m - 1];
+            const bool inside = p2 >= 0.f && fmaf(ga, sa[m - 1], -p2 * ca[m - 1]) >= 0.f;
+            const float dot = inside ? fast_sqrt(fmaf(ga, ga, p2 * p2)) : (p2 < 0.f ? ga : gb);
+            if (dot > best) best = dot;
+            ga = gb;
+        }
+        return best;
+    }
+    template <class V> __device__ __forceinline__ void finish(Coef& c, V, V) const { c.best0 = best_dot(c, 1.f, 0.f); }
+    __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const { return kappa * (best_dot(c, cs, sn) - c.best0); }
+    __device__ __forceinline__ float logp_x(const Coef& c) const { return kappa * c.best0; }
+};
+
+// column view of one lane's vector in shared memory
+struct SCol {
+    float* p;
+    __device__ __forceinline__ float& operator[](int j) const { return p[j * GC_BLOCK]; }
+};
+
+// ------------------------------------------------------------------ kernel
+template <class Policy, int KIND>
+__global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
+    extern __shared__ __align__(16) float gc_smem[];
+    const int d = P.d;
+    SCol xs{gc_smem + threadIdx.x}, us{gc_smem + (size_t)d * GC_BLOCK + threadIdx.x};
+    Policy pol;
+    pol.stage(P, gc_smem + 2 * (size_t)d * GC_BLOCK);
+    __syncthreads();
+
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < a.N;
+    const int nbn = (d + 3) >> 2;
+    const bool aux_in_last = philox_aux_in_last(d);
+    const int pb = aux_in_last ? nbn : nbn + 1;
+    const int quorum = a.quorum;
+    const int n_steps = (int)a.n_steps;
+    constexpr float LN2 = 0.6931471805599453f;
+
+    float* st = static_cast<float*>(a.state) + (live ? c : 0) * d;
+    for (int j = 0; j < d; ++j) { xs[j] = live ? st[j] : (j == 0 ? 1.f : 0.f); us[j] = 0.f; }
+
+    PhiloxDraws<float> dr;
+    dr.init(a.seed, a.chain0 + (uint64_t)c, d);
+    unsigned long long rej_total = live ? a.n_reject[c] : 0ull;
+    unsigned int rej_window = 0;
+    float* samples = static_cast<float*>(a.samples);
+    float* lpo = static_cast<float*>(a.logp);
+    int since_keep = 0;
+    int64_t kept = 0;
+
+    typename Policy::Coef co;
+    pol.begin(co);
+    float lo = 0.f, hi = 2.f, lnu = 0.f, dl_acc = 0.f, lp_x = 0.f;
+    float sn = 0.f, cs = 1.f;
+    int t = live ? 0 : n_steps;
+    int r = 0, batch = 0;
+    bool inloop = false, pending = false, moved = false;
+
+    auto finish_transition = [&]() {
+        // apply the accepted move, renormalise (|x| would otherwise drift in fp32), store
+        float xx = 0.f;
+        for (int j = 0; j < d; ++j) {
+            const float v = moved ? fmaf(cs, xs[j], sn * us[j]) : xs[j];
+            xs[j] = v;
+            xx = fmaf(v, v, xx);
+        }
+        const float inx = rsqrtf(xx);
+        for (int j = 0; j < d; ++j) xs[j] *= inx;
+        rej_total += (unsigned)r;
+        rej_window += (unsigned)r;
+        if (++since_keep == (int)a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (samples) {
+                float* o = samples + (k * a.N + c) * d;
+                if ((d & 1) == 0) for (int j = 0; j < d; j += 2) *reinterpret_cast<float2*>(o + j) = make_float2(xs[j], xs[j + 1]);
+                else for (int j = 0; j < d; ++j) o[j] = xs[j];
+            }
+            if (lpo) lpo[k * a.N + c] = lp_x + (moved ? dl_acc : 0.f);
+            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            rej_window = 0;
+        }
+        pending = false;
+    };
+
+    while (true) {
+        const bool need = !inloop && t < n_steps;
+        const unsigned m_need = __ballot_sync(0xffffffffu, need);
+        const unsigned m_loop = __ballot_sync(0xffffffffu, inloop);
+        if ((m_need | m_loop) == 0u) break;
+
+        if (m_loop == 0u || __popc(m_need) >= quorum) {
+            if (need) {
+                if (pending) finish_transition();
+                else {
+                    // first transition of a launch: normalise a state that is not unit yet (a user's
+                    // initial state); a state written by finish_transition is left bit-for-bit alone so
+                    // that splitting a run over launches does not change the chain
+                    float xx = 0.f;
+                    for (int j = 0; j < d; ++j) xx = fmaf(xs[j], xs[j], xx);
+                    if (fabsf(xx - 1.f) > 1e-5f) {
+                        const float inx = rsqrtf(xx);
+                        for (int j = 0; j < d; ++j) xs[j] *= inx;
+                    }
+                }
+                const uint64_t step = a.step0 + (uint64_t)t;
+                dr.s_lo = (uint32_t)step;
+                dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
+                // normals -> u, z.x
+                uint32_t aux0 = 0, aux1 = 0;
+                float zx = 0.f;
+                for (int b = 0; b < nbn; ++b) {
+                    const U4 w = dr.block(b);
+                    float n0, n1, n2, n3;
+                    box_muller_fast(w.x, w.y, n0, n1);
+                    box_muller_fast(w.z, w.w, n2, n3);
+                    const int j = 4 * b;
+                    us[j] = n0; zx = fmaf(n0, xs[j], zx);
+                    if (j + 1 < d) { us[j + 1] = n1; zx = fmaf(n1, xs[j + 1], zx); }
+                    if (j + 2 < d) { us[j + 2] = n2; zx = fmaf(n2, xs[j + 2], zx); }
+                    if (j + 3 < d) { us[j + 3] = n3; zx = fmaf(n3, xs[j + 3], zx); }
+                    if (b == nbn - 1) { aux0 = w.z; aux1 = w.w; }
+                }
+                if (!aux_in_last) { const U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
+                float pp = 0.f;
+                for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); us[j] = p; pp = fmaf(p, p, pp); }
+                const float inp = rsqrtf(pp);
+                pol.begin(co);
+                for (int j = 0; j < d; ++j) { const float uj = us[j] * inp; us[j] = uj; pol.accumulate(co, j, xs[j], uj); }
+                pol.finish(co, xs, us);
+                lp_x = pol.logp_x(co);
+                lnu = LN2 * fast_lg2(u01(aux0, 0.f));
+                if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }
+                else { lo = 0.f; hi = 2.0f; }
+                r = 0; batch = 0; moved = false;
+                ++t;
+                inloop = true;
+            }
+        }
+
+        if (inloop) {
+            const U4 w = dr.block(pb + batch);
+            const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
+            float tt[FAST_BATCH], sb_[FAST_BATCH], cb_[FAST_BATCH], dl[FAST_BATCH];
+            float lo_ = lo, hi_ = hi;
+#pragma unroll
+            for (int i = 0; i < FAST_BATCH; ++i) {
+                tt[i] = fmaf(hi_ - lo_, u01(wi[i], 0.f), lo_);
+                if (KIND == SHRINK) { if (tt[i] < 0.f) lo_ = tt[i]; else hi_ = tt[i]; }
+            }
+#pragma unroll
+            for (int i = 0; i < FAST_BATCH; ++i) {
+                sincospif(tt[i], &sb_[i], &cb_[i]);
+                dl[i] = pol.delta(co, cb_[i], sb_[i]);
+            }
+            int first = FAST_BATCH;
+#pragma unroll
+            for (int i = FAST_BATCH - 1; i >= 0; --i) if (dl[i] > lnu) first = i;
+            const int cap = KIND == SHRINK ? FAST_SHRINK_CAP : MAX_PROPOSALS;
+            if (first < FAST_BATCH) {
+#pragma unroll
+                for (int i = 0; i < FAST_BATCH; ++i) if (i == first) { sn = sb_[i]; cs = cb_[i]; dl_acc = dl[i]; }
+                r += first;
+                moved = true; inloop = false; pending = true;
+            } else {
+                r += FAST_BATCH;
+                lo = lo_; hi = hi_;
+                ++batch;
+                if (r >= cap || !(lp_x == lp_x)) { inloop = false; pending = true; }  // cap / NaN density: stay at x
+            }
+        }
+    }
+
+    if (live) {
+        if (pending) finish_transition();
+        for (int j = 0; j < d; ++j) st[j] = xs[j];
+        a.n_reject[c] = rej_total;
+    }
+}
+
+}  // namespace geosss

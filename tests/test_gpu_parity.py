@@ -224,10 +224,55 @@ def test_fast_path_follows_reference_under_shared_draws(golden, cls, kind, cfg):
     assert clean >= 0.9 * N * n, (clean, N * n)
 
 
+def gc_case(golden, cfg):
+    """(device pdf, oracle pdf, d) for the great-circle fast kernels."""
+    if cfg in ("c4diag", "c4dense", "d10"):
+        A = golden("logprob_bingham")[f"{cfg}_A"]
+        return gs.Bingham(A), targets.Bingham(A), len(A)
+    if cfg == "bf":
+        g = golden("logprob_bingham")
+        return gs.BinghamFisher(g["bf_A"], g["bf_b"]), targets.Bingham(g["bf_A"], g["bf_b"]), len(g["bf_A"])
+    knots = golden("logprob_curved")[f"{cfg}_knots"]
+    return gs.CurvedVonMisesFisher(gs.SlerpCurve(knots), 500.0), targets.CurvedVMF(knots, 500.0), knots.shape[1]
+
+
+@pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
+                                      (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
+@pytest.mark.parametrize("cfg", ["c4diag", "c4dense", "d10", "bf", "c3", "d3"])
+def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, cls, kind, cfg):
+    """Bingham(-Fisher) and curved-vMF throughput kernels vs the float64 reference algorithm fed the
+    same Philox draws: <= 1e-4 until the first accept/reject flip."""
+    pdf, ora, d = gc_case(golden, cfg)
+    N, n = 12, (25 if kind == samplers.SHRINK else 8)
+    x0 = gs.sample_sphere(d - 1, N, seed=13)
+    if cfg.startswith("c4") or cfg == "d10":
+        x0[: N // 2] = gs.radial_projection(pdf.mode + 0.3 * x0[: N // 2])  # some chains start near the mode
+    seed = 777
+    smp = cls(pdf, x0, seed, dtype="float32", path="fast")
+    got = smp.sample(n + 1)
+    assert smp.path == "fast" and got.dtype == F32 and got.shape == (N, n + 1, d)
+    clean = 0
+    for c in range(N):
+        want, _ = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32)
+        err = np.max(np.abs(got[c, 1:] - want), axis=1)
+        bad = np.nonzero(err > 1e-4)[0]
+        clean += bad[0] if len(bad) else n
+    assert clean >= 0.9 * N * n, (clean, N * n)
+
+
 def test_shard_invariance_and_continuation(golden):
     """Chains depend on (seed, global chain id, step) only: splitting chains over samplers or
     steps over calls does not change them (what makes 1/2/4/8-GPU runs identical)."""
     g = golden("traj_c2")
+    for pdf, d in ((gc_case(golden, "c4diag")[0], 50), (gc_case(golden, "d3")[0], 3)):
+        x0 = gs.sample_sphere(d - 1, 100, seed=3)
+        whole = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5, path="fast").sample(21)
+        b = gs.ShrinkageSphericalSliceSampler(pdf, x0[37:], 5, path="fast", chain_offset=37).sample(21)
+        assert np.array_equal(whole[37:], b)
+        s = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5, path="fast")
+        first = s.sample(9).copy()
+        second = s.sample(13)
+        assert np.array_equal(np.concatenate([first, second[:, 1:]], axis=1), whole)
     pdf = mixture(100.0 * g["modes"])
     x0 = gs.sample_sphere(9, 200, seed=3)
     for path in ("fast", "literal"):
