@@ -13,6 +13,7 @@
 #include "diag.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_gc.cuh"
+#include "kernels_logp_fast.cuh"
 #include "kernels_literal.cuh"
 
 using namespace geosss;
@@ -66,6 +67,7 @@ struct geosss_target {
     int K = 0, single = 0;
     Arr mu, logw, logi0;
     std::vector<double> h_mu, h_const;  // host copies for the fast path's parameter block
+    Arr consts;                         // (K) log w - log 2pi - log i0, device
     // Bingham
     Arr A, b, Adiag;
     int has_b = 0, diag = 0;
@@ -88,7 +90,7 @@ struct geosss_target {
                 (T)log_outlier, (T)beta, nt, ns, k, outlier};
     }
     void release() {
-        for (Arr* a : {&mu, &logw, &logi0, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
     }
 };
 
@@ -190,6 +192,7 @@ extern "C" int geosss_target_create_vmf_mixture(int d, int K, const double* mu, 
     int rc = t->mu.upload(mu, (size_t)K * d);
     if (!rc) rc = t->logw.upload(lw.data(), K);
     if (!rc) rc = t->logi0.upload(li.data(), K);
+    if (!rc) rc = t->consts.upload(t->h_const.data(), K);
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
     return 0;
@@ -312,6 +315,49 @@ template <typename T> static int logp_literal(geosss_target* t, const void* x, v
     return 0;
 }
 
+static int g_sm_count = 0;
+
+template <class Policy> static int launch_logp_tiled(const LpParams& p, const float* x, float* out, int64_t N, cudaStream_t st) {
+    const size_t smem = ((size_t)LP_STAGES * LP_ROWS * p.d + Policy::smem_floats(p)) * sizeof(float);
+    if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: tile does not fit shared memory");
+    if (!g_sm_count) {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CU(cudaFuncSetAttribute(k_logp_tiled<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logp_tiled<Policy>, LP_ROWS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = (N + LP_ROWS - 1) / LP_ROWS;
+    int64_t grid = (int64_t)g_sm_count * per_sm;  // persistent: a multiple of the SM count
+    if (grid > n_tiles) grid = n_tiles;
+    k_logp_tiled<Policy><<<(unsigned)grid, LP_ROWS, smem, st>>>(p, x, out, N);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
+    LpParams p{};
+    p.d = t->d;
+    const float* xi = static_cast<const float*>(x);
+    float* o = static_cast<float*>(out);
+    switch (t->kind) {
+        case TGT_VMF_MIX:
+            if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
+            p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
+            return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
+        case TGT_BINGHAM:
+            p.diag = t->diag; p.a0 = t->diag ? t->Adiag.f : t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
+            return launch_logp_tiled<BinghamLp>(p, xi, o, N, st);
+        case TGT_CURVED_VMF:
+            if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
+            p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
+            return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
+        default: return fail(GEOSSS_E_UNSUPPORTED, "log_prob: no fast kernel for this target");
+    }
+}
+
 extern "C" int geosss_log_prob(geosss_target_t t, int dtype, int path, const void* x, void* out, int64_t N, void* stream) {
     if (!t || N < 0) return fail(GEOSSS_E_INVALID, "log_prob: bad arguments");
     if (N == 0) return 0;
@@ -319,7 +365,7 @@ extern "C" int geosss_log_prob(geosss_target_t t, int dtype, int path, const voi
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (path == GEOSSS_PATH_FAST) {
         if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: the fast path is float32 only");
-        return fail(GEOSSS_E_UNSUPPORTED, "log_prob: no fast kernel for this target yet");
+        return logp_fast(t, x, out, N, st);
     }
     return dtype == GEOSSS_F64 ? logp_literal<double>(t, x, out, N, st) : logp_literal<float>(t, x, out, N, st);
 }

@@ -108,14 +108,17 @@ struct CurvedGc {
     // max over segments of x(theta) . nearest-point, first segment wins ties (argmin of arccos)
     __device__ __forceinline__ float best_dot(const Coef& c, float cs, float sn) const {
         float ga = fmaf(cs, c.gx[0], sn * c.gu[0]);
-        float best = -INFINITY;
+        float best = 0.f, best_clipped = -INFINITY;
 #pragma unroll
         for (int m = 1; m < GC_MAX_KNOTS; ++m) if (m < M) {
             const float gb = fmaf(cs, c.gx[m], sn * c.gu[m]);
             const float p2 = (gb - ga * ca[m - 1]) * isa[m - 1];
             const bool inside = p2 >= 0.f && fmaf(ga, sa[m - 1], -p2 * ca[m - 1]) >= 0.f;
             const float dot = inside ? fast_sqrt(fmaf(ga, ga, p2 * p2)) : (p2 < 0.f ? ga : gb);
-            if (dot > best) best = dot;
+            // the reference ranks segments by arccos(clip(dot, -1, 1)) (spherical_curve.py:32,102): dots above
+            // 1 (|x| > 1) tie at distance 0 and the first such segment wins, but its unclipped dot is returned
+            const float dc = fminf(dot, 1.f);
+            if (dc > best_clipped) { best_clipped = dc; best = dot; }
             ga = gb;
         }
         return best;

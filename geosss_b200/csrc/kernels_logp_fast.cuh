@@ -1,0 +1,186 @@
+// Standalone batched log_prob at the HBM roof (float32): vMF mixture, Bingham(-Fisher), curved vMF.
+//
+//   geosss/distributions.py:78-86,113-114,156-157,218-221,272-275 evaluated for rows x of an (N, d) array
+//   (the only vectorised use upstream: scripts/mixture_vMF.py:104, scripts/curve_vMF.py:119-120).
+//
+// The operator reads (d+1)*4 bytes per point and does O(Kd) flops, so it is bandwidth-bound.
+// Persistent blocks walk over tiles of TILE_ROWS consecutive rows.  A tile is one contiguous
+// span of TILE_ROWS*d floats, so it is fetched with ONE bulk asynchronous copy (TMA unit,
+// cp.async.bulk global->shared, completion on an mbarrier) into a two-stage ring: tile i+1 is
+// in flight while the threads evaluate tile i from shared memory, lane per row.  Target
+// parameters (means, A, knots) are staged into shared memory once per block.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "kernels_fast.cuh"
+#include "kernels_gc.cuh"
+
+namespace geosss {
+
+constexpr int LP_ROWS = 128;  // rows per tile = threads per block
+constexpr int LP_STAGES = 2;
+constexpr int LP_MAX_K = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();  // a lost copy must not hang the GPU
+    }
+}
+
+struct LpParams {
+    const float* a0;  // vMF: mu (K,d) | Bingham: A or diag | curved: knots (M,d)
+    const float* a1;  // vMF: consts (K) natural log | Bingham: b or null | curved: cos(ang)
+    const float* a2;  // curved: sin(ang)
+    float kappa;
+    int d, K, M, diag, single;
+};
+
+// ---- policies: stage parameters, evaluate one row held in shared memory -------------------------
+struct VmfLp {
+    const float* mu;  // shared (K, d), times log2(e)
+    const float* c;   // shared (K), times log2(e)
+    int d, K;
+    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)p.K * p.d + p.K; }
+    __device__ void stage(const LpParams& p, float* sm) {
+        d = p.d; K = p.K;
+        constexpr float L2E = 1.4426950408889634f;
+        for (int i = threadIdx.x; i < K * d; i += blockDim.x) sm[i] = p.a0[i] * L2E;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) sm[K * d + i] = p.a1[i] * L2E;
+        mu = sm; c = sm + K * d;
+    }
+    __device__ __forceinline__ float eval(const float* row) const {
+        float s[LP_MAX_K];
+#pragma unroll
+        for (int k = 0; k < LP_MAX_K; ++k) s[k] = 0.f;
+        for (int j = 0; j < d; ++j) {
+            const float xj = row[j];
+#pragma unroll
+            for (int k = 0; k < LP_MAX_K; ++k) if (k < K) s[k] = fmaf(mu[k * d + j], xj, s[k]);
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < LP_MAX_K; ++k) if (k < K) { s[k] += c[k]; m = fmaxf(m, s[k]); }
+        if (!(m > -INFINITY)) return m;  // i0 overflow: every component is -inf, like the reference
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < LP_MAX_K; ++k) if (k < K) acc += fast_ex2(s[k] - m);
+        return (m + fast_lg2(acc)) * 0.6931471805599453f;
+    }
+};
+
+struct BinghamLp {
+    BinghamGc g;
+    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)(p.diag ? p.d : p.d * p.d) + (p.a1 ? p.d : 0); }
+    __device__ void stage(const LpParams& p, float* sm) {
+        GcParams q{};
+        q.a0 = p.a0; q.a1 = p.a1; q.d = p.d; q.diag = p.diag;
+        g.stage(q, sm);
+    }
+    __device__ __forceinline__ float eval(const float* row) const {
+        const int d = g.d;
+        float q = 0.f;
+        if (g.diag) {
+            for (int j = 0; j < d; ++j) q = fmaf(g.A[j] * row[j], row[j], q);
+        } else {
+            for (int i = 0; i < d; ++i) {
+                const float* ar = g.A + i * d;
+                float ax = 0.f;
+                for (int j = 0; j < d; ++j) ax = fmaf(ar[j], row[j], ax);
+                q = fmaf(row[i], ax, q);
+            }
+        }
+        if (g.b) for (int j = 0; j < d; ++j) q = fmaf(g.b[j], row[j], q);
+        return q;
+    }
+};
+
+struct CurvedLp {
+    CurvedGc g;
+    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)p.M * p.d + 3 * (size_t)(p.M - 1); }
+    __device__ void stage(const LpParams& p, float* sm) {
+        GcParams q{};
+        q.a0 = p.a0; q.a1 = p.a1; q.a2 = p.a2; q.d = p.d; q.M = p.M; q.kappa = p.kappa;
+        g.stage(q, sm);
+    }
+    __device__ __forceinline__ float eval(const float* row) const {
+        CurvedGc::Coef co;
+        g.begin(co);
+        for (int j = 0; j < g.d; ++j) g.accumulate(co, j, row[j], 0.f);
+        return g.kappa * g.best_dot(co, 1.f, 0.f);
+    }
+};
+
+template <class Policy>
+__global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(LpParams P, const float* __restrict__ x, float* __restrict__ out, int64_t N) {
+    extern __shared__ __align__(128) unsigned char lp_smem_raw[];
+    float* lp_smem = reinterpret_cast<float*>(lp_smem_raw);
+    __shared__ __align__(8) uint64_t full[LP_STAGES];
+    const int d = P.d;
+    const size_t tile_floats = (size_t)LP_ROWS * d;
+    float* stage_buf[LP_STAGES];
+#pragma unroll
+    for (int s = 0; s < LP_STAGES; ++s) stage_buf[s] = lp_smem + s * tile_floats;
+    Policy pol;
+    pol.stage(P, lp_smem + LP_STAGES * tile_floats);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < LP_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (N + LP_ROWS - 1) / LP_ROWS;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    // a tile can use the bulk engine when it is complete (byte count a multiple of 16) and x is 16-byte aligned
+    auto bulk_ok = [&](int64_t tile) { return aligned && (tile + 1) * LP_ROWS <= N; };
+    auto issue = [&](int64_t tile, int s) {
+        if (tile < n_tiles && bulk_ok(tile) && threadIdx.x == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full[s], (uint32_t)(tile_floats * sizeof(float)));
+            bulk_g2s(stage_buf[s], x + tile * tile_floats, (uint32_t)(tile_floats * sizeof(float)), &full[s]);
+        }
+    };
+
+    uint32_t phase[LP_STAGES] = {0, 0};
+    int64_t tile = blockIdx.x;
+    issue(tile, 0);
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int s = it & 1;
+        issue(tile + gridDim.x, s ^ 1);  // prefetch the next tile of this block
+        const int64_t row0 = tile * LP_ROWS;
+        if (bulk_ok(tile)) {
+            mbar_wait(&full[s], phase[s]);
+            phase[s] ^= 1;
+        } else {  // ragged last tile / unaligned input: plain coalesced loads
+            const int64_t n_here = (N - row0 < LP_ROWS ? N - row0 : LP_ROWS) * d;
+            for (int64_t i = threadIdx.x; i < n_here; i += blockDim.x) stage_buf[s][i] = x[row0 * d + i];
+            __syncthreads();
+        }
+        const int64_t r = row0 + threadIdx.x;
+        if (r < N) out[r] = pol.eval(stage_buf[s] + (size_t)threadIdx.x * d);
+        __syncthreads();  // everyone is done with stage s before it is refilled two iterations later
+    }
+}
+
+}  // namespace geosss

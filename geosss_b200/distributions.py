@@ -87,8 +87,12 @@ class Distribution(ABC):
         with torch.cuda.device(dev):
             if xd.shape[0] == 0:
                 return out if is_torch else out.cpu().numpy()
-            _lib.check(_lib.lib().geosss_log_prob(self._handle(dev), code, _lib.PATH_LITERAL, xd.data_ptr(),
-                                                   out.data_ptr(), xd.shape[0], _device.stream_ptr(dev)))
+            lib, h, args = _lib.lib(), self._handle(dev), (xd.data_ptr(), out.data_ptr(), xd.shape[0], _device.stream_ptr(dev))
+            # float32: bandwidth-bound tiled kernels where one exists for the target, else the literal kernel
+            rc = lib.geosss_log_prob(h, code, _lib.PATH_FAST, *args) if code == _lib.F32 else _lib.E_UNSUPPORTED
+            if rc == _lib.E_UNSUPPORTED:
+                rc = lib.geosss_log_prob(h, code, _lib.PATH_LITERAL, *args)
+            _lib.check(rc)
         if is_torch:
             res = out if x.is_cuda else out.cpu()
             return res[0] if single else res
