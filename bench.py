@@ -261,6 +261,33 @@ def main_ours(a):
     h2d = N * d * 4
     d2h = T * N * d * 4 + N * 8
 
+    # ---- the bandwidth-bound operator of the path: standalone batched log_prob (fp32), input > L2 ----
+    lp_roof = None
+    if rank == 0:
+        try:
+            n_pts = 1 << 24  # 2^24 x 40 B = 671 MB read per launch (L2 is 126 MB)
+            xs_lp = torch.nn.functional.normalize(torch.randn(n_pts, d, device=dev), dim=1)
+            out_lp = torch.empty(n_pts, device=dev)
+            h = pdf._handle(dev)
+            run_lp = lambda: _lib.check(_lib.lib().geosss_log_prob(h, _lib.F32, _lib.PATH_FAST, xs_lp.data_ptr(), out_lp.data_ptr(),
+                                                                   n_pts, torch.cuda.current_stream(dev).cuda_stream))
+            for _ in range(3):
+                run_lp()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                run_lp()
+            e1.record()
+            torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) * 1e-3 / 10
+            gbs = n_pts * (d + 1) * 4 / sec / 1e9
+            lp_roof = {"kernel": "k_logp_tiled<VmfLp> (TMA bulk-staged)", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                       "frac": gbs / peak, "points_per_s": n_pts / sec, "algorithmic_bytes_per_launch": n_pts * (d + 1) * 4,
+                       "avg_launch_ms": sec * 1e3}
+            del xs_lp, out_lp
+        except Exception as exc:
+            lp_roof = {"error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = cpu_arm(a, a.cpu_transitions)
@@ -279,7 +306,7 @@ def main_ours(a):
                              "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
                              "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
                              "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
-                "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
+                "roofline_log_prob": lp_roof, "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
                 "samples_per_sec_per_gpu": value / world}
         print(json.dumps(line))
     if world > 1:

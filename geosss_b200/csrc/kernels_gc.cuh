@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
             }
 #pragma unroll
             for (int i = 0; i < FAST_BATCH; ++i) {
-                sincospif(tt[i], &sb_[i], &cb_[i]);
+                fast_sincospi(tt[i], sb_[i], cb_[i]);
                 dl[i] = pol.delta(co, cb_[i], sb_[i]);
             }
             int first = FAST_BATCH;

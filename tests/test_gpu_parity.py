@@ -103,6 +103,26 @@ def test_logprob_empty_and_ragged(golden):
         pdf.log_prob(np.zeros(4))
 
 
+def test_fast_logprob_tiles_ragged_unaligned_large(golden):
+    """Tiled float32 log_prob: complete tiles go through the bulk-copy ring, the ragged last tile and
+    16-byte-unaligned inputs through plain loads; all must agree with the float64 literal kernel."""
+    g = golden("logprob_vmf")
+    pdf = mixture(100.0 * g["c2_modes"])
+    gen = np.random.default_rng(0)
+    for n in (127, 128, 129, 1000, 128 * 300 + 5):
+        x = gs.radial_projection(gen.standard_normal((n + 1, 10)))
+        want = pdf.log_prob(x)  # float64 literal
+        xt = torch.as_tensor(x, dtype=torch.float32).cuda()
+        got = pdf.log_prob(xt).cpu().numpy()
+        assert rel_err(got, want) <= 1e-5
+        got_unaligned = pdf.log_prob(xt[1:]).cpu().numpy()  # row offset 40 B: not 16-byte aligned
+        assert rel_err(got_unaligned, want[1:]) <= 1e-5
+    for pdf2, d in ((gs.random_bingham(50, 300, 0, True, 6982), 50), (gs.random_bingham(7, 30, 0, False, 1), 7),
+                    (gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(10, 100, 0.5, seed=4562)), 500.0), 100)):
+        x = gs.radial_projection(gen.standard_normal((128 * 9 + 17, d)))
+        assert rel_err(pdf2.log_prob(x.astype(F32)), pdf2.log_prob(x)) <= 2e-5
+
+
 # ------------------------------------------------------------------ trajectories under the reference's draws
 def tape_cases(golden):
     g = golden("traj_c1")
