@@ -34,7 +34,7 @@ def c5_target():
     g = np.load(os.path.join(ROOT, "tests", "golden", "logprob_cpd.npz"))
     n = len(g["c5_source"])
     return gs.CoherentPointDrift(gs.PointCloud(g["c5_target"], np.ones(len(g["c5_target"]))),
-                                 gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=0, omega=0.4)
+                                 gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=20, omega=0.4, dense=True)
 
 
 def cases(quick):

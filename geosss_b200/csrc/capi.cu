@@ -77,7 +77,7 @@ struct geosss_target {
     Arr knots, ang, cosang, sinang;
     // CPD
     int nt = 0, ns = 0, k = 0, outlier = 1;
-    double sigma2 = 1, log_const = 0, log_outlier = 0, beta = 1;
+    double sigma2 = 1, log_const = 0, log_outlier = 0, beta = 1, max_logw = 0;
     Arr tgt, wt, src, logws;
 
     template <typename T> VmfMixP<T> vmf() const { return {mu.get<T>(), logw.get<T>(), logi0.get<T>(), K, d, single}; }
@@ -132,6 +132,12 @@ static int target_fast_supported(const geosss_target* t) {
         if (t->kind == TGT_CURVED_VMF && t->M > GC_MAX_KNOTS) return -1;
         return gc_smem_bytes(t, gc_params(t)) <= 200 * 1024 ? 0 : -1;
     }
+    if (t->kind == TGT_CPD) {
+        // dense sum with a finite outlier floor; the k-nearest truncation stays on the literal path
+        const bool dense = t->k <= 0 || t->k >= t->ns;
+        return (dense && t->outlier && std::isfinite(t->log_outlier) && std::isfinite(t->log_const) &&
+                (size_t)CPD_WARPS * 4 * t->ns * sizeof(float) <= 200 * 1024) ? 0 : -1;
+    }
     return -1;
 }
 
@@ -160,6 +166,19 @@ static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a
     }
     if (t->kind == TGT_BINGHAM) return launch_gc<BinghamGc>(t, kind, a, st);
     if (t->kind == TGT_CURVED_VMF) return launch_gc<CurvedGc>(t, kind, a, st);
+    if (t->kind == TGT_CPD && !target_fast_supported(t)) {
+        const size_t smem = (size_t)CPD_WARPS * 4 * t->ns * sizeof(float);
+        const unsigned grid = (unsigned)((a.N + CPD_WARPS - 1) / CPD_WARPS);
+        if (kind == SHRINK) {
+            CU(cudaFuncSetAttribute(k_sampler_cpd_fast<SHRINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sampler_cpd_fast<SHRINK><<<grid, CPD_WARPS * 32, smem, st>>>(t->cpd<float>(), (float)t->max_logw, a);
+        } else {
+            CU(cudaFuncSetAttribute(k_sampler_cpd_fast<REJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sampler_cpd_fast<REJECT><<<grid, CPD_WARPS * 32, smem, st>>>(t->cpd<float>(), (float)t->max_logw, a);
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     return fail(GEOSSS_E_UNSUPPORTED, "run: no fast kernel for this target");
 }
 
@@ -275,6 +294,8 @@ extern "C" int geosss_target_create_cpd(int n_t, int n_s, const double* target, 
     std::vector<double> wt(n_t, 1.0), lws(n_s, 0.0);
     if (w_t) wt.assign(w_t, w_t + n_t);
     if (w_s) for (int i = 0; i < n_s; ++i) lws[i] = std::log(w_s[i]);
+    t->max_logw = lws[0];
+    for (int i = 1; i < n_s; ++i) t->max_logw = lws[i] > t->max_logw ? lws[i] : t->max_logw;
     int rc = t->tgt.upload(target, (size_t)n_t * 3);
     if (!rc) rc = t->src.upload(source, (size_t)n_s * 3);
     if (!rc) rc = t->wt.upload(wt.data(), n_t);
@@ -354,6 +375,14 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
             p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
+        case TGT_CPD: {
+            if (target_fast_supported(t)) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast CPD kernel needs the dense sum with an outlier term");
+            const size_t smem = (size_t)CPD_WARPS * 4 * t->ns * sizeof(float);
+            CU(cudaFuncSetAttribute(k_logp_cpd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_logp_cpd_fast<<<(unsigned)((N + CPD_WARPS - 1) / CPD_WARPS), CPD_WARPS * 32, smem, st>>>(t->cpd<float>(), (float)t->max_logw, xi, o, N);
+            CU(cudaGetLastError());
+            return 0;
+        }
         default: return fail(GEOSSS_E_UNSUPPORTED, "log_prob: no fast kernel for this target");
     }
 }

@@ -10,9 +10,10 @@
 // hazard of SURVEY.md section 7), and no log is needed per proposal.
 //
 // Deliberate deviations from the literal path, all distribution-preserving: x is renormalised
-// at every transition (the reference lets |x| drift), the bracket is kept in half-turns so
-// sincospif needs no range reduction, log p(x) is not re-evaluated from scratch but from the
-// fresh a_k, and a proposal cap keeps a chain at x instead of looping for ever.
+// at every transition (the reference lets |x| drift), the bracket is kept in half-turns and
+// (cos, sin) come from the MUFU pipe followed by a Newton renormalisation (fast_sincospi), log p(x)
+// is not re-evaluated from scratch but from the fresh a_k, and a proposal cap keeps a chain at x
+// instead of looping for ever.
 //
 // One lane per chain; state, direction and the 2K scores live in registers (D, K are template
 // parameters, D padded to a multiple of 4 with zeros); mixture parameters are read from the

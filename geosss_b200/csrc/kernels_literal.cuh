@@ -8,6 +8,17 @@
 
 namespace geosss {
 
+__device__ __forceinline__ float fast_ex2_lit(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2_lit(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 constexpr int LANE_BLOCK = 128;  // threads per block, lane-per-chain kernels
 constexpr int CPD_WARPS = 4;     // warps (= chains or points) per block, CPD kernels
 
@@ -193,6 +204,121 @@ __global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd(CpdP<T> p, RunAr
         a.n_reject[c] = rej_total;
         if (a.status) a.status[c] = good ? 0 : 1;
     }
+}
+
+// Float32 throughput variant (dense sum with outlier column only): one pass over the pairs with the
+// fixed shift M0 = max(log_outlier, log_const + max_k log w_k) >= every term, so nothing can overflow and
+// the outlier term keeps the row sum away from zero; exp on the MUFU pipe in base 2 with all constants
+// folded into one FFMA per pair:  2^(lw2_k + c2 + d2 * q2 - M2).
+struct CpdWarpLogPFast {
+    CpdP<float> p;
+    float* moved;
+    float q2, c2m, out2m, m0;  // -0.5 log2(e) / sigma^2, (log_const - M0) log2(e), (log_outlier - M0) log2(e), M0
+    float* lw2;                 // shared (ns): log w_k * log2(e)
+    template <class Vec> __device__ __forceinline__ float operator()(Vec q) const {
+        const int lane = threadIdx.x & 31;
+        float R[9];
+        quat_to_matrix<float>(q[0], q[1], q[2], q[3], R);
+        __syncwarp();
+        cpd_move_source(p, R, moved, lane, 32);
+        __syncwarp();
+        double acc = 0.0;
+        const float base = exp2f(out2m);
+        for (int l = lane; l < p.nt; l += 32) {
+            const float t0 = p.tgt[3 * l], t1 = p.tgt[3 * l + 1], t2 = p.tgt[3 * l + 2];
+            float s0 = base, s1 = 0.f;
+            int k = 0;
+            for (; k + 1 < p.ns; k += 2) {
+                const float e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+                const float f0 = t0 - moved[3 * k + 3], f1 = t1 - moved[3 * k + 4], f2 = t2 - moved[3 * k + 5];
+                const float d2a = fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), d2b = fmaf(f0, f0, fmaf(f1, f1, f2 * f2));
+                s0 += fast_ex2_lit(fmaf(d2a, q2, lw2[k] + c2m));
+                s1 += fast_ex2_lit(fmaf(d2b, q2, lw2[k + 1] + c2m));
+            }
+            if (k < p.ns) {
+                const float e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+                s0 += fast_ex2_lit(fmaf(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), q2, lw2[k] + c2m));
+            }
+            acc += (double)((m0 + 0.6931471805599453f * fast_lg2_lit(s0 + s1)) * p.wt[l]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = __shfl_sync(0xffffffffu, acc, 0);
+        return p.beta * (float)acc;
+    }
+    // per-warp set-up; smem per warp: 3*ns (moved) + ns (lw2) floats
+    __device__ __forceinline__ void init(const CpdP<float>& p_, float* warp_smem, float max_logw) {
+        p = p_; moved = warp_smem; lw2 = warp_smem + 3 * p.ns;
+        constexpr float L2E = 1.4426950408889634f;
+        const int lane = threadIdx.x & 31;
+        for (int k = lane; k < p.ns; k += 32) lw2[k] = p.logws[k] * L2E;
+        m0 = fmaxf(p.log_outlier, p.log_const + max_logw);
+        q2 = -0.5f * L2E / p.sigma2;
+        c2m = (p.log_const - m0) * L2E;
+        out2m = (p.log_outlier - m0) * L2E;
+        __syncwarp();
+    }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd_fast(CpdP<float> p, float max_logw, RunArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * CPD_WARPS + warp;
+    if (c >= a.N) return;
+    CpdWarpLogPFast f;
+    f.init(p, reinterpret_cast<float*>(smem_raw) + (size_t)warp * 4 * p.ns, max_logw);
+    float xs[4], us[4], ys[4];
+    Reg4<float> x{xs}, u{us}, y{ys};
+    float* st = static_cast<float*>(a.state) + c * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xs[j] = st[j];
+    PhiloxDraws<float> dr;
+    dr.init(a.seed, a.chain0 + (uint64_t)c, 4);
+    unsigned long long rej_total = a.n_reject[c];
+    unsigned int rej_window = 0;
+    float* samples = static_cast<float*>(a.samples);
+    float* lpo = static_cast<float*>(a.logp);
+    int64_t since_keep = 0, kept = 0;
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+        dr.begin_step(a.step0 + (uint64_t)t);
+        float lp;
+        int r = transition_literal<float, KIND>(4, x, u, y, dr, f, &lp);
+        rej_total += (unsigned)r;
+        rej_window += (unsigned)r;
+        if (++since_keep == a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (lane == 0) {
+                if (samples) {
+                    float* o = samples + (k * a.N + c) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = xs[j];
+                }
+                if (lpo) lpo[k * a.N + c] = lp;
+                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            }
+            rej_window = 0;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st[j] = xs[j];
+        a.n_reject[c] = rej_total;
+    }
+}
+
+__global__ void __launch_bounds__(CPD_WARPS * 32) k_logp_cpd_fast(CpdP<float> p, float max_logw, const float* __restrict__ q,
+                                                                  float* __restrict__ out, int64_t N) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    int64_t i = (int64_t)blockIdx.x * CPD_WARPS + warp;
+    if (i >= N) return;
+    CpdWarpLogPFast f;
+    f.init(p, reinterpret_cast<float*>(smem_raw) + (size_t)warp * 4 * p.ns, max_logw);
+    SVec<const float> v{q + i * 4, 1};
+    float val = f(v);
+    if ((threadIdx.x & 31) == 0) out[i] = val;
 }
 
 }  // namespace geosss

@@ -92,6 +92,30 @@ def test_logprob_cpd(golden, dtype, tol):
     assert rel_err(gm.log_prob(g["cube_q"].astype(dtype)), g["cube_logp_gmm"]) <= rtol
 
 
+def test_cpd_fast_path(golden):
+    """float32 throughput CPD kernels (dense sum): log_prob within 1e-3 abs of the reference's k=20 values,
+    and the sampler follows the float64 reference algorithm under shared Philox draws."""
+    g = golden("logprob_cpd")
+    n = len(g["c5_source"])
+    pdf = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"], np.ones(len(g["c5_target"]))),
+                                gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=20, omega=0.4, dense=True)
+    got = pdf.log_prob(g["c5_q"].astype(F32))
+    assert np.max(np.abs(got - g["c5_logp"])) <= 1e-3
+    ora = targets.CPD(g["c5_target"], g["c5_source"], sigma=1.0, k=20, omega=0.4, source_weights=np.ones(n) / n)
+    x0 = gs.sample_sphere(3, 6, seed=17)
+    for cls, kind, steps in ((gs.ShrinkageSphericalSliceSampler, samplers.SHRINK, 12), (gs.RejectionSphericalSliceSampler, samplers.REJECT, 4)):
+        smp = cls(pdf, x0, 4242, dtype="float32", path="fast")
+        out = smp.sample(steps + 1)
+        assert smp.path == "fast"
+        clean = 0
+        for c in range(6):
+            want, _ = oracle_chain(ora, kind, x0[c], 4242, c, steps, 4, F32)
+            err = np.max(np.abs(out[c, 1:] - want), axis=1)
+            bad = np.nonzero(err > 2e-4)[0]
+            clean += bad[0] if len(bad) else steps
+        assert clean >= 0.8 * 6 * steps, (clean, 6 * steps)
+
+
 def test_logprob_empty_and_ragged(golden):
     g = golden("logprob_vmf")
     pdf = mixture(g["c1_mus"])
