@@ -338,8 +338,8 @@ template <typename T> static int logp_literal(geosss_target* t, const void* x, v
 
 static int g_sm_count = 0;
 
-template <class Policy> static int launch_logp_tiled(const LpParams& p, const float* x, float* out, int64_t N, cudaStream_t st) {
-    const size_t smem = ((size_t)LP_STAGES * LP_ROWS * p.d + Policy::smem_floats(p)) * sizeof(float);
+template <class Policy> static int launch_logp_tiled(const typename Policy::Params& p, const float* x, float* out, int64_t N, cudaStream_t st) {
+    const size_t smem = ((size_t)LP_STAGES * LP_ROWS * Policy::dim(p) + Policy::smem_floats(p)) * sizeof(float);
     if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: tile does not fit shared memory");
     if (!g_sm_count) {
         int dev = 0;
@@ -358,6 +358,31 @@ template <class Policy> static int launch_logp_tiled(const LpParams& p, const fl
     return 0;
 }
 
+template <int K> static int logp_vmf_const_k(int Dp, const VmfFastParams& P, const float* x, float* o, int64_t N, cudaStream_t st) {
+    switch (Dp) {
+        case 4: return launch_logp_tiled<VmfLpConst<K, 4>>(P, x, o, N, st);
+        case 8: return launch_logp_tiled<VmfLpConst<K, 8>>(P, x, o, N, st);
+        case 12: return launch_logp_tiled<VmfLpConst<K, 12>>(P, x, o, N, st);
+        default: return launch_logp_tiled<VmfLpConst<K, 16>>(P, x, o, N, st);
+    }
+}
+
+// small mixtures (d <= 16, K <= 8): parameters in the constant bank
+static int logp_vmf_const(geosss_target* t, const float* x, float* o, int64_t N, cudaStream_t st) {
+    const VmfFastParams P = make_vmf_fast_params(t->d, t->K, t->h_mu.data(), t->h_const.data());
+    const int Dp = (t->d + 3) / 4 * 4;
+    switch (t->K) {
+        case 1: return logp_vmf_const_k<1>(Dp, P, x, o, N, st);
+        case 2: return logp_vmf_const_k<2>(Dp, P, x, o, N, st);
+        case 3: return logp_vmf_const_k<3>(Dp, P, x, o, N, st);
+        case 4: return logp_vmf_const_k<4>(Dp, P, x, o, N, st);
+        case 5: return logp_vmf_const_k<5>(Dp, P, x, o, N, st);
+        case 6: return logp_vmf_const_k<6>(Dp, P, x, o, N, st);
+        case 7: return logp_vmf_const_k<7>(Dp, P, x, o, N, st);
+        default: return logp_vmf_const_k<8>(Dp, P, x, o, N, st);
+    }
+}
+
 static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
     LpParams p{};
     p.d = t->d;
@@ -366,6 +391,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
     switch (t->kind) {
         case TGT_VMF_MIX:
             if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
+            if (!fast_supported(t->kind, t->d, t->K, t->single)) return logp_vmf_const(t, xi, o, N, st);
             p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
         case TGT_BINGHAM:

@@ -313,6 +313,23 @@ inline int fast_supported(int target_kind, int d, int K, int single) {
     return 0;
 }
 
+// (K, D) zero-padded parameter block in log2 units
+inline VmfFastParams make_vmf_fast_params(int d, int K, const double* mu, const double* consts) {
+    const int Dp = (d + 3) / 4 * 4;
+    VmfFastParams P;
+    const double L2E = 1.4426950408889634;
+    for (int k = 0; k < FAST_MAX_K; ++k) {
+        for (int j = 0; j < FAST_MAX_D; ++j) P.mu[k * FAST_MAX_D + j] = 0.f;
+        P.c[k] = 0.f;
+    }
+    for (int k = 0; k < K; ++k) {
+        for (int j = 0; j < d; ++j) P.mu[k * Dp + j] = (float)(mu[(size_t)k * d + j] * L2E);
+        P.c[k] = (float)(consts[k] * L2E);
+    }
+    P.d = d;
+    return P;
+}
+
 template <int K, int D> static int launch_vmf_fast_kd(int kind, const VmfFastParams& P, const RunArgs& a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.N + FAST_BLOCK - 1) / FAST_BLOCK);
     if (a.n_steps > 0x7fffffff) return -1;
@@ -334,17 +351,7 @@ template <int K> static int launch_vmf_fast_k(int kind, int Dp, const VmfFastPar
 inline int launch_fast(int target_kind, int kind, int d, int K, const double* mu, const double* consts, const RunArgs& a, cudaStream_t st) {
     if (fast_supported(target_kind, d, K, 0)) return -3;
     const int Dp = (d + 3) / 4 * 4;
-    VmfFastParams P;
-    const double L2E = 1.4426950408889634;
-    for (int k = 0; k < FAST_MAX_K; ++k) {
-        for (int j = 0; j < FAST_MAX_D; ++j) P.mu[k * FAST_MAX_D + j] = 0.f;
-        P.c[k] = 0.f;
-    }
-    for (int k = 0; k < K; ++k) {
-        for (int j = 0; j < d; ++j) P.mu[k * Dp + j] = (float)(mu[(size_t)k * d + j] * L2E);
-        P.c[k] = (float)(consts[k] * L2E);
-    }
-    P.d = d;
+    const VmfFastParams P = make_vmf_fast_params(d, K, mu, consts);
     switch (K) {
         case 1: return launch_vmf_fast_k<1>(kind, Dp, P, a, st);
         case 2: return launch_vmf_fast_k<2>(kind, Dp, P, a, st);

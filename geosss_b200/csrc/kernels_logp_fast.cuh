@@ -57,7 +57,39 @@ struct LpParams {
 };
 
 // ---- policies: stage parameters, evaluate one row held in shared memory -------------------------
+// vMF mixture with compile-time K and padded D: means and constants sit in the kernel-parameter constant
+// bank (same block as the sampler kernel), so the K*d FMAs per point take them as immediate operands and
+// the only shared-memory traffic is the point itself.
+template <int K, int D> struct VmfLpConst {
+    using Params = VmfFastParams;
+    static __host__ __device__ size_t smem_floats(const Params&) { return 0; }
+    static __host__ __device__ int dim(const Params& p) { return p.d; }
+    __device__ void stage(const Params&, float*) {}
+    __device__ __forceinline__ float eval(const Params& P, const float* row) const {
+        const int d = P.d;
+        float s[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) s[k] = P.c[k];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float xj = j < d ? row[j] : 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) s[k] = fmaf(P.mu[k * D + j], xj, s[k]);
+        }
+        float m = s[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) m = fmaxf(m, s[k]);
+        if (!(m > -INFINITY)) return m;  // i0 overflow: every component is -inf, like the reference
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc += fast_ex2(s[k] - m);
+        return (m + fast_lg2(acc)) * 0.6931471805599453f;
+    }
+};
+
 struct VmfLp {
+    using Params = LpParams;
+    static __host__ __device__ int dim(const Params& p) { return p.d; }
     const float* mu;  // shared (K, d), times log2(e)
     const float* c;   // shared (K), times log2(e)
     int d, K;
@@ -69,7 +101,7 @@ struct VmfLp {
         for (int i = threadIdx.x; i < K; i += blockDim.x) sm[K * d + i] = p.a1[i] * L2E;
         mu = sm; c = sm + K * d;
     }
-    __device__ __forceinline__ float eval(const float* row) const {
+    __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
         float s[LP_MAX_K];
 #pragma unroll
         for (int k = 0; k < LP_MAX_K; ++k) s[k] = 0.f;
@@ -90,6 +122,8 @@ struct VmfLp {
 };
 
 struct BinghamLp {
+    using Params = LpParams;
+    static __host__ __device__ int dim(const Params& p) { return p.d; }
     BinghamGc g;
     static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)(p.diag ? p.d : p.d * p.d) + (p.a1 ? p.d : 0); }
     __device__ void stage(const LpParams& p, float* sm) {
@@ -97,7 +131,7 @@ struct BinghamLp {
         q.a0 = p.a0; q.a1 = p.a1; q.d = p.d; q.diag = p.diag;
         g.stage(q, sm);
     }
-    __device__ __forceinline__ float eval(const float* row) const {
+    __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
         const int d = g.d;
         float q = 0.f;
         if (g.diag) {
@@ -116,6 +150,8 @@ struct BinghamLp {
 };
 
 struct CurvedLp {
+    using Params = LpParams;
+    static __host__ __device__ int dim(const Params& p) { return p.d; }
     CurvedGc g;
     static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)p.M * p.d + 3 * (size_t)(p.M - 1); }
     __device__ void stage(const LpParams& p, float* sm) {
@@ -123,7 +159,7 @@ struct CurvedLp {
         q.a0 = p.a0; q.a1 = p.a1; q.a2 = p.a2; q.d = p.d; q.M = p.M; q.kappa = p.kappa;
         g.stage(q, sm);
     }
-    __device__ __forceinline__ float eval(const float* row) const {
+    __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
         CurvedGc::Coef co;
         g.begin(co);
         for (int j = 0; j < g.d; ++j) g.accumulate(co, j, row[j], 0.f);
@@ -132,11 +168,12 @@ struct CurvedLp {
 };
 
 template <class Policy>
-__global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(LpParams P, const float* __restrict__ x, float* __restrict__ out, int64_t N) {
+__global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(const __grid_constant__ typename Policy::Params P, const float* __restrict__ x,
+                                                        float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(128) unsigned char lp_smem_raw[];
     float* lp_smem = reinterpret_cast<float*>(lp_smem_raw);
     __shared__ __align__(8) uint64_t full[LP_STAGES];
-    const int d = P.d;
+    const int d = Policy::dim(P);
     const size_t tile_floats = (size_t)LP_ROWS * d;
     float* stage_buf[LP_STAGES];
 #pragma unroll
@@ -178,7 +215,7 @@ __global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(LpParams P, const float*
             __syncthreads();
         }
         const int64_t r = row0 + threadIdx.x;
-        if (r < N) out[r] = pol.eval(stage_buf[s] + (size_t)threadIdx.x * d);
+        if (r < N) out[r] = pol.eval(P, stage_buf[s] + (size_t)threadIdx.x * d);
         __syncthreads();  // everyone is done with stage s before it is refilled two iterations later
     }
 }
