@@ -507,7 +507,7 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
     a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
     // quorum of the persistent bracket loop (kernels_fast.cuh); tuned on B200, see DESIGN.md
-    a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 14;
+    a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 20;
     if (const char* q = std::getenv("GEOSSS_QUORUM")) { int v = std::atoi(q); if (v >= 1 && v <= 32) a.quorum = v; }
     return a;
 }

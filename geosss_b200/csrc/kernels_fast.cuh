@@ -248,7 +248,79 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
             }
         }
 
-        if (inloop) {
+        // ---- cooperative batches (reject sampler): when at most 16 chains of the warp are still looking
+        // for an acceptable proposal, the idle lanes help.  Reject proposals are i.i.d. uniform on the
+        // circle and proposal j of a chain is a pure function of (seed, chain, step, j), so g = 32/nW lanes
+        // can evaluate 4g consecutive proposals of one chain at once; the lowest accepted index wins,
+        // which is exactly what the sequential loop of geosss/mcmc.py:368-374 returns.
+        bool own_batch = inloop;
+        if (KIND == REJECT) {
+            const unsigned m_now = __ballot_sync(0xffffffffu, inloop);
+            const int nW = __popc(m_now);
+            if (nW > 0 && nW <= 16) {
+                own_batch = false;
+                const int lane = threadIdx.x & 31;
+                const int lg = 31 - __clz(32 / nW);  // helpers per chain g = 2^lg
+                const int g = 1 << lg;
+                const int grp = lane >> lg, sub = lane & (g - 1);
+                const bool helping = grp < nW;
+                const int owner = __fns(m_now, 0, (helping ? grp : 0) + 1);
+                float Ao[K], Bo[K], Go[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    Ao[k] = __shfl_sync(0xffffffffu, A[k], owner);
+                    Bo[k] = __shfl_sync(0xffffffffu, B[k], owner);
+                    Go[k] = __shfl_sync(0xffffffffu, G[k], owner);
+                }
+                const int batch_o = __shfl_sync(0xffffffffu, batch, owner);
+                const int t_o = __shfl_sync(0xffffffffu, t, owner);
+                int jacc = 0x7fffffff;
+                float sn_h = 0.f, cs_h = 1.f, S_h = 0.f;
+                if (helping) {
+                    const uint64_t chain_o = a.chain0 + (uint64_t)(c - lane + owner);
+                    const uint64_t step_o = a.step0 + (uint64_t)(t_o - 1);
+                    const U4 w = philox4x32_10(U4{(uint32_t)chain_o, (uint32_t)(chain_o >> 32), (uint32_t)step_o,
+                                                  (((uint32_t)(step_o >> 32) & 0xFFFFu) << 16) | (uint32_t)(pb + batch_o + sub)},
+                                               dr.k0, dr.k1);
+                    const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
+                    float sb_[FAST_BATCH], cb_[FAST_BATCH], Sb[FAST_BATCH];
+#pragma unroll
+                    for (int i = 0; i < FAST_BATCH; ++i) {
+                        fast_sincospi(fmaf(2.0f, u01(wi[i], 0.f), 0.f), sb_[i], cb_[i]);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc += fast_ex2(fmaf(cb_[i], Ao[k], fmaf(sb_[i], Bo[k], Go[k])));
+                        Sb[i] = acc;
+                    }
+#pragma unroll
+                    for (int i = FAST_BATCH - 1; i >= 0; --i)
+                        if (Sb[i] > 1.0f) { jacc = FAST_BATCH * sub + i; sn_h = sb_[i]; cs_h = cb_[i]; S_h = Sb[i]; }
+                }
+                int jmin = jacc;
+                for (int o = g >> 1; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+                // every owner reads its group's verdict (group index = rank of the owner among looping lanes)
+                const int rank = __popc(m_now & ((1u << lane) - 1u));
+                const int src = (inloop ? rank : 0) << lg;
+                const int jmine = __shfl_sync(0xffffffffu, jmin, src);
+                const int wl = src + (jmine == 0x7fffffff ? 0 : jmine / FAST_BATCH);
+                const float sn_w = __shfl_sync(0xffffffffu, sn_h, wl);
+                const float cs_w = __shfl_sync(0xffffffffu, cs_h, wl);
+                const float S_w = __shfl_sync(0xffffffffu, S_h, wl);
+                if (inloop) {
+                    if (jmine != 0x7fffffff) {
+                        sn = sn_w; cs = cs_w; S = S_w;
+                        r += jmine;
+                        moved = true; inloop = false; pending = true;
+                    } else {
+                        r += FAST_BATCH * g;
+                        batch += g;
+                        if (r >= cap) { inloop = false; pending = true; }
+                    }
+                }
+            }
+        }
+
+        if (own_batch) {
             const U4 w = dr.block(pb + batch);
             const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
             float tt[FAST_BATCH], sb_[FAST_BATCH], cb_[FAST_BATCH], Sb[FAST_BATCH];
