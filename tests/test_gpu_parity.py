@@ -446,3 +446,63 @@ def test_launcher_and_bingham_relative_ess(golden):
         out[method] = diagnostics.ess(s.permute(1, 0, 2), pdf.mode, 500)[1]
     assert out["sss-reject"] > 0.6
     assert 0.05 < out["sss-shrink"] < 0.5 and out["sss-shrink"] < out["sss-reject"]
+
+
+# ------------------------------------------------------------------ C-ABI details: thinning, logp / rejection outputs, edge shapes
+def _run_raw(pdf, cls, x0, seed, n_steps, thin, path):
+    """geosss_sampler_run through the Python wrapper's private hook, with every optional output."""
+    smp = cls(pdf, torch.as_tensor(x0).cuda(), seed, path=path)
+    n_keep = n_steps // thin
+    N, d = x0.shape
+    samples = torch.empty((n_keep, N, d), dtype=torch.float32, device="cuda")
+    logp = torch.empty((n_keep, N), dtype=torch.float32, device="cuda")
+    nrej = torch.zeros((n_keep, N), dtype=torch.int32, device="cuda")
+    smp._run_device(n_steps, samples, thin=thin, logp=logp, nrej=nrej)
+    torch.cuda.synchronize()
+    return smp, samples.cpu().numpy(), logp.cpu().numpy(), nrej.cpu().numpy()
+
+
+@pytest.mark.parametrize("cfg", ["vmf", "c4diag", "d3", "cpd"])
+@pytest.mark.parametrize("cls", [gs.ShrinkageSphericalSliceSampler, gs.RejectionSphericalSliceSampler])
+def test_thinning_logp_and_rejection_outputs(golden, cfg, cls):
+    if cfg == "vmf":
+        pdf, d = mixture(100.0 * golden("traj_c2")["modes"]), 10
+    elif cfg == "cpd":
+        g = golden("logprob_cpd")
+        n = len(g["c5_source"])
+        pdf, d = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n),
+                                       sigma=1.0, k=20, omega=0.4, dense=True), 4
+    else:
+        pdf, _, d = gc_case(golden, cfg)
+    N = 70 if cfg != "cpd" else 9
+    steps = 24 if cfg != "cpd" else 6
+    x0 = gs.sample_sphere(d - 1, N, seed=4)
+    smp1, s1, lp1, r1 = _run_raw(pdf, cls, x0, 9, steps, 1, "fast")
+    smp3, s3, lp3, r3 = _run_raw(pdf, cls, x0, 9, steps, 3, "fast")
+    assert smp1.path == "fast"
+    # thinning keeps every third state of the same chain and sums the rejections in between
+    assert np.array_equal(s3, s1[2::3]) and np.array_equal(lp3, lp1[2::3])
+    assert np.array_equal(r3, r1.reshape(steps // 3, 3, N).sum(1))
+    assert int(r1.sum()) == smp1.n_reject
+    # logp_out is the log-density of the kept state
+    want = np.asarray(pdf.log_prob(s1.reshape(-1, d).astype(np.float64))).reshape(steps, N)
+    tol = 2e-3 if cfg == "cpd" else 3e-4
+    assert np.max(np.abs(lp1 - want) / np.maximum(1.0, np.abs(want))) <= tol
+
+
+def test_edge_shapes_fast_path():
+    """One chain, K = 1, d = 2..16 and a chain count that is not a multiple of the block size."""
+    gen = np.random.default_rng(3)
+    for d in (2, 3, 4, 5, 8, 13, 16):
+        mus = 12.0 * gs.sample_sphere(d - 1, 2, seed=d)
+        for pdf in (mixture(mus), gs.VonMisesFisher(mus[0])):
+            for N in (1, 33):
+                x0 = gs.sample_sphere(d - 1, N, seed=1)
+                out = gs.ShrinkageSphericalSliceSampler(pdf, x0 if N > 1 else x0[0], 5, path="fast").sample(30, 5)
+                assert out.shape == ((N, 30, d) if N > 1 else (30, d))
+                assert np.all(np.isfinite(out)) and np.allclose(np.linalg.norm(out, axis=-1), 1, atol=1e-4)
+    # n_steps = 0 is a no-op; a second call continues
+    pdf = mixture(12.0 * gs.sample_sphere(4, 3, seed=2))
+    smp = gs.RejectionSphericalSliceSampler(pdf, torch.as_tensor(gs.sample_sphere(4, 5, seed=3)).cuda(), 1)
+    smp._run_device(0, None)
+    assert smp.rng.steps_done == 0 and smp.n_reject == 0
