@@ -134,9 +134,9 @@ def main_reference(a):
     per_core = max(200, a.cpu_transitions // 5)
     for _ in range(a.warmup):
         cpu_arm(a, 50)
-    total, cores, rej, wall = 0, 1, 0.0, 0.0
+    total, cores, rej, wall, last = 0, 1, 0.0, 0.0, {}
     for _ in range(a.steps):
-        r = cpu_arm(a, per_core)
+        r = last = cpu_arm(a, per_core)
         total += r["transitions"]
         wall += r["wall_s"]  # process start-up and imports are outside the timed region
         cores = r["cores"]
@@ -149,6 +149,8 @@ def main_reference(a):
                              "sample": f"oracle port of the reference samplers, {cores} independent chains x {per_core} transitions per step, "
                                        f"mean rejections/transition {rej:.2f}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ess": {"relative_ess_x0": last.get("relative_ess_x0"), "ess_per_sec": last.get("ess_per_sec"),
+                    "chains_used": cores, "draws": per_core, "estimator": "oracle/ess.py ess_multichain on the last step's chains"},
             "gpu_launches": 0}
     print(json.dumps(line))
 

@@ -35,8 +35,8 @@ def run_chain(args):
     x0 = sphere.sample_sphere(pdf.d - 1, seed=init_seed)
     smp = samplers.SliceSampler(kind, pdf.log_prob, x0, np.random.default_rng(child))
     t0 = time.perf_counter()
-    smp.sample(n_transitions + 1)
-    return n_transitions, smp.n_reject, time.perf_counter() - t0
+    out = smp.sample(n_transitions + 1)
+    return n_transitions, smp.n_reject, time.perf_counter() - t0, out[1:, 0].copy()
 
 
 def run_all_cores(workload, kind, n_transitions, n_procs=None):
@@ -52,8 +52,17 @@ def run_all_cores(workload, kind, n_transitions, n_procs=None):
         res = pool.map(run_chain, [(workload, kind, i, n_transitions) for i in range(n_procs)])
         wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
-    return {"value": total / wall, "cores": n_procs, "wall_s": wall, "transitions": total,
-            "mean_rejections": sum(r[1] for r in res) / total}
+    out = {"value": total / wall, "cores": n_procs, "wall_s": wall, "transitions": total,
+           "mean_rejections": sum(r[1] for r in res) / total}
+    try:  # ESS of the first coordinate over the CPU chains, same estimator as the GPU arm
+        from . import ess
+        trace = np.stack([r[3] for r in res])
+        rel = ess.ess_multichain(trace, min(trace.shape[1] // 2, 400)) / trace.size
+        out["relative_ess_x0"] = float(rel)
+        out["ess_per_sec"] = float(rel * out["value"])
+    except Exception as exc:
+        out["ess_error"] = str(exc)
+    return out
 
 
 def _warm(_):

@@ -448,6 +448,19 @@ def test_launcher_and_bingham_relative_ess(golden):
     assert 0.05 < out["sss-shrink"] < 0.5 and out["sss-shrink"] < out["sss-reject"]
 
 
+@pytest.mark.parametrize("d,vmax,want", [(10, 30.0, {"sss-reject": 1.58, "sss-shrink": 0.54}),
+                                         (50, 300.0, {"sss-reject": 1.57, "sss-shrink": 0.20})])
+def test_published_mean_geodesic_step_on_bingham(d, vmax, want):
+    """BASELINE.md / scripts/Bingham.ipynb:276-279, 515-518: mean geodesic distance between successive samples
+    on random_bingham(d, vmax, 0, eigensystem=True, seed=6982), chains started at the mode."""
+    pdf = gs.random_bingham(d, vmax, 0.0, True, 6982)
+    x0 = torch.as_tensor(np.tile(pdf.mode, (128, 1))).cuda()
+    for method, target in want.items():
+        s = gs.SamplerLauncher(pdf, x0, 3000, burnin=0.1, seed=11).run(method)  # (N, n, d) on the device
+        step = torch.arccos(torch.clamp((s[:, 1:] * s[:, :-1]).sum(-1), -1, 1)).mean().item()
+        assert abs(step - target) <= 0.04, (method, step, target)
+
+
 # ------------------------------------------------------------------ C-ABI details: thinning, logp / rejection outputs, edge shapes
 def _run_raw(pdf, cls, x0, seed, n_steps, thin, path):
     """geosss_sampler_run through the Python wrapper's private hook, with every optional output."""
