@@ -69,6 +69,8 @@ struct BinghamGc {
             c.qxx = fmaf(xi, ax, c.qxx); c.qxu = fmaf(xi, au, c.qxu); c.quu = fmaf(ui, au, c.quu);
         }
     }
+    // the direction was accumulated unscaled: u = inp * p
+    __device__ __forceinline__ void scale_u(Coef& c, float inp) const { c.qxu *= inp; c.quu *= inp * inp; c.bu *= inp; }
     __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const {
         float dlt = sn * fmaf(sn, c.quu - c.qxx, 2.f * cs * c.qxu);
         if (b) dlt += fmaf(cs - 1.f, c.bx, sn * c.bu);
@@ -79,18 +81,22 @@ struct BinghamGc {
 
 struct CurvedGc {
     struct Coef { float gx[GC_MAX_KNOTS], gu[GC_MAX_KNOTS], best0; };
-    const float* knotsT;  // shared (d, M): knotsT[j * M + m]
+    const float* knotsT;  // shared (d, MP): knotsT[j * MP + m], MP = 4 ceil(M/4), zero for m >= M (float4 loads)
     const float* ca;      // shared (M-1)
     const float* isa;     // shared (M-1) 1 / (sin(ang) + 1e-10)
     const float* sa;      // shared (M-1)
     float kappa;
     int d, M;
 
-    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)p.M * p.d + 3 * (size_t)(p.M - 1); }
+    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)((p.M + 3) & ~3) * p.d + 3 * (size_t)(p.M - 1) + 4; }
     __device__ void stage(const GcParams& p, float* sm) {
         d = p.d; M = p.M; kappa = p.kappa;
-        for (int i = threadIdx.x; i < M * d; i += blockDim.x) { const int m = i / d, j = i - m * d; sm[j * M + m] = p.a0[i]; }
-        float* c_ = sm + M * d;
+        const int MP = (M + 3) & ~3;
+        for (int i = threadIdx.x; i < MP * d; i += blockDim.x) {
+            const int j = i / MP, m = i - j * MP;
+            sm[i] = m < M ? p.a0[m * d + j] : 0.f;
+        }
+        float* c_ = sm + MP * d;
         float* is_ = c_ + (M - 1);
         float* s_ = is_ + (M - 1);
         for (int i = threadIdx.x; i < M - 1; i += blockDim.x) { c_[i] = p.a1[i]; s_[i] = p.a2[i]; is_[i] = 1.f / (p.a2[i] + 1e-10f); }
@@ -101,9 +107,21 @@ struct CurvedGc {
         for (int m = 0; m < GC_MAX_KNOTS; ++m) { c.gx[m] = 0.f; c.gu[m] = 0.f; }
     }
     __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
-        const float* col = knotsT + j * M;
+        const int nq = (M + 3) >> 2;  // warp-uniform
+        const float4* col = reinterpret_cast<const float4*>(knotsT + j * (nq << 2));
 #pragma unroll
-        for (int m = 0; m < GC_MAX_KNOTS; ++m) if (m < M) { const float k = col[m]; c.gx[m] = fmaf(k, xj, c.gx[m]); c.gu[m] = fmaf(k, uj, c.gu[m]); }
+        for (int q = 0; q < GC_MAX_KNOTS / 4; ++q) if (q < nq) {
+            const float4 k = col[q];
+            c.gx[4 * q] = fmaf(k.x, xj, c.gx[4 * q]);         c.gu[4 * q] = fmaf(k.x, uj, c.gu[4 * q]);
+            c.gx[4 * q + 1] = fmaf(k.y, xj, c.gx[4 * q + 1]); c.gu[4 * q + 1] = fmaf(k.y, uj, c.gu[4 * q + 1]);
+            c.gx[4 * q + 2] = fmaf(k.z, xj, c.gx[4 * q + 2]); c.gu[4 * q + 2] = fmaf(k.z, uj, c.gu[4 * q + 2]);
+            c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]); c.gu[4 * q + 3] = fmaf(k.w, uj, c.gu[4 * q + 3]);
+        }
+    }
+    // the direction was accumulated unscaled: u = inp * p
+    __device__ __forceinline__ void scale_u(Coef& c, float inp) const {
+#pragma unroll
+        for (int m = 0; m < GC_MAX_KNOTS; ++m) c.gu[m] *= inp;
     }
     // max over segments of x(theta) . nearest-point, first segment wins ties (argmin of arccos)
     __device__ __forceinline__ float best_dot(const Coef& c, float cs, float sn) const {
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
     typename Policy::Coef co;
     pol.begin(co);
     float lo = 0.f, hi = 2.f, lnu = 0.f, dl_acc = 0.f, lp_x = 0.f;
-    float sn = 0.f, cs = 1.f;
+    float sn = 0.f, cs = 1.f, u_scale = 1.f;  // us[] holds the UNSCALED tangent p; u = u_scale * p
     int t = live ? 0 : n_steps;
     int r = 0, batch = 0;
     bool inloop = false, pending = false, moved = false;
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
         // apply the accepted move, renormalise (|x| would otherwise drift in fp32), store
         float xx = 0.f;
         for (int j = 0; j < d; ++j) {
-            const float v = moved ? fmaf(cs, xs[j], sn * us[j]) : xs[j];
+            const float v = moved ? fmaf(cs, xs[j], (sn * u_scale) * us[j]) : xs[j];
             xs[j] = v;
             xx = fmaf(v, v, xx);
         }
@@ -241,10 +259,11 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
                 if (!aux_in_last) { const U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
                 float pp = 0.f;
                 for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); us[j] = p; pp = fmaf(p, p, pp); }
-                const float inp = rsqrtf(pp);
+                u_scale = rsqrtf(pp);
                 pol.begin(co);
-                for (int j = 0; j < d; ++j) { const float uj = us[j] * inp; us[j] = uj; pol.accumulate(co, j, xs[j], uj); }
+                for (int j = 0; j < d; ++j) pol.accumulate(co, j, xs[j], us[j]);
                 pol.finish(co, xs, us);
+                pol.scale_u(co, u_scale);
                 lp_x = pol.logp_x(co);
                 lnu = LN2 * fast_lg2(u01(aux0, 0.f));
                 if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }

@@ -153,7 +153,7 @@ struct CurvedLp {
     using Params = LpParams;
     static __host__ __device__ int dim(const Params& p) { return p.d; }
     CurvedGc g;
-    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)p.M * p.d + 3 * (size_t)(p.M - 1); }
+    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)((p.M + 3) & ~3) * p.d + 3 * (size_t)(p.M - 1) + 4; }
     __device__ void stage(const LpParams& p, float* sm) {
         GcParams q{};
         q.a0 = p.a0; q.a1 = p.a1; q.a2 = p.a2; q.d = p.d; q.M = p.M; q.kappa = p.kappa;
