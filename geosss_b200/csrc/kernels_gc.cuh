@@ -71,6 +71,14 @@ struct BinghamGc {
     }
     // the direction was accumulated unscaled: u = inp * p
     __device__ __forceinline__ void scale_u(Coef& c, float inp) const { c.qxu *= inp; c.quu *= inp * inp; c.bu *= inp; }
+    // another lane's coefficients (cooperative reject batches)
+    __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
+        Coef o;
+        o.qxx = __shfl_sync(0xffffffffu, c.qxx, src); o.qxu = __shfl_sync(0xffffffffu, c.qxu, src);
+        o.quu = __shfl_sync(0xffffffffu, c.quu, src); o.bx = __shfl_sync(0xffffffffu, c.bx, src);
+        o.bu = __shfl_sync(0xffffffffu, c.bu, src);
+        return o;
+    }
     __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const {
         float dlt = sn * fmaf(sn, c.quu - c.qxx, 2.f * cs * c.qxu);
         if (b) dlt += fmaf(cs - 1.f, c.bx, sn * c.bu);
@@ -122,6 +130,18 @@ struct CurvedGc {
     __device__ __forceinline__ void scale_u(Coef& c, float inp) const {
 #pragma unroll
         for (int m = 0; m < GC_MAX_KNOTS; ++m) c.gu[m] *= inp;
+    }
+    // another lane's coefficients (cooperative reject batches)
+    __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
+        Coef o;
+        const int nq = (M + 3) >> 2;
+#pragma unroll
+        for (int m = 0; m < GC_MAX_KNOTS; ++m) {
+            if ((m >> 2) < nq) { o.gx[m] = __shfl_sync(0xffffffffu, c.gx[m], src); o.gu[m] = __shfl_sync(0xffffffffu, c.gu[m], src); }
+            else { o.gx[m] = 0.f; o.gu[m] = 0.f; }
+        }
+        o.best0 = __shfl_sync(0xffffffffu, c.best0, src);
+        return o;
     }
     // max over segments of x(theta) . nearest-point, first segment wins ties (argmin of arccos)
     __device__ __forceinline__ float best_dot(const Coef& c, float cs, float sn) const {
@@ -274,7 +294,66 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
             }
         }
 
-        if (inloop) {
+        // cooperative batches for the reject sampler: see k_vmf_fast (kernels_fast.cuh)
+        bool own_batch = inloop;
+        if (KIND == REJECT) {
+            const unsigned m_now = __ballot_sync(0xffffffffu, inloop);
+            const int nW = __popc(m_now);
+            if (nW > 0 && nW <= 16) {
+                own_batch = false;
+                const int lane = threadIdx.x & 31;
+                const int lg = 31 - __clz(32 / nW);
+                const int g = 1 << lg;
+                const int grp = lane >> lg, sub = lane & (g - 1);
+                const bool helping = grp < nW;
+                const int owner = __fns(m_now, 0, (helping ? grp : 0) + 1);
+                const typename Policy::Coef co_o = pol.fetch(co, owner);
+                const float lnu_o = __shfl_sync(0xffffffffu, lnu, owner);
+                const int batch_o = __shfl_sync(0xffffffffu, batch, owner);
+                const int t_o = __shfl_sync(0xffffffffu, t, owner);
+                int jacc = 0x7fffffff;
+                float sn_h = 0.f, cs_h = 1.f, dl_h = 0.f;
+                if (helping) {
+                    const uint64_t chain_o = a.chain0 + (uint64_t)(c - lane + owner);
+                    const uint64_t step_o = a.step0 + (uint64_t)(t_o - 1);
+                    const U4 w = philox4x32_10(U4{(uint32_t)chain_o, (uint32_t)(chain_o >> 32), (uint32_t)step_o,
+                                                  (((uint32_t)(step_o >> 32) & 0xFFFFu) << 16) | (uint32_t)(pb + batch_o + sub)},
+                                               dr.k0, dr.k1);
+                    const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
+                    float sb_[FAST_BATCH], cb_[FAST_BATCH], dl[FAST_BATCH];
+#pragma unroll
+                    for (int i = 0; i < FAST_BATCH; ++i) {
+                        fast_sincospi(fmaf(2.0f, u01(wi[i], 0.f), 0.f), sb_[i], cb_[i]);
+                        dl[i] = pol.delta(co_o, cb_[i], sb_[i]);
+                    }
+#pragma unroll
+                    for (int i = FAST_BATCH - 1; i >= 0; --i)
+                        if (dl[i] > lnu_o) { jacc = FAST_BATCH * sub + i; sn_h = sb_[i]; cs_h = cb_[i]; dl_h = dl[i]; }
+                }
+                int jmin = jacc;
+                for (int o = g >> 1; o > 0; o >>= 1) jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+                const int rank = __popc(m_now & ((1u << lane) - 1u));
+                const int src = (inloop ? rank : 0) << lg;
+                const int jmine = __shfl_sync(0xffffffffu, jmin, src);
+                const int wl = src + (jmine == 0x7fffffff ? 0 : jmine / FAST_BATCH);
+                const float sn_w = __shfl_sync(0xffffffffu, sn_h, wl);
+                const float cs_w = __shfl_sync(0xffffffffu, cs_h, wl);
+                const float dl_w = __shfl_sync(0xffffffffu, dl_h, wl);
+                if (inloop) {
+                    if (jmine != 0x7fffffff) {
+                        sn = sn_w; cs = cs_w; dl_acc = dl_w;
+                        r += jmine;
+                        moved = true; inloop = false; pending = true;
+                    } else {
+                        r += FAST_BATCH * g;
+                        batch += g;
+                        if (r >= MAX_PROPOSALS || !(lp_x == lp_x)) { inloop = false; pending = true; }
+                    }
+                }
+            }
+        }
+
+        if (own_batch) {
             const U4 w = dr.block(pb + batch);
             const uint32_t wi[FAST_BATCH] = {w.x, w.y, w.z, w.w};
             float tt[FAST_BATCH], sb_[FAST_BATCH], cb_[FAST_BATCH], dl[FAST_BATCH];
