@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -569,45 +570,61 @@ extern "C" int geosss_sampler_get_state_host(geosss_sampler_t s, double* x_host,
 }
 
 namespace {
+// Streams, events and the two device staging buffers of the host-buffer pipeline.  They are kept
+// per device between calls (allocation and release of 2 x 64 MB cost more than the kernels they
+// serve); a call takes the pipe of the current device under a lock and grows it when needed.
 struct HostPipe {
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t filled[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
     void* buf[2] = {nullptr, nullptr};
-    ~HostPipe() {
-        for (int i = 0; i < 2; ++i) {
-            if (filled[i]) cudaEventDestroy(filled[i]);
-            if (drained[i]) cudaEventDestroy(drained[i]);
-            if (buf[i]) cudaFree(buf[i]);
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (!compute) {
+            CU(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CU(cudaEventCreateWithFlags(&filled[i], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+            }
         }
-        if (compute) cudaStreamDestroy(compute);
-        if (copy) cudaStreamDestroy(copy);
+        if (bytes > cap) {
+            for (int i = 0; i < 2; ++i) {
+                if (buf[i]) CU(cudaFree(buf[i]));
+                buf[i] = nullptr;
+            }
+            cap = 0;
+            for (int i = 0; i < 2; ++i) CU(cudaMalloc(&buf[i], bytes));
+            cap = bytes;
+        }
+        return 0;
     }
 };
+constexpr int MAX_DEVICES = 64;
+HostPipe g_pipes[MAX_DEVICES];
+std::mutex g_pipe_mutex;
 }  // namespace
 
 // n_skip transitions without output, then n_keep transitions whose states stream to the host:
 // chunk i is sampled into buf[i & 1] on one stream while chunk i-1 drains over PCIe on another.
 extern "C" int geosss_sampler_run_host(geosss_sampler_t s, int64_t n_skip, int64_t n_keep, void* samples_host) {
     if (!s || n_skip < 0 || n_keep < 0 || (n_keep > 0 && !samples_host)) return fail(GEOSSS_E_INVALID, "run_host: bad arguments");
-    HostPipe h;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(GEOSSS_E_UNSUPPORTED, "run_host: device index out of range");
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    HostPipe& h = g_pipes[dev];
     CU(cudaDeviceSynchronize());  // earlier work on other streams (set_state, run) must have landed
-    CU(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
-    int rc = 0;
+    const size_t row = (size_t)s->N * s->t->d * s->esize();  // one retained state of every chain
+    int64_t chunk = (int64_t)((size_t)(64u << 20) / row);
+    if (chunk < 1) chunk = 1;
+    if (n_keep > 0 && chunk > n_keep) chunk = n_keep;
+    int rc = h.ensure(n_keep > 0 ? (size_t)chunk * row : 0);
+    if (rc) return rc;
     if (n_skip > 0) {
         rc = geosss_sampler_run(s, n_skip, 1, nullptr, nullptr, nullptr, h.compute);
         if (rc) return rc;
     }
     if (n_keep > 0) {
-        const size_t row = (size_t)s->N * s->t->d * s->esize();  // one retained state of every chain
-        int64_t chunk = (int64_t)((size_t)(64u << 20) / row);
-        if (chunk < 1) chunk = 1;
-        if (chunk > n_keep) chunk = n_keep;
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaMalloc(&h.buf[i], (size_t)chunk * row));
-            CU(cudaEventCreateWithFlags(&h.filled[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&h.drained[i], cudaEventDisableTiming));
-        }
         unsigned char* out = static_cast<unsigned char*>(samples_host);
         int64_t done = 0;
         for (int i = 0; done < n_keep; ++i) {

@@ -209,7 +209,8 @@ class Sampler:
         else:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
             if keeps_current:
-                buf[0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype)
+                cur = self._host_state if self.rng.steps_done == 0 else self.state.reshape(self.N, self.d)
+                buf[0] = torch.as_tensor(cur, dtype=self._tdtype)
             dst = buf[1:] if keeps_current else buf
             with torch.cuda.device(self.device):
                 _lib.check(lib.geosss_sampler_run_host(h, n_skip, n_new, dst.data_ptr() if n_new else None))
