@@ -108,7 +108,8 @@ struct geosss_sampler {
 
 // ------------------------------------------------------------------ fast-path dispatch
 static size_t gc_smem_bytes(const geosss_target* t, const GcParams& p) {
-    const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p) : CurvedGc::smem_floats(p);
+    const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p)
+                       : t->kind == TGT_VMF_MIX ? VmfGc::smem_floats(p) : CurvedGc::smem_floats(p);
     return (2 * (size_t)t->d * GC_BLOCK + pol) * sizeof(float);
 }
 
@@ -119,6 +120,8 @@ static GcParams gc_params(const geosss_target* t) {
         p.diag = t->diag;
         p.a0 = t->diag ? t->Adiag.f : t->A.f;
         p.a1 = t->has_b ? t->b.f : nullptr;
+    } else if (t->kind == TGT_VMF_MIX) {
+        p.M = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f;
     } else {
         p.M = t->M; p.kappa = (float)t->kappa;
         p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
@@ -128,7 +131,11 @@ static GcParams gc_params(const geosss_target* t) {
 
 // 0 when a float32 throughput kernel exists for this target / shape
 static int target_fast_supported(const geosss_target* t) {
-    if (t->kind == TGT_VMF_MIX) return fast_supported(t->kind, t->d, t->K, t->single);
+    if (t->kind == TGT_VMF_MIX) {
+        if (!fast_supported(t->kind, t->d, t->K, t->single)) return 0;           // register-resident kernel
+        if (t->K > GC_MAX_K) return -1;
+        return gc_smem_bytes(t, gc_params(t)) <= 200 * 1024 ? 0 : -1;           // shared-memory kernel
+    }
     if (t->kind == TGT_BINGHAM || t->kind == TGT_CURVED_VMF) {
         if (t->kind == TGT_CURVED_VMF && t->M > GC_MAX_KNOTS) return -1;
         return gc_smem_bytes(t, gc_params(t)) <= 200 * 1024 ? 0 : -1;
@@ -159,6 +166,7 @@ template <class Policy> static int launch_gc(const geosss_target* t, int kind, c
 }
 
 static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {
+    if (t->kind == TGT_VMF_MIX && fast_supported(t->kind, t->d, t->K, t->single)) return launch_gc<VmfGc>(t, kind, a, st);
     if (t->kind == TGT_VMF_MIX) {
         int rc = launch_fast(t->kind, kind, t->d, t->K, t->h_mu.data(), t->h_const.data(), a, st);
         if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));

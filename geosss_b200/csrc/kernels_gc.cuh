@@ -166,6 +166,75 @@ struct CurvedGc {
     __device__ __forceinline__ float logp_x(const Coef& c) const { return kappa * c.best0; }
 };
 
+// vMF mixture of any dimension that fits shared memory and up to GC_MAX_K components (the register-
+// resident k_vmf_fast covers d <= 16, K <= 8): scores mu_k . y = c A_k + s B_k as in kernels_fast.cuh,
+// log p(y) - log p(x) through a max-shifted base-2 log-sum-exp.
+constexpr int GC_MAX_K = 16;
+struct VmfGc {
+    struct Coef { float A[GC_MAX_K], B[GC_MAX_K], lp2; };
+    const float* muT;  // shared (d, KP): muT[j * KP + k] * log2(e), KP = 4 ceil(K/4), zero padded
+    const float* c2;   // shared (KP): constants * log2(e), -inf for the padding
+    int d, K;
+
+    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)((p.M + 3) & ~3) * (p.d + 1) + 4; }
+    __device__ void stage(const GcParams& p, float* sm) {  // p.M carries K, a0 = mu (K,d), a1 = consts (K)
+        d = p.d; K = p.M;
+        const int KP = (K + 3) & ~3;
+        constexpr float L2E = 1.4426950408889634f;
+        for (int i = threadIdx.x; i < KP * d; i += blockDim.x) {
+            const int j = i / KP, k = i - j * KP;
+            sm[i] = k < K ? p.a0[k * d + j] * L2E : 0.f;
+        }
+        float* c_ = sm + KP * d;
+        for (int i = threadIdx.x; i < KP; i += blockDim.x) c_[i] = i < K ? p.a1[i] * L2E : -INFINITY;
+        muT = sm; c2 = c_;
+    }
+    __device__ __forceinline__ void begin(Coef& c) const {
+#pragma unroll
+        for (int k = 0; k < GC_MAX_K; ++k) { c.A[k] = 0.f; c.B[k] = 0.f; }
+    }
+    __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
+        const int nq = (K + 3) >> 2;
+        const float4* col = reinterpret_cast<const float4*>(muT + j * (nq << 2));
+#pragma unroll
+        for (int q = 0; q < GC_MAX_K / 4; ++q) if (q < nq) {
+            const float4 m = col[q];
+            c.A[4 * q] = fmaf(m.x, xj, c.A[4 * q]);         c.B[4 * q] = fmaf(m.x, uj, c.B[4 * q]);
+            c.A[4 * q + 1] = fmaf(m.y, xj, c.A[4 * q + 1]); c.B[4 * q + 1] = fmaf(m.y, uj, c.B[4 * q + 1]);
+            c.A[4 * q + 2] = fmaf(m.z, xj, c.A[4 * q + 2]); c.B[4 * q + 2] = fmaf(m.z, uj, c.B[4 * q + 2]);
+            c.A[4 * q + 3] = fmaf(m.w, xj, c.A[4 * q + 3]); c.B[4 * q + 3] = fmaf(m.w, uj, c.B[4 * q + 3]);
+        }
+    }
+    __device__ __forceinline__ void scale_u(Coef& c, float inp) const {
+#pragma unroll
+        for (int k = 0; k < GC_MAX_K; ++k) c.B[k] *= inp;
+    }
+    __device__ __forceinline__ float lse2(const Coef& c, float cs, float sn) const {
+        const int KP = (K + 3) & ~3;
+        float e[GC_MAX_K], m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < GC_MAX_K; ++k) if (k < KP) { e[k] = fmaf(cs, c.A[k], fmaf(sn, c.B[k], c2[k])); m = fmaxf(m, e[k]); }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < GC_MAX_K; ++k) if (k < KP) acc += fast_ex2(e[k] - m);
+        return m + fast_lg2(acc);
+    }
+    template <class V> __device__ __forceinline__ void finish(Coef& c, V, V) const { c.lp2 = lse2(c, 1.f, 0.f); }
+    __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const { return 0.6931471805599453f * (lse2(c, cs, sn) - c.lp2); }
+    __device__ __forceinline__ float logp_x(const Coef& c) const { return 0.6931471805599453f * c.lp2; }
+    __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
+        Coef o;
+        const int nq = (K + 3) >> 2;
+#pragma unroll
+        for (int k = 0; k < GC_MAX_K; ++k) {
+            if ((k >> 2) < nq) { o.A[k] = __shfl_sync(0xffffffffu, c.A[k], src); o.B[k] = __shfl_sync(0xffffffffu, c.B[k], src); }
+            else { o.A[k] = 0.f; o.B[k] = 0.f; }
+        }
+        o.lp2 = __shfl_sync(0xffffffffu, c.lp2, src);
+        return o;
+    }
+};
+
 // column view of one lane's vector in shared memory
 struct SCol {
     float* p;

@@ -304,6 +304,32 @@ def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, c
     assert clean >= 0.9 * N * n, (clean, N * n)
 
 
+@pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
+                                      (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
+@pytest.mark.parametrize("d,K,kappa", [(40, 12, 60.0), (17, 3, 200.0), (100, 16, 30.0)])
+def test_high_dimensional_vmf_mixture_fast_kernel(cls, kind, d, K, kappa):
+    """vMF mixtures beyond the register kernel's d <= 16 / K <= 8 run on the shared-memory kernel."""
+    mus = kappa * gs.sample_sphere(d - 1, K, seed=d)
+    w = np.linspace(1.0, 2.0, K)
+    pdf, ora = mixture(mus, w), targets.VMFMixture(mus, w)
+    N, n = 10, (20 if kind == samplers.SHRINK else 6)
+    x0 = gs.sample_sphere(d - 1, N, seed=3)
+    x0[: N // 2] = gs.radial_projection(mus[0] / kappa + 0.2 * x0[: N // 2])
+    smp = cls(pdf, x0, 31337, dtype="float32", path="fast")
+    got = smp.sample(n + 1)
+    assert smp.path == "fast"
+    clean = 0
+    for c in range(N):
+        want, _ = oracle_chain(ora, kind, x0[c], 31337, c, n, d, F32)
+        bad = np.nonzero(np.max(np.abs(got[c, 1:] - want), axis=1) > 1e-4)[0]
+        clean += bad[0] if len(bad) else n
+    assert clean >= 0.9 * N * n, (clean, N * n)
+    # literal fp32 agrees in distribution of rejections (same algorithm): compare mean rejections loosely
+    lit = cls(pdf, x0, 31337, dtype="float32", path="literal")
+    lit.sample(n + 1)
+    assert abs(lit.n_reject - smp.n_reject) <= 0.2 * max(lit.n_reject, 10)
+
+
 def test_shard_invariance_and_continuation(golden):
     """Chains depend on (seed, global chain id, step) only: splitting chains over samplers or
     steps over calls does not change them (what makes 1/2/4/8-GPU runs identical)."""
