@@ -224,6 +224,18 @@ def main_ours(a):
     algo_bytes = N * T * d * 4
     achieved = algo_bytes / avg_launch_s / 1e9
 
+    # compute-side view of the same launch: ALGORITHMIC flops (9d + E (3d + 4 + F_logp),
+    # E = 1 + measured rejections, F_logp = 2Kd + 7K + 2) against the nominal FP32 FMA peak at the measured clock
+    K_mix = 5
+    flops_per_transition = 9 * d + (1.0 + rej) * (3 * d + 4 + 2 * K_mix * d + 7 * K_mix + 2)
+    sm_mhz = clk.get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_ach = flops_per_transition * N * T / avg_launch_s / 1e12
+    roof_compute = {"bound": "fp32 issue (nominal 148 SM x 128 FMA lanes x 2 x SM clock)", "achieved": fp32_ach, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak, "algorithmic_flops_per_transition": flops_per_transition,
+                    "note": "the reference algorithm's flop count; the kernel itself also spends ~45% of its instructions on "
+                            "Philox, Box-Muller and MUFU work that this count ignores (profiles/*k_vmf_fast*)"}
+
     # ESS of the first coordinate (scripts/ess_mixture_vMF.py:233) over the last retained step, all chains of
     # all ranks: autocovariances on the GPU (csrc/diag.cuh), max_lag+2 doubles all-reduced, Geyer cut on the host
     from geosss_b200 import diagnostics
@@ -308,7 +320,7 @@ def main_ours(a):
                              "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
                              "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
                              "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
-                "roofline_log_prob": lp_roof, "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
+                "roofline_compute": roof_compute, "roofline_log_prob": lp_roof, "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
                 "samples_per_sec_per_gpu": value / world}
         print(json.dumps(line))
     if world > 1:

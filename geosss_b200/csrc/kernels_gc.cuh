@@ -38,15 +38,18 @@ struct GcParams {
 // ------------------------------------------------------------------ policies
 struct BinghamGc {
     struct Coef { float qxx, qxu, quu, bx, bu; };
-    const float* A;  // shared: diagonal (d) or dense (d, d)
+    const float* A;  // shared: diagonal (d) or dense (d, dp) with rows padded to dp = 4 ceil(d/4) floats
     const float* b;  // shared or null
-    int d, diag;
+    int d, dp, diag;
 
-    static __host__ __device__ size_t smem_floats(const GcParams& p) { return (size_t)(p.diag ? p.d : p.d * p.d) + (p.a1 ? p.d : 0); }
+    static __host__ __device__ size_t smem_floats(const GcParams& p) {
+        return (size_t)(p.diag ? p.d : p.d * ((p.d + 3) & ~3)) + (p.a1 ? p.d : 0) + 4;
+    }
     __device__ void stage(const GcParams& p, float* sm) {
-        d = p.d; diag = p.diag;
-        const int nA = diag ? d : d * d;
-        for (int i = threadIdx.x; i < nA; i += blockDim.x) sm[i] = p.a0[i];
+        d = p.d; diag = p.diag; dp = (d + 3) & ~3;
+        const int nA = diag ? dp : d * dp;
+        if (diag) { for (int i = threadIdx.x; i < dp; i += blockDim.x) sm[i] = i < d ? p.a0[i] : 0.f; }
+        else for (int i = threadIdx.x; i < nA; i += blockDim.x) { const int r = i / dp, q = i - r * dp; sm[i] = q < d ? p.a0[r * d + q] : 0.f; }
         if (p.a1) for (int i = threadIdx.x; i < d; i += blockDim.x) sm[nA + i] = p.a1[i];
         A = sm;
         b = p.a1 ? sm + nA : nullptr;
@@ -59,14 +62,25 @@ struct BinghamGc {
         }
         if (b) { c.bx = fmaf(b[j], xj, c.bx); c.bu = fmaf(b[j], uj, c.bu); }
     }
+    // dense A: (A x)_i and (A u)_i for four rows i at a time.  A is symmetric, so A[i..i+3][j] is read as
+    // the contiguous A[j][i..i+3] (one 16-byte broadcast load); per j that is 3 loads for 8 FMAs.
     template <class V> __device__ __forceinline__ void finish(Coef& c, V xs, V us) const {
         if (diag) return;
-        for (int i = 0; i < d; ++i) {
-            const float* row = A + i * d;
-            float ax = 0.f, au = 0.f;
-            for (int j = 0; j < d; ++j) { const float aij = row[j]; ax = fmaf(aij, xs[j], ax); au = fmaf(aij, us[j], au); }
-            const float xi = xs[i], ui = us[i];
-            c.qxx = fmaf(xi, ax, c.qxx); c.qxu = fmaf(xi, au, c.qxu); c.quu = fmaf(ui, au, c.quu);
+        for (int i = 0; i < dp; i += 4) {
+            float ax[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < d; ++j) {
+                const float4 a4 = *reinterpret_cast<const float4*>(A + j * dp + i);
+                const float xj = xs[j], uj = us[j];
+                ax[0] = fmaf(a4.x, xj, ax[0]); au[0] = fmaf(a4.x, uj, au[0]);
+                ax[1] = fmaf(a4.y, xj, ax[1]); au[1] = fmaf(a4.y, uj, au[1]);
+                ax[2] = fmaf(a4.z, xj, ax[2]); au[2] = fmaf(a4.z, uj, au[2]);
+                ax[3] = fmaf(a4.w, xj, ax[3]); au[3] = fmaf(a4.w, uj, au[3]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (i + q < d) {
+                const float xi = xs[i + q], ui = us[i + q];
+                c.qxx = fmaf(xi, ax[q], c.qxx); c.qxu = fmaf(xi, au[q], c.qxu); c.quu = fmaf(ui, au[q], c.quu);
+            }
         }
     }
     // the direction was accumulated unscaled: u = inp * p

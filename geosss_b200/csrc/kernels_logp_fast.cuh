@@ -125,7 +125,9 @@ struct BinghamLp {
     using Params = LpParams;
     static __host__ __device__ int dim(const Params& p) { return p.d; }
     BinghamGc g;
-    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)(p.diag ? p.d : p.d * p.d) + (p.a1 ? p.d : 0); }
+    static __host__ __device__ size_t smem_floats(const LpParams& p) {
+        return (size_t)(p.diag ? p.d : p.d * ((p.d + 3) & ~3)) + (p.a1 ? p.d : 0) + 4;
+    }
     __device__ void stage(const LpParams& p, float* sm) {
         GcParams q{};
         q.a0 = p.a0; q.a1 = p.a1; q.d = p.d; q.diag = p.diag;
@@ -137,11 +139,16 @@ struct BinghamLp {
         if (g.diag) {
             for (int j = 0; j < d; ++j) q = fmaf(g.A[j] * row[j], row[j], q);
         } else {
-            for (int i = 0; i < d; ++i) {
-                const float* ar = g.A + i * d;
-                float ax = 0.f;
-                for (int j = 0; j < d; ++j) ax = fmaf(ar[j], row[j], ax);
-                q = fmaf(row[i], ax, q);
+            for (int i = 0; i < g.dp; i += 4) {  // four rows of A x at a time (A symmetric: column block = row block)
+                float ax[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < d; ++j) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(g.A + j * g.dp + i);
+                    const float xj = row[j];
+                    ax[0] = fmaf(a4.x, xj, ax[0]); ax[1] = fmaf(a4.y, xj, ax[1]);
+                    ax[2] = fmaf(a4.z, xj, ax[2]); ax[3] = fmaf(a4.w, xj, ax[3]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (i + k < d) q = fmaf(row[i + k], ax[k], q);
             }
         }
         if (g.b) for (int j = 0; j < d; ++j) q = fmaf(g.b[j], row[j], q);
