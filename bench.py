@@ -224,6 +224,16 @@ def main_ours(a):
     algo_bytes = N * T * d * 4
     achieved = algo_bytes / avg_launch_s / 1e9
 
+    # DRAM traffic of this launch from the committed ncu capture (profiles/r1_traffic.json), when the workload matches
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)["k_vmf_fast<5,12,SHRINK>"]
+        if a.sampler == "shrink" and tr["chains"] == N and tr["transitions_per_step"] == T and a.kappa == 100.0:
+            traffic = tr["quorum_22_default"]["dram_read"] + tr["quorum_22_default"]["dram_write"]
+    except Exception:
+        traffic = None
+
     # compute-side view of the same launch: ALGORITHMIC flops (9d + E (3d + 4 + F_logp),
     # E = 1 + measured rejections, F_logp = 2Kd + 7K + 2) against the nominal FP32 FMA peak at the measured clock
     K_mix = 5
@@ -317,7 +327,7 @@ def main_ours(a):
                         "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs, "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
                 "gpu_launches": a.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
                              "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
                              "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
                 "roofline_compute": roof_compute, "roofline_log_prob": lp_roof, "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,
