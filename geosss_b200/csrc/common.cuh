@@ -61,6 +61,25 @@ template <> struct Const<double> {
     static GEOSSS_HD double bracket_floor() { return 1e-18; }
 };
 
+#if defined(__CUDACC__)
+// MUFU-pipe approximations used by the float32 throughput kernels (relative error ~2^-22)
+__device__ __forceinline__ float fast_ex2(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+#endif
+
 // Strided view of one chain's vector inside a (d, N) column-major workspace: element j of
 // chain c lives at base[c + j*N], so the 32 lanes of a warp touch 32 consecutive words.
 template <typename T> struct SVec {

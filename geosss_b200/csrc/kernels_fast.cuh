@@ -38,22 +38,6 @@ struct VmfFastParams {
     int d;                              // true dimension (<= D)
 };
 
-__device__ __forceinline__ float fast_ex2(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float fast_lg2(float v) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
-__device__ __forceinline__ float fast_sqrt(float v) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
 // (sin, cos) of pi * t for |t| <= 2 on the MUFU pipe (2 MUFU + 7 FMA-pipe instructions instead of the
 // ~25 of sincospif): |error| ~ 5e-7 rad on the angle, then one Newton step puts (c, s) back on the unit
 // circle to fp32 rounding so that y = c x + s u keeps unit norm.  The angle error is a smooth 1e-6-relative

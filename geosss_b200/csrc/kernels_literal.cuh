@@ -8,17 +8,6 @@
 
 namespace geosss {
 
-__device__ __forceinline__ float fast_ex2_lit(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float fast_lg2_lit(float v) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 constexpr int LANE_BLOCK = 128;  // threads per block, lane-per-chain kernels
 constexpr int CPD_WARPS = 4;     // warps (= chains or points) per block, CPD kernels
 
@@ -232,14 +221,14 @@ struct CpdWarpLogPFast {
                 const float e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
                 const float f0 = t0 - moved[3 * k + 3], f1 = t1 - moved[3 * k + 4], f2 = t2 - moved[3 * k + 5];
                 const float d2a = fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), d2b = fmaf(f0, f0, fmaf(f1, f1, f2 * f2));
-                s0 += fast_ex2_lit(fmaf(d2a, q2, lw2[k] + c2m));
-                s1 += fast_ex2_lit(fmaf(d2b, q2, lw2[k + 1] + c2m));
+                s0 += fast_ex2(fmaf(d2a, q2, lw2[k] + c2m));
+                s1 += fast_ex2(fmaf(d2b, q2, lw2[k + 1] + c2m));
             }
             if (k < p.ns) {
                 const float e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
-                s0 += fast_ex2_lit(fmaf(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), q2, lw2[k] + c2m));
+                s0 += fast_ex2(fmaf(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), q2, lw2[k] + c2m));
             }
-            acc += (double)((m0 + 0.6931471805599453f * fast_lg2_lit(s0 + s1)) * p.wt[l]);
+            acc += (double)((m0 + 0.6931471805599453f * fast_lg2(s0 + s1)) * p.wt[l]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
