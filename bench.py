@@ -238,10 +238,13 @@ def main_ours(a):
     # E = 1 + measured rejections, F_logp = 2Kd + 7K + 2) against the nominal FP32 FMA peak at the measured clock
     K_mix = 5
     flops_per_transition = 9 * d + (1.0 + rej) * (3 * d + 4 + 2 * K_mix * d + 7 * K_mix + 2)
-    sm_mhz = clk.get("sm_mhz") or 1965.0
-    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_micro_peaks.json")) as f:
+            fp32_peak, fp32_src = float(json.load(f)["fp32_tflops_sustained"]), "measured FFMA microbenchmark (profiles/r1_micro_peaks.json)"
+    except Exception:
+        fp32_peak, fp32_src = 148 * 128 * 2 * (clk.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "nominal 148 SM x 128 lanes x 2 x SM clock"
     fp32_ach = flops_per_transition * N * T / avg_launch_s / 1e12
-    roof_compute = {"bound": "fp32 issue (nominal 148 SM x 128 FMA lanes x 2 x SM clock)", "achieved": fp32_ach, "peak": fp32_peak,
+    roof_compute = {"bound": "fp32 FMA issue", "peak_source": fp32_src, "achieved": fp32_ach, "peak": fp32_peak,
                     "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak, "algorithmic_flops_per_transition": flops_per_transition,
                     "note": "the reference algorithm's flop count; the kernel itself also spends ~45% of its instructions on "
                             "Philox, Box-Muller and MUFU work that this count ignores (profiles/*k_vmf_fast*)"}
