@@ -8,7 +8,7 @@ Workload (BASELINE.json configs[1], scripts/mixture_vMF.py): mixture of K=5 von 
 components on S^9 (d=10), modes = sample_sphere(9, 5, seed=1234), kappa=100, GeoSSS-shrink,
 65,536 chains PER GPU (weak scaling: each rank owns a disjoint block of global chain ids).
 One "step" = --transitions Markov transitions of every chain, every state retained in HBM
-(step-major (T, N, d) float32), exactly what ``sampler.sample()`` returns.  One step is one
+(chain-major (N, T, d) float32), exactly what ``sampler.sample()`` returns for CUDA input.  One step is one
 launch of the sampler kernel; its output (T*N*40 B >> L2) is larger than L2.
 
 value  = transitions of all chains of all ranks / device time (CUDA events, max over ranks)
@@ -57,7 +57,7 @@ def workload_dict(a):
 def config_dict(a, n_gpus):
     return {"workload": f"C2 vMF mixture d=10 K=5 kappa={a.kappa:g} (scripts/mixture_vMF.py), sss-{a.sampler}",
             "chains_per_gpu": a.chains, "chains_total": a.chains * n_gpus, "transitions_per_step": a.transitions,
-            "retention": "every state, (T,N,d) float32 in HBM", "l2": "outputs_larger_than_L2",
+            "retention": "every state, (N,T,d) float32 in HBM", "l2": "outputs_larger_than_L2",
             "sharding": f"chains x{n_gpus}"}
 
 
@@ -189,12 +189,12 @@ def main_ours(a):
     cls = gs.ShrinkageSphericalSliceSampler if a.sampler == "shrink" else gs.RejectionSphericalSliceSampler
     x0 = gs.sample_sphere(d - 1, N, seed=np.random.SeedSequence(48485).spawn(world)[rank])
     smp = cls(pdf, torch.as_tensor(x0).to(dev), 48385, chain_offset=rank * N)
-    buf = torch.empty((T, N, d), dtype=torch.float32, device=dev)
+    buf = torch.empty((N, T, d), dtype=torch.float32, device=dev)  # chain-major: what sample() returns for CUDA input
 
     # burn-in + warm-up
     smp._run_device(200, None)
     for _ in range(max(a.warmup, 3)):
-        smp._run_device(T, buf)
+        smp._run_device(T, buf, chain_major=True)
     rej0 = int(smp.n_reject_per_chain.sum())
 
     clocks = ClockSampler(local)
@@ -205,7 +205,7 @@ def main_ours(a):
     t_host0 = time.perf_counter()
     for s, e in ev:
         s.record()
-        smp._run_device(T, buf)  # one kernel launch: T transitions of N chains, all states retained
+        smp._run_device(T, buf, chain_major=True)  # one kernel launch: T transitions of N chains, all states retained
         e.record()
     barrier()
     t_host1 = time.perf_counter()
@@ -230,7 +230,7 @@ def main_ours(a):
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tr = json.load(f)["k_vmf_fast<5,12,SHRINK>"]
         if a.sampler == "shrink" and tr["chains"] == N and tr["transitions_per_step"] == T and a.kappa == 100.0:
-            traffic = tr["quorum_22_default"]["dram_read"] + tr["quorum_22_default"]["dram_write"]
+            traffic = tr["chain_major_quorum_22_default"]["dram_read"] + tr["chain_major_quorum_22_default"]["dram_write"]
     except Exception:
         traffic = None
 

@@ -11,6 +11,7 @@ import os
 F32, F64 = 0, 1
 REJECT, SHRINK = 0, 1
 PATH_LITERAL, PATH_FAST = 0, 1
+STEP_MAJOR, CHAIN_MAJOR = 0, 1
 
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
 
@@ -34,13 +35,14 @@ SIGNATURES = {
     "geosss_sampler_set_state": (_i, [_p, _p, _p]),
     "geosss_sampler_get_state": (_i, [_p, _p, _p, _p]),
     "geosss_sampler_run": (_i, [_p, _i64, _i64, _p, _p, _p, _p]),
+    "geosss_sampler_run_layout": (_i, [_p, _i64, _i64, _i, _i64, _i64, _p, _p, _p, _p]),
     "geosss_sampler_run_tape": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     "geosss_sampler_steps_done": (_i64, [_p]),
     "geosss_sampler_destroy": (_i, [_p]),
     "geosss_sampler_set_state_host": (_i, [_p, _pd]),
     "geosss_sampler_get_state_host": (_i, [_p, _pd, _p]),
     "geosss_sampler_run_host": (_i, [_p, _i64, _i64, _p]),
-    "geosss_diag_ess_partials": (_i, [_p, _i, _i64, _i64, _i, _p, _i, _p, _p]),
+    "geosss_diag_ess_partials": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _p, _p]),
     "geosss_sample_host": (_i, [_p, _i, _i, _i, _i64, _pd, _u64, _u64, _i64, _i64, _p, _p]),
 }
 

@@ -516,6 +516,7 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
     a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
     // quorum of the persistent bracket loop (kernels_fast.cuh); tuned on B200, see DESIGN.md
+    a.ss_step = s->N * (int64_t)s->t->d; a.ss_chain = s->t->d; a.sl_step = s->N; a.sl_chain = 1;  // step-major
     a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 20;
     if (const char* q = std::getenv("GEOSSS_QUORUM")) { int v = std::atoi(q); if (v >= 1 && v <= 32) a.quorum = v; }
     return a;
@@ -523,10 +524,23 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
 
 extern "C" int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* samples_out, void* logp_out,
                                   uint32_t* nrej_out, void* stream) {
+    return geosss_sampler_run_layout(s, n_steps, thin, GEOSSS_STEP_MAJOR, 0, 0, samples_out, logp_out, nrej_out, stream);
+}
+
+extern "C" int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, int64_t thin, int layout, int64_t chain_stride,
+                                         int64_t scalar_chain_stride, void* samples_out, void* logp_out, uint32_t* nrej_out,
+                                         void* stream) {
     if (!s || n_steps < 0 || thin < 1) return fail(GEOSSS_E_INVALID, "run: need n_steps >= 0 and thin >= 1");
+    if (layout != GEOSSS_STEP_MAJOR && layout != GEOSSS_CHAIN_MAJOR) return fail(GEOSSS_E_INVALID, "run: unknown output layout");
     if (n_steps == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RunArgs a = base_args(s, n_steps, thin);
+    if (layout == GEOSSS_CHAIN_MAJOR) {
+        const int64_t n_keep = n_steps / thin;
+        a.ss_step = s->t->d; a.ss_chain = chain_stride > 0 ? chain_stride : n_keep * (int64_t)s->t->d;
+        a.sl_step = 1; a.sl_chain = scalar_chain_stride > 0 ? scalar_chain_stride : n_keep;
+        if (a.ss_chain < n_keep * (int64_t)s->t->d || a.sl_chain < n_keep) return fail(GEOSSS_E_INVALID, "run: chain stride smaller than a chain's output");
+    }
     a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
     int rc = s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
     if (rc) return rc;
@@ -681,8 +695,11 @@ extern "C" int geosss_sample_host(geosss_target_t t, int kind, int dtype, int pa
 }
 
 // ------------------------------------------------------------------ diagnostics
-extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int64_t n_draws, int64_t n_chains, int d,
+extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
                                         const void* direction, int max_lag, double* out, void* stream) {
+    if (layout != GEOSSS_STEP_MAJOR && layout != GEOSSS_CHAIN_MAJOR) return fail(GEOSSS_E_INVALID, "diag_ess_partials: unknown layout");
+    const int64_t step_stride = layout == GEOSSS_STEP_MAJOR ? n_chains * (int64_t)d : d;
+    const int64_t chain_stride = layout == GEOSSS_STEP_MAJOR ? d : n_draws * (int64_t)d;
     if (!samples || !direction || !out || n_draws < 2 || n_chains < 1 || d < 1 || max_lag < 1 || max_lag > n_draws)
         return fail(GEOSSS_E_INVALID, "diag_ess_partials: bad arguments");
     const size_t smem = (size_t)n_draws * sizeof(float);
@@ -691,11 +708,11 @@ extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int64_t 
     CU(cudaMemsetAsync(out, 0, (size_t)(max_lag + 2) * sizeof(double), st));
     if (dtype == GEOSSS_F64) {
         CU(cudaFuncSetAttribute(k_ess_partials<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ess_partials<double><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const double*>(samples), n_draws, n_chains, d,
+        k_ess_partials<double><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const double*>(samples), n_draws, step_stride, chain_stride, d,
                                                                              static_cast<const double*>(direction), max_lag, out);
     } else {
         CU(cudaFuncSetAttribute(k_ess_partials<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ess_partials<float><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const float*>(samples), n_draws, n_chains, d,
+        k_ess_partials<float><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const float*>(samples), n_draws, step_stride, chain_stride, d,
                                                                             static_cast<const float*>(direction), max_lag, out);
     }
     CU(cudaGetLastError());

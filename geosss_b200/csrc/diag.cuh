@@ -16,18 +16,20 @@ namespace geosss {
 
 constexpr int DIAG_BLOCK = 256;
 
-// samples: (n, N, d) step-major float; out: max_lag + 2 doubles, zeroed by the caller:
+// samples: draw t of chain c at samples[t * step_stride + c * chain_stride + j] (step-major (n, N, d):
+// (N d, d); chain-major (N, n, d): (d, n d)); out: max_lag + 2 doubles, zeroed by the caller:
 //   out[l] += acov_c(l) for l < max_lag;  out[max_lag] += mean_c;  out[max_lag+1] += mean_c^2
 template <typename T>
-__global__ void __launch_bounds__(DIAG_BLOCK) k_ess_partials(const T* __restrict__ samples, int64_t n, int64_t N, int d,
-                                                             const T* __restrict__ v, int max_lag, double* __restrict__ out) {
+__global__ void __launch_bounds__(DIAG_BLOCK) k_ess_partials(const T* __restrict__ samples, int64_t n, int64_t step_stride,
+                                                             int64_t chain_stride, int d, const T* __restrict__ v, int max_lag,
+                                                             double* __restrict__ out) {
     extern __shared__ float trace[];  // n floats
     __shared__ double red[DIAG_BLOCK / 32];
     __shared__ double mean_s;
     const int64_t c = blockIdx.x;
     double part = 0.0;
     for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
-        const T* row = samples + (t * N + c) * d;
+        const T* row = samples + t * step_stride + c * chain_stride;
         double f = 0.0;
         for (int j = 0; j < d; ++j) f += (double)row[j] * (double)v[j];
         trace[t] = (float)f;

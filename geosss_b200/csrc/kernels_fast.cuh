@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
                     if (++since_keep == (int)a.thin) {
                         const int64_t k = kept++;
                         since_keep = 0;
-                        if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
-                        if (lpo) lpo[k * a.N + c] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
-                        if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+                        if (samples) store_row<D>(samples + (k * a.ss_step + c * a.ss_chain), x, d);
+                        if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                        if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
                         rej_window = 0;
                     }
                     pending = false;
@@ -350,9 +350,9 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
             rej_window += (unsigned)r;
             if (++since_keep == (int)a.thin) {
                 const int64_t k = kept++;
-                if (samples) store_row<D>(samples + (k * a.N + c) * d, x, d);
-                if (lpo) lpo[k * a.N + c] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
-                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+                if (samples) store_row<D>(samples + (k * a.ss_step + c * a.ss_chain), x, d);
+                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             }
         }
 #pragma unroll

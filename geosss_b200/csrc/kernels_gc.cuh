@@ -310,12 +310,12 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
             const int64_t k = kept++;
             since_keep = 0;
             if (samples) {
-                float* o = samples + (k * a.N + c) * d;
+                float* o = samples + (k * a.ss_step + c * a.ss_chain);
                 if ((d & 1) == 0) for (int j = 0; j < d; j += 2) *reinterpret_cast<float2*>(o + j) = make_float2(xs[j], xs[j + 1]);
                 else for (int j = 0; j < d; ++j) o[j] = xs[j];
             }
-            if (lpo) lpo[k * a.N + c] = lp_x + (moved ? dl_acc : 0.f);
-            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp_x + (moved ? dl_acc : 0.f);
+            if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             rej_window = 0;
         }
         pending = false;

@@ -73,6 +73,9 @@ struct RunArgs {
     unsigned long long* n_reject;  // (N) running totals
     int* status;          // (N) tape mode: 0 ok, 1 tape exhausted; may be null
     int quorum;           // fast path: lanes that must wait before a warp runs the prologue (32 = lock-step)
+    // output layout in elements: kept state k of chain c goes to samples[k * ss_step + c * ss_chain + j],
+    // scalars to [k * sl_step + c * sl_chain]  (step-major: (N d, d, N, 1); chain-major: (d, n_keep d, 1, n_keep))
+    int64_t ss_step, ss_chain, sl_step, sl_chain;
 };
 
 template <typename T, int KIND, bool TAPE> struct DrawsOf;
@@ -122,11 +125,11 @@ __global__ void __launch_bounds__(LANE_BLOCK) k_sampler_lane(P p, RunArgs a) {
             const int64_t k = kept++;
             since_keep = 0;
             if (samples) {
-                T* o = samples + (k * a.N + c) * d;
+                T* o = samples + (k * a.ss_step + c * a.ss_chain);
                 for (int j = 0; j < d; ++j) o[j] = x[j];
             }
-            if (lpo) lpo[k * a.N + c] = lp;
-            if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+            if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
+            if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             rej_window = 0;
         }
     }
@@ -177,12 +180,12 @@ __global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd(CpdP<T> p, RunAr
             since_keep = 0;
             if (lane == 0) {
                 if (samples) {
-                    T* o = samples + (k * a.N + c) * 4;
+                    T* o = samples + (k * a.ss_step + c * a.ss_chain);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = xs[j];
                 }
-                if (lpo) lpo[k * a.N + c] = lp;
-                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
+                if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             }
             rej_window = 0;
         }
@@ -288,12 +291,12 @@ __global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd_fast(CpdP<float>
             since_keep = 0;
             if (lane == 0) {
                 if (samples) {
-                    float* o = samples + (k * a.N + c) * 4;
+                    float* o = samples + (k * a.ss_step + c * a.ss_chain);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o[j] = xs[j];
                 }
-                if (lpo) lpo[k * a.N + c] = lp;
-                if (a.nrej) a.nrej[k * a.N + c] = rej_window;
+                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
+                if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             }
             rej_window = 0;
         }

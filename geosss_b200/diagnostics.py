@@ -45,14 +45,17 @@ def ess_from_partials(partials, n_draws, n_chains):
     return ess, ess / (m * n)
 
 
-def ess_partials(samples, direction=None, max_lag=None):
-    """Device partial sums for samples of shape (n_draws, n_chains, d) (the step-major layout the
-    kernels write; pass ``result.permute(1, 0, 2)`` of a ``sample()`` output).  CUDA tensor in,
-    CUDA float64 tensor of length max_lag + 2 out."""
+def ess_partials(samples, direction=None, max_lag=None, chain_major=True):
+    """Device partial sums.  ``samples``: CUDA tensor, ``(n_chains, n_draws, d)`` as returned by
+    ``sample()`` (``chain_major=True``, default) or step-major ``(n_draws, n_chains, d)``.
+    Returns a CUDA float64 tensor of length max_lag + 2."""
     if not (isinstance(samples, torch.Tensor) and samples.is_cuda):
         raise ValueError("ess_partials needs a CUDA tensor; there is no CPU fallback")
     samples = samples.contiguous()
-    n, N, d = samples.shape
+    if chain_major:
+        N, n, d = samples.shape
+    else:
+        n, N, d = samples.shape
     code, tdt, _ = _device.dtype_code(samples.dtype)
     max_lag = int(min(n, max_lag if max_lag is not None else n // 2))
     v = torch.zeros(d, dtype=tdt, device=samples.device)
@@ -62,18 +65,20 @@ def ess_partials(samples, direction=None, max_lag=None):
         v.copy_(torch.as_tensor(np.asarray(direction, dtype=float)))
     out = torch.empty(max_lag + 2, dtype=torch.float64, device=samples.device)
     with torch.cuda.device(samples.device):
-        _lib.check(_lib.lib().geosss_diag_ess_partials(samples.data_ptr(), code, n, N, d, v.data_ptr(), max_lag,
+        _lib.check(_lib.lib().geosss_diag_ess_partials(samples.data_ptr(), code,
+                                                       _lib.CHAIN_MAJOR if chain_major else _lib.STEP_MAJOR, n, N, d, v.data_ptr(), max_lag,
                                                        out.data_ptr(), _device.stream_ptr(samples.device)))
     return out
 
 
-def ess(samples, direction=None, max_lag=None, group=None):
-    """Multi-chain ESS of x . direction (default: first coordinate).  With a torch.distributed
+def ess(samples, direction=None, max_lag=None, group=None, chain_major=True):
+    """Multi-chain ESS of x . direction (default: first coordinate) over ``(n_chains, n_draws, d)``
+    samples (or step-major with ``chain_major=False``).  With a torch.distributed
     ``group`` (or the default group when initialised) the partial sums are all-reduced, so every
     rank returns the ESS of ALL chains of all ranks."""
     import torch.distributed as dist
-    part = ess_partials(samples, direction, max_lag)
-    n, N, _ = samples.shape
+    part = ess_partials(samples, direction, max_lag, chain_major)
+    N, n = (samples.shape[0], samples.shape[1]) if chain_major else (samples.shape[1], samples.shape[0])
     total = torch.tensor([float(N)], dtype=torch.float64, device=samples.device)
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(part, group=group)

@@ -165,11 +165,12 @@ class Sampler:
         self._run_device(1, None)
         return self.state.copy()
 
-    def _run_device(self, n_steps, samples, thin=1, logp=None, nrej=None):
+    def _run_device(self, n_steps, samples, thin=1, logp=None, nrej=None, chain_major=False, chain_stride=0):
         h = self._sampler()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().geosss_sampler_run(
-                h, n_steps, thin, None if samples is None else samples.data_ptr(),
+            _lib.check(_lib.lib().geosss_sampler_run_layout(
+                h, n_steps, thin, _lib.CHAIN_MAJOR if chain_major else _lib.STEP_MAJOR, chain_stride, 0,
+                None if samples is None else samples.data_ptr(),
                 None if logp is None else logp.data_ptr(), None if nrej is None else nrej.data_ptr(),
                 _device.stream_ptr(self.device)))
         self.rng.steps_done += n_steps
@@ -177,11 +178,11 @@ class Sampler:
     def sample(self, n_samples, burnin=0, return_all_samples=False, *, out=None):
         """Markov chain(s) of the requested length (mcmc.py:55-77).
 
-        Returns float arrays of the sampler's dtype: ``(n, d)`` for one chain, ``(N, n, d)`` for N
-        chains (a transposed view of the step-major ``(n, N, d)`` buffer the kernels write).
-        numpy in -> numpy out through pinned host memory, with device->host copies overlapped
-        with sampling; a CUDA tensor as ``initial_state`` -> CUDA tensor out, no host copy.
-        ``out``: optional preallocated ``(n, N, d)`` pinned tensor / CUDA tensor to fill.
+        Returns float arrays of the sampler's dtype: ``(n, d)`` for one chain, ``(N, n, d)`` for N chains.
+        numpy in -> numpy out through pinned host memory (step-major chunks, device->host copies overlapped
+        with sampling; the result is the transposed view of that ``(n, N, d)`` buffer); a CUDA tensor as
+        ``initial_state`` -> contiguous ``(N, n, d)`` CUDA tensor written chain-major by the kernels, no host copy.
+        ``out``: optional preallocated buffer to fill: pinned ``(n, N, d)`` or CUDA ``(N, n, d)``.
         """
         assert n_samples > 0
         burnin = determine_burnin(n_samples, burnin)
@@ -192,20 +193,20 @@ class Sampler:
         h = self._sampler()
         lib = _lib.lib()
         on_device = self._torch_io and self._device_req is not None
-        shape = (n_out, self.N, self.d)
         if out is not None:
-            if tuple(out.shape) != shape or out.dtype != self._tdtype or not out.is_contiguous():
-                raise ValueError(f"out must be a contiguous {self._tdtype} tensor of shape {shape}")
             on_device = out.is_cuda
+        shape = (self.N, n_out, self.d) if on_device else (n_out, self.N, self.d)
+        if out is not None and (tuple(out.shape) != shape or out.dtype != self._tdtype or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous {self._tdtype} tensor of shape {shape}")
         if on_device:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, device=self.device)
             if keeps_current:
-                buf[0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype, device=self.device)
+                buf[:, 0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype, device=self.device)
             if n_skip:
                 self._run_device(n_skip, None)
-            if n_new:
-                self._run_device(n_new, buf[1:] if keeps_current else buf)
-            res = buf.permute(1, 0, 2)
+            if n_new:  # every chain appends its rows behind its own slot 0: (N, n_out, d) chain-major
+                self._run_device(n_new, buf[:, 1:] if keeps_current else buf, chain_major=True, chain_stride=n_out * self.d)
+            res = buf
         else:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
             if keeps_current:

@@ -46,6 +46,11 @@ enum { GEOSSS_REJECT = 0, GEOSSS_SHRINK = 1 };
 /* LITERAL: reference operation order (any target, either dtype).
  * FAST:    float32 throughput kernels that use the great-circle algebra. */
 enum { GEOSSS_PATH_LITERAL = 0, GEOSSS_PATH_FAST = 1 };
+/* layout of retained outputs: STEP_MAJOR (n_keep, N, d) -- contiguous per step, what host streaming wants;
+ * CHAIN_MAJOR (N, n_keep, d) -- the (chain, draw, dim) array the reference's scripts build
+ * (scripts/protein_reg3d3d.py:346-349); every lane appends to its own contiguous stream, so sectors are
+ * completed by the chain that opened them. */
+enum { GEOSSS_STEP_MAJOR = 0, GEOSSS_CHAIN_MAJOR = 1 };
 
 enum {
     GEOSSS_OK = 0,
@@ -100,6 +105,12 @@ int geosss_sampler_get_state(geosss_sampler_t s, void* x, uint64_t* n_reject, vo
  * rejections accumulated since the previous kept state; any of them may be NULL. */
 int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* samples_out,
                        void* logp_out, uint32_t* nrej_out, void* stream);
+/* The same with the output layout chosen: CHAIN_MAJOR writes samples_out (N, n_keep, d), logp_out and
+ * nrej_out (N, n_keep).  chain_stride / scalar_chain_stride (in elements, 0 = dense) let a chain's rows
+ * land inside a larger (N, n_total, d) array, e.g. behind an initial-state slot. */
+int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, int64_t thin, int layout,
+                              int64_t chain_stride, int64_t scalar_chain_stride, void* samples_out,
+                              void* logp_out, uint32_t* nrej_out, void* stream);
 /* Parity mode: draws come from a flat float64 tape per chain, in the order the reference consumes
  * them (d normals, level uniform, [bracket uniform,] one uniform per proposal; next transition).
  * tape_offsets: (N + 1) int64.  status: (N) 0 ok / 1 tape exhausted early, or NULL. */
@@ -134,12 +145,13 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
 
 /* ---- diagnostics ("next" row of the scope table: ESS half of the metric) --------------------- */
 
-/* Partial sums for the multi-chain ESS of f(x) = x . direction over samples (n_draws, n_chains, d)
- * (step-major, device, `dtype`); direction: (d) device, `dtype`.  out: (max_lag + 2) doubles on the
+/* Partial sums for the multi-chain ESS of f(x) = x . direction over samples in STEP_MAJOR
+ * (n_draws, n_chains, d) or CHAIN_MAJOR (n_chains, n_draws, d) layout (device, `dtype`); direction: (d)
+ * device, `dtype`.  out: (max_lag + 2) doubles on the
  * device: out[l] = sum over chains of the biased autocovariance at lag l (geosss/utils.py:91-112
  * per chain), out[max_lag] = sum of chain means, out[max_lag + 1] = sum of squared chain means.
  * The sums are additive over chain shards, so ranks all-reduce `out` and finish on the host. */
-int geosss_diag_ess_partials(const void* samples, int dtype, int64_t n_draws, int64_t n_chains, int d,
+int geosss_diag_ess_partials(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
                              const void* direction, int max_lag, double* out, void* stream);
 
 #ifdef __cplusplus

@@ -450,12 +450,14 @@ def test_device_ess_matches_oracle(dtype):
     xt = torch.as_tensor(x, dtype=dtype).cuda()
     v = np.array([0.5, -1.0, 0.25, 2.0])
     for direction, trace in ((None, x[:, :, 0].T), (v, (x @ v).T)):
-        got, rel = diagnostics.ess(xt, direction, 200)
+        got, rel = diagnostics.ess(xt, direction, 200, chain_major=False)
         want = E.ess_multichain(trace, 200)
+        got_cm, _ = diagnostics.ess(xt.permute(1, 0, 2).contiguous(), direction, 200)  # (chains, draws, d), as sample() returns
+        assert abs(got_cm - got) <= 1e-9 * got
         assert abs(got - want) <= (1e-4 if dtype == torch.float64 else 2e-3) * want  # the trace is staged in fp32 shared memory
         assert abs(rel - want / (n * N)) < 1e-3
     # relative ESS of an AR(1) with r = 0.75 is (1 - r) / (1 + r)
-    assert abs(diagnostics.ess(xt, None, 200)[1] - 0.25 / 1.75) < 0.03
+    assert abs(diagnostics.ess(xt, None, 200, chain_major=False)[1] - 0.25 / 1.75) < 0.03
 
 
 def test_launcher_and_bingham_relative_ess(golden):
@@ -469,7 +471,7 @@ def test_launcher_and_bingham_relative_ess(golden):
         la = gs.SamplerLauncher(pdf, torch.as_tensor(x0).cuda(), 2000, burnin=0.2, seed=3)
         s = la.run(method)  # (N, n, d) CUDA tensor
         assert tuple(s.shape) == (256, 2000, 10)
-        out[method] = diagnostics.ess(s.permute(1, 0, 2), pdf.mode, 500)[1]
+        out[method] = diagnostics.ess(s, pdf.mode, 500)[1]
     assert out["sss-reject"] > 0.6
     assert 0.05 < out["sss-shrink"] < 0.5 and out["sss-shrink"] < out["sss-reject"]
 
