@@ -224,8 +224,54 @@ def golden_misc():
     save("misc", **out)
 
 
+
+
+def golden_api_surface():
+    """Names and call signatures of the reference's public interface for the path (drop-in check)."""
+    import inspect
+    import json
+    from geosss import mcmc, distributions, registration, pointcloud, spherical_curve, sphere, utils
+
+    def params(fn):
+        return [p for p in inspect.signature(fn).parameters if p != "self"]
+
+    items = {
+        "ShrinkageSphericalSliceSampler": mcmc.ShrinkageSphericalSliceSampler,
+        "RejectionSphericalSliceSampler": mcmc.RejectionSphericalSliceSampler,
+        "VonMisesFisher": distributions.VonMisesFisher, "MixtureModel": distributions.MixtureModel,
+        "Bingham": distributions.Bingham, "BinghamFisher": distributions.BinghamFisher,
+        "CurvedVonMisesFisher": distributions.CurvedVonMisesFisher,
+        "CoherentPointDrift": registration.CoherentPointDrift, "GaussianMixtureModel": registration.GaussianMixtureModel,
+        "PointCloud": pointcloud.PointCloud, "SlerpCurve": spherical_curve.SlerpCurve, "SamplerLauncher": utils.SamplerLauncher,
+    }
+    surface = {"classes": {}, "functions": {}}
+    for name, cls in items.items():
+        entry = {"init": params(cls.__init__)}
+        for meth in ("sample", "log_prob", "run", "find_nearest", "transform_positions"):
+            if hasattr(cls, meth):
+                fn = getattr(cls, meth)
+                entry[meth] = params(getattr(fn, "__wrapped__", fn))
+        surface["classes"][name] = entry
+    for name, fn in {"determine_burnin": mcmc.determine_burnin, "random_bingham": distributions.random_bingham,
+                     "brownian_curve": spherical_curve.brownian_curve, "sample_sphere": sphere.sample_sphere,
+                     "radial_projection": sphere.radial_projection, "orthogonal_projection": sphere.orthogonal_projection,
+                     "spherical_projection": sphere.spherical_projection, "sample_subsphere": sphere.sample_subsphere,
+                     "distance": sphere.distance, "quat2matrix": pointcloud.quat2matrix}.items():
+        surface["functions"][name] = params(fn)
+    surface["attributes"] = {"Bingham": ["A", "v", "U", "d", "mode", "max_log_prob"], "MixtureModel": ["pdfs", "weights"],
+                             "VonMisesFisher": ["mu", "d", "kappa", "mode", "max_log_prob"], "CurvedVonMisesFisher": ["curve", "kappa", "d"],
+                             "sampler": ["state", "rng", "target", "n_reject"]}
+    with open(os.path.join(OUT, "api_surface.json"), "w") as f:
+        json.dump(surface, f, indent=1, sort_keys=True)
+    print("api_surface.json written")
+
+
 if __name__ == "__main__":
-    with np.errstate(over="ignore", divide="ignore"):
-        t, s = golden_logprob()
-        golden_trajectories(t, s)
-        golden_misc()
+    if len(sys.argv) > 1 and sys.argv[1] == "api":
+        golden_api_surface()
+    else:
+        with np.errstate(over="ignore", divide="ignore"):
+            t, s = golden_logprob()
+            golden_trajectories(t, s)
+            golden_misc()
+        golden_api_surface()

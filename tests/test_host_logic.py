@@ -104,3 +104,40 @@ def test_counters_are_class_level_like_upstream():
     assert b.log_prob.num_calls == 3 and gs.VonMisesFisher.log_prob.num_calls == 3
     b.log_prob.reset_counters()
     assert a.log_prob.num_calls == 0
+
+
+def test_public_surface_is_a_superset_of_the_reference(golden):
+    """Every class, function, method and argument of the reference's interface for this path
+    (tests/golden/api_surface.json, recorded from the upstream package) exists here under the same
+    name, with the reference's arguments first and in the same order (extras are keyword-only or
+    trailing with defaults)."""
+    import inspect
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "api_surface.json")) as f:
+        ref = json.load(f)
+
+    def params(fn):
+        fn = getattr(fn, "func", fn)  # unwrap the call-counting descriptor
+        return [p for p in inspect.signature(fn).parameters if p != "self"]
+
+    for name, entry in ref["classes"].items():
+        cls = getattr(gs, name)
+        got = params(cls.__init__)
+        assert got[: len(entry["init"])] == entry["init"], (name, got, entry["init"])
+        for meth, want in entry.items():
+            if meth == "init":
+                continue
+            raw = inspect.getattr_static(cls, meth)
+            got = params(raw)
+            assert got[: len(want)] == want, (name, meth, got, want)
+    for name, want in ref["functions"].items():
+        got = params(getattr(gs, name))
+        assert got[: len(want)] == want, (name, got, want)
+    pdf = gs.random_bingham(4, 3.0, 0.0, False, 1)
+    for attr in ref["attributes"]["Bingham"]:
+        assert hasattr(pdf, attr)
+    mix = gs.MixtureModel([gs.VonMisesFisher(np.ones(3))])
+    assert all(hasattr(mix, a) for a in ref["attributes"]["MixtureModel"])
+    assert all(hasattr(mix.pdfs[0], a) for a in ref["attributes"]["VonMisesFisher"])
+    smp = gs.ShrinkageSphericalSliceSampler(mix, np.array([1.0, 0, 0]), 1)
+    assert all(hasattr(smp, a) for a in ref["attributes"]["sampler"])
