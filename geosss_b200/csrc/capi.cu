@@ -347,24 +347,29 @@ template <typename T> static int logp_literal(geosss_target* t, const void* x, v
 
 static int g_sm_count = 0;
 
-template <class Policy> static int launch_logp_tiled(const typename Policy::Params& p, const float* x, float* out, int64_t N, cudaStream_t st) {
-    const size_t smem = ((size_t)LP_STAGES * LP_ROWS * Policy::dim(p) + Policy::smem_floats(p)) * sizeof(float);
+template <class Policy, int ROWS> static int launch_logp_tiled_rows(const typename Policy::Params& p, const float* x, float* out, int64_t N, cudaStream_t st) {
+    const size_t smem = ((size_t)LP_STAGES * ROWS * Policy::dim(p) + Policy::smem_floats(p)) * sizeof(float);
     if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: tile does not fit shared memory");
     if (!g_sm_count) {
         int dev = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    CU(cudaFuncSetAttribute(k_logp_tiled<Policy>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_logp_tiled<Policy, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logp_tiled<Policy>, LP_ROWS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logp_tiled<Policy, ROWS>, ROWS, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t n_tiles = (N + LP_ROWS - 1) / LP_ROWS;
+    const int64_t n_tiles = (N + ROWS - 1) / ROWS;
     int64_t grid = (int64_t)g_sm_count * per_sm;  // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
-    k_logp_tiled<Policy><<<(unsigned)grid, LP_ROWS, smem, st>>>(p, x, out, N);
+    k_logp_tiled<Policy, ROWS><<<(unsigned)grid, ROWS, smem, st>>>(p, x, out, N);
     CU(cudaGetLastError());
     return 0;
+}
+
+// wide rows (d > 48) use 64-row tiles: a two-stage ring of 128 x d floats would leave one or two blocks per SM
+template <class Policy> static int launch_logp_tiled(const typename Policy::Params& p, const float* x, float* out, int64_t N, cudaStream_t st) {
+    return Policy::dim(p) > 48 ? launch_logp_tiled_rows<Policy, 64>(p, x, out, N, st) : launch_logp_tiled_rows<Policy, LP_ROWS>(p, x, out, N, st);
 }
 
 template <int K> static int logp_vmf_const_k(int Dp, const VmfFastParams& P, const float* x, float* o, int64_t N, cudaStream_t st) {

@@ -18,7 +18,7 @@
 
 namespace geosss {
 
-constexpr int LP_ROWS = 128;  // rows per tile = threads per block
+constexpr int LP_ROWS = 128;  // rows per tile = threads per block (64 for wide rows, so that several blocks fit an SM)
 constexpr int LP_STAGES = 2;
 constexpr int LP_MAX_K = 8;
 
@@ -174,14 +174,14 @@ struct CurvedLp {
     }
 };
 
-template <class Policy>
-__global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(const __grid_constant__ typename Policy::Params P, const float* __restrict__ x,
-                                                        float* __restrict__ out, int64_t N) {
+template <class Policy, int ROWS = LP_ROWS>
+__global__ void __launch_bounds__(ROWS) k_logp_tiled(const __grid_constant__ typename Policy::Params P, const float* __restrict__ x,
+                                                     float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(128) unsigned char lp_smem_raw[];
     float* lp_smem = reinterpret_cast<float*>(lp_smem_raw);
     __shared__ __align__(8) uint64_t full[LP_STAGES];
     const int d = Policy::dim(P);
-    const size_t tile_floats = (size_t)LP_ROWS * d;
+    const size_t tile_floats = (size_t)ROWS * d;
     float* stage_buf[LP_STAGES];
 #pragma unroll
     for (int s = 0; s < LP_STAGES; ++s) stage_buf[s] = lp_smem + s * tile_floats;
@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(const __grid_constant__ 
     }
     __syncthreads();
 
-    const int64_t n_tiles = (N + LP_ROWS - 1) / LP_ROWS;
+    const int64_t n_tiles = (N + ROWS - 1) / ROWS;
     const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     // a tile can use the bulk engine when it is complete (byte count a multiple of 16) and x is 16-byte aligned
-    auto bulk_ok = [&](int64_t tile) { return aligned && (tile + 1) * LP_ROWS <= N; };
+    auto bulk_ok = [&](int64_t tile) { return aligned && (tile + 1) * ROWS <= N; };
     auto issue = [&](int64_t tile, int s) {
         if (tile < n_tiles && bulk_ok(tile) && threadIdx.x == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(LP_ROWS) k_logp_tiled(const __grid_constant__ 
     for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
         const int s = it & 1;
         issue(tile + gridDim.x, s ^ 1);  // prefetch the next tile of this block
-        const int64_t row0 = tile * LP_ROWS;
+        const int64_t row0 = tile * ROWS;
         if (bulk_ok(tile)) {
             mbar_wait(&full[s], phase[s]);
             phase[s] ^= 1;
         } else {  // ragged last tile / unaligned input: plain coalesced loads
-            const int64_t n_here = (N - row0 < LP_ROWS ? N - row0 : LP_ROWS) * d;
+            const int64_t n_here = (N - row0 < ROWS ? N - row0 : ROWS) * d;
             for (int64_t i = threadIdx.x; i < n_here; i += blockDim.x) stage_buf[s][i] = x[row0 * d + i];
             __syncthreads();
         }
