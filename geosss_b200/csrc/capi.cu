@@ -107,10 +107,14 @@ struct geosss_sampler {
 };
 
 // ------------------------------------------------------------------ fast-path dispatch
+// the normals stay in shared memory for d < 64 and for dense Bingham (kernels_gc.cuh, STORE); measured on
+// B200: regenerating them pays at d = 100 (+37 %, twice the resident warps) and costs 6 % at d = 50
+static bool gc_store_normals(const geosss_target* t) { return t->d < 64 || (t->kind == TGT_BINGHAM && !t->diag); }
+
 static size_t gc_smem_bytes(const geosss_target* t, const GcParams& p) {
     const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p)
                        : t->kind == TGT_VMF_MIX ? VmfGc::smem_floats(p) : CurvedGc::smem_floats(p);
-    return (2 * (size_t)t->d * GC_BLOCK + pol) * sizeof(float);
+    return ((gc_store_normals(t) ? 2 : 1) * (size_t)t->d * GC_BLOCK + pol) * sizeof(float);
 }
 
 static GcParams gc_params(const geosss_target* t) {
@@ -149,20 +153,21 @@ static int target_fast_supported(const geosss_target* t) {
     return -1;
 }
 
+template <class Policy, int KIND, bool STORE> static int launch_gc_one(const GcParams& p, size_t smem, const RunArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.N + GC_BLOCK - 1) / GC_BLOCK);
+    CU(cudaFuncSetAttribute(k_gc_fast<Policy, KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gc_fast<Policy, KIND, STORE><<<grid, GC_BLOCK, smem, st>>>(p, a);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 template <class Policy> static int launch_gc(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {
     const GcParams p = gc_params(t);
     const size_t smem = gc_smem_bytes(t, p);
-    const unsigned grid = (unsigned)((a.N + GC_BLOCK - 1) / GC_BLOCK);
     if (a.n_steps > 0x7fffffff) return fail(GEOSSS_E_INVALID, "run: at most 2^31-1 transitions per call");
-    if (kind == SHRINK) {
-        CU(cudaFuncSetAttribute(k_gc_fast<Policy, SHRINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gc_fast<Policy, SHRINK><<<grid, GC_BLOCK, smem, st>>>(p, a);
-    } else {
-        CU(cudaFuncSetAttribute(k_gc_fast<Policy, REJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gc_fast<Policy, REJECT><<<grid, GC_BLOCK, smem, st>>>(p, a);
-    }
-    CU(cudaGetLastError());
-    return 0;
+    if (gc_store_normals(t))
+        return kind == SHRINK ? launch_gc_one<Policy, SHRINK, true>(p, smem, a, st) : launch_gc_one<Policy, REJECT, true>(p, smem, a, st);
+    return kind == SHRINK ? launch_gc_one<Policy, SHRINK, false>(p, smem, a, st) : launch_gc_one<Policy, REJECT, false>(p, smem, a, st);
 }
 
 static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {

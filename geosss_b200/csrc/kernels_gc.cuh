@@ -38,6 +38,7 @@ struct GcParams {
 // ------------------------------------------------------------------ policies
 struct BinghamGc {
     struct Coef { float qxx, qxu, quu, bx, bu; };
+    __device__ __forceinline__ bool needs_vector() const { return !diag; }  // dense A: finish() reads the stored normals
     const float* A;  // shared: diagonal (d) or dense (d, dp) with rows padded to dp = 4 ceil(d/4) floats
     const float* b;  // shared or null
     int d, dp, diag;
@@ -83,8 +84,12 @@ struct BinghamGc {
             }
         }
     }
-    // the direction was accumulated unscaled: u = inp * p
-    __device__ __forceinline__ void scale_u(Coef& c, float inp) const { c.qxu *= inp; c.quu *= inp * inp; c.bu *= inp; }
+    // coefficients were accumulated against the raw normals z; the direction is u = inp (z - zx x)
+    __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
+        c.quu = inp * inp * fmaf(zx, fmaf(zx, c.qxx, -2.f * c.qxu), c.quu);
+        c.qxu = inp * fmaf(-zx, c.qxx, c.qxu);
+        c.bu = inp * fmaf(-zx, c.bx, c.bu);
+    }
     // another lane's coefficients (cooperative reject batches)
     __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
         Coef o;
@@ -103,6 +108,7 @@ struct BinghamGc {
 
 struct CurvedGc {
     struct Coef { float gx[GC_MAX_KNOTS], gu[GC_MAX_KNOTS], best0; };
+    __device__ __forceinline__ bool needs_vector() const { return false; }
     const float* knotsT;  // shared (d, MP): knotsT[j * MP + m], MP = 4 ceil(M/4), zero for m >= M (float4 loads)
     const float* ca;      // shared (M-1)
     const float* isa;     // shared (M-1) 1 / (sin(ang) + 1e-10)
@@ -140,10 +146,10 @@ struct CurvedGc {
             c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]); c.gu[4 * q + 3] = fmaf(k.w, uj, c.gu[4 * q + 3]);
         }
     }
-    // the direction was accumulated unscaled: u = inp * p
-    __device__ __forceinline__ void scale_u(Coef& c, float inp) const {
+    // coefficients were accumulated against the raw normals z; the direction is u = inp (z - zx x)
+    __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
 #pragma unroll
-        for (int m = 0; m < GC_MAX_KNOTS; ++m) c.gu[m] *= inp;
+        for (int m = 0; m < GC_MAX_KNOTS; ++m) c.gu[m] = inp * fmaf(-zx, c.gx[m], c.gu[m]);
     }
     // another lane's coefficients (cooperative reject batches)
     __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
@@ -186,6 +192,7 @@ struct CurvedGc {
 constexpr int GC_MAX_K = 16;
 struct VmfGc {
     struct Coef { float A[GC_MAX_K], B[GC_MAX_K], lp2; };
+    __device__ __forceinline__ bool needs_vector() const { return false; }
     const float* muT;  // shared (d, KP): muT[j * KP + k] * log2(e), KP = 4 ceil(K/4), zero padded
     const float* c2;   // shared (KP): constants * log2(e), -inf for the padding
     int d, K;
@@ -219,9 +226,9 @@ struct VmfGc {
             c.A[4 * q + 3] = fmaf(m.w, xj, c.A[4 * q + 3]); c.B[4 * q + 3] = fmaf(m.w, uj, c.B[4 * q + 3]);
         }
     }
-    __device__ __forceinline__ void scale_u(Coef& c, float inp) const {
+    __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) c.B[k] *= inp;
+        for (int k = 0; k < GC_MAX_K; ++k) c.B[k] = inp * fmaf(-zx, c.A[k], c.B[k]);
     }
     __device__ __forceinline__ float lse2(const Coef& c, float cs, float sn) const {
         const int KP = (K + 3) & ~3;
@@ -256,13 +263,18 @@ struct SCol {
 };
 
 // ------------------------------------------------------------------ kernel
-template <class Policy, int KIND>
+// STORE: the d normals of the current transition are kept in shared memory next to x (needed for small d,
+// where |z - (z.x) x|^2 is formed from the stored vector, and for dense Bingham).  Otherwise only x is
+// resident -- half the shared memory, twice the resident warps -- the scores are accumulated against the
+// raw normals on the fly (u = inp (z - zx x) is linear in z) and the accepted move regenerates the normals
+// from the chain's Philox counter: x' = (c - s inp zx) x + (s inp) z.
+template <class Policy, int KIND, bool STORE>
 __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
     extern __shared__ __align__(16) float gc_smem[];
     const int d = P.d;
     SCol xs{gc_smem + threadIdx.x}, us{gc_smem + (size_t)d * GC_BLOCK + threadIdx.x};
     Policy pol;
-    pol.stage(P, gc_smem + 2 * (size_t)d * GC_BLOCK);
+    pol.stage(P, gc_smem + (STORE ? 2 : 1) * (size_t)d * GC_BLOCK);
     __syncthreads();
 
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
     constexpr float LN2 = 0.6931471805599453f;
 
     float* st = static_cast<float*>(a.state) + (live ? c : 0) * d;
-    for (int j = 0; j < d; ++j) { xs[j] = live ? st[j] : (j == 0 ? 1.f : 0.f); us[j] = 0.f; }
+    for (int j = 0; j < d; ++j) { xs[j] = live ? st[j] : (j == 0 ? 1.f : 0.f); if (STORE) us[j] = 0.f; }
 
     PhiloxDraws<float> dr;
     dr.init(a.seed, a.chain0 + (uint64_t)c, d);
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
     typename Policy::Coef co;
     pol.begin(co);
     float lo = 0.f, hi = 2.f, lnu = 0.f, dl_acc = 0.f, lp_x = 0.f;
-    float sn = 0.f, cs = 1.f, u_scale = 1.f;  // us[] holds the UNSCALED tangent p; u = u_scale * p
+    float sn = 0.f, cs = 1.f, u_scale = 1.f, zx_keep = 0.f;  // direction u = u_scale (z - zx_keep x), z = the transition's normals
     int t = live ? 0 : n_steps;
     int r = 0, batch = 0;
     bool inloop = false, pending = false, moved = false;
@@ -297,10 +309,25 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
     auto finish_transition = [&]() {
         // apply the accepted move, renormalise (|x| would otherwise drift in fp32), store
         float xx = 0.f;
-        for (int j = 0; j < d; ++j) {
-            const float v = moved ? fmaf(cs, xs[j], (sn * u_scale) * us[j]) : xs[j];
-            xs[j] = v;
-            xx = fmaf(v, v, xx);
+        if (moved) {
+            const float beta = sn * u_scale, alpha = fmaf(-beta, zx_keep, cs);  // x' = alpha x + beta z
+            if (STORE) {
+                for (int j = 0; j < d; ++j) { const float v = fmaf(alpha, xs[j], beta * us[j]); xs[j] = v; xx = fmaf(v, v, xx); }
+            } else {
+                for (int b = 0; b < nbn; ++b) {  // dr still holds the counters of the transition being finished
+                    const U4 w = dr.block(b);
+                    float n0, n1, n2, n3;
+                    box_muller_fast(w.x, w.y, n0, n1);
+                    box_muller_fast(w.z, w.w, n2, n3);
+                    const int j = 4 * b;
+                    float v = fmaf(alpha, xs[j], beta * n0); xs[j] = v; xx = fmaf(v, v, xx);
+                    if (j + 1 < d) { v = fmaf(alpha, xs[j + 1], beta * n1); xs[j + 1] = v; xx = fmaf(v, v, xx); }
+                    if (j + 2 < d) { v = fmaf(alpha, xs[j + 2], beta * n2); xs[j + 2] = v; xx = fmaf(v, v, xx); }
+                    if (j + 3 < d) { v = fmaf(alpha, xs[j + 3], beta * n3); xs[j + 3] = v; xx = fmaf(v, v, xx); }
+                }
+            }
+        } else {
+            for (int j = 0; j < d; ++j) xx = fmaf(xs[j], xs[j], xx);
         }
         const float inx = rsqrtf(xx);
         for (int j = 0; j < d; ++j) xs[j] *= inx;
@@ -344,29 +371,43 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
                 const uint64_t step = a.step0 + (uint64_t)t;
                 dr.s_lo = (uint32_t)step;
                 dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
-                // normals -> u, z.x
+                // one pass over the d normals: z.x, |z|^2 and the target's scores against z
                 uint32_t aux0 = 0, aux1 = 0;
-                float zx = 0.f;
+                float zx = 0.f, zz = 0.f;
+                pol.begin(co);
+                const bool on_the_fly = !pol.needs_vector();
+                auto take = [&](int j, float n) {
+                    const float xj = xs[j];
+                    if (STORE) us[j] = n;
+                    zx = fmaf(n, xj, zx);
+                    zz = fmaf(n, n, zz);
+                    if (on_the_fly) pol.accumulate(co, j, xj, n);
+                };
                 for (int b = 0; b < nbn; ++b) {
                     const U4 w = dr.block(b);
                     float n0, n1, n2, n3;
                     box_muller_fast(w.x, w.y, n0, n1);
                     box_muller_fast(w.z, w.w, n2, n3);
                     const int j = 4 * b;
-                    us[j] = n0; zx = fmaf(n0, xs[j], zx);
-                    if (j + 1 < d) { us[j + 1] = n1; zx = fmaf(n1, xs[j + 1], zx); }
-                    if (j + 2 < d) { us[j + 2] = n2; zx = fmaf(n2, xs[j + 2], zx); }
-                    if (j + 3 < d) { us[j + 3] = n3; zx = fmaf(n3, xs[j + 3], zx); }
+                    take(j, n0);
+                    if (j + 1 < d) take(j + 1, n1);
+                    if (j + 2 < d) take(j + 2, n2);
+                    if (j + 3 < d) take(j + 3, n3);
                     if (b == nbn - 1) { aux0 = w.z; aux1 = w.w; }
                 }
                 if (!aux_in_last) { const U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
-                float pp = 0.f;
-                for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); us[j] = p; pp = fmaf(p, p, pp); }
+                float pp;
+                if (STORE) {  // |z - zx x|^2 from the stored vector: no cancellation for small d
+                    pp = 0.f;
+                    for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); pp = fmaf(p, p, pp); }
+                    if (!on_the_fly) for (int j = 0; j < d; ++j) pol.accumulate(co, j, xs[j], us[j]);
+                } else {
+                    pp = fmaf(-zx, zx, zz);  // x is unit; used for d >= 64 only, where zx^2 << |z|^2
+                }
                 u_scale = rsqrtf(pp);
-                pol.begin(co);
-                for (int j = 0; j < d; ++j) pol.accumulate(co, j, xs[j], us[j]);
+                zx_keep = zx;
                 pol.finish(co, xs, us);
-                pol.scale_u(co, u_scale);
+                pol.fixup(co, zx, u_scale);
                 lp_x = pol.logp_x(co);
                 lnu = LN2 * fast_lg2(u01(aux0, 0.f));
                 if (KIND == SHRINK) { hi = 2.0f * u01(aux1, 0.f); lo = hi - 2.0f; }
