@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(CPD_WARPS * 32) k_sampler_cpd_fast(CpdP<float>
     }
 }
 
-__global__ void __launch_bounds__(CPD_WARPS * 32) k_logp_cpd_fast(CpdP<float> p, float max_logw, const float* __restrict__ q,
+static __global__ void __launch_bounds__(CPD_WARPS * 32) k_logp_cpd_fast(CpdP<float> p, float max_logw, const float* __restrict__ q,
                                                                   float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
