@@ -547,3 +547,42 @@ def test_edge_shapes_fast_path():
     smp = gs.RejectionSphericalSliceSampler(pdf, torch.as_tensor(gs.sample_sphere(4, 5, seed=3)).cuda(), 1)
     smp._run_device(0, None)
     assert smp.rng.steps_done == 0 and smp.n_reject == 0
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes: size-independent properties
+@pytest.mark.parametrize("cfg,N,steps", [("c2", 65536, 40), ("c3", 1 << 20, 3), ("c4", 1 << 20, 4), ("c5", 1 << 18, 2)])
+def test_full_size_configs_properties(golden, cfg, N, steps):
+    """At the chain counts BASELINE.json names: every retained state is finite and on the sphere, the
+    first 96 chains are bit-identical to a 96-chain run (chains depend on (seed, chain id, step) only),
+    logp_out equals log_prob of the retained state, rejection totals add up."""
+    if cfg == "c2":
+        pdf, d = mixture(100.0 * golden("traj_c2")["modes"]), 10
+    elif cfg == "c3":
+        pdf, d = gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(10, 100, 0.5, seed=4562)), 500.0), 100
+    elif cfg == "c4":
+        pdf, d = gs.random_bingham(50, 300, 0, True, 6982), 50
+    else:
+        g = golden("logprob_cpd")
+        n = len(g["c5_source"])
+        pdf, d = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n),
+                                       sigma=1.0, k=20, omega=0.4, dense=True), 4
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.nn.functional.normalize(torch.randn(N, d, device="cuda", generator=gen, dtype=torch.float64), dim=1)
+    smp = gs.ShrinkageSphericalSliceSampler(pdf, x0, 2024)
+    out = torch.empty((N, steps, d), dtype=torch.float32, device="cuda")
+    logp = torch.empty((N, steps), dtype=torch.float32, device="cuda")
+    nrej = torch.zeros((N, steps), dtype=torch.int32, device="cuda")
+    smp._run_device(steps, out, logp=logp, nrej=nrej, chain_major=True)
+    torch.cuda.synchronize()
+    assert smp.path == "fast"
+    assert bool(torch.isfinite(out).all())
+    assert float((out.norm(dim=-1) - 1).abs().max()) < 2e-4
+    assert int(nrej.sum()) == smp.n_reject and smp.n_reject > 0
+    small = gs.ShrinkageSphericalSliceSampler(pdf, x0[:96], 2024)
+    out_s = torch.empty((96, steps, d), dtype=torch.float32, device="cuda")
+    small._run_device(steps, out_s, chain_major=True)
+    assert torch.equal(out[:96], out_s)
+    idx = torch.arange(0, N, max(1, N // 512), device="cuda")
+    want = pdf.log_prob(out[idx, -1].double())
+    tol = 2e-3 if cfg == "c5" else 3e-4
+    assert float(((logp[idx, -1].double() - want).abs() / want.abs().clamp(min=1)).max()) <= tol
