@@ -15,6 +15,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_gc.cuh"
 #include "kernels_logp_fast.cuh"
+#include "kernels_tc.cuh"
 #include "kernels_literal.cuh"
 
 using namespace geosss;
@@ -414,6 +415,28 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
         case TGT_BINGHAM:
+            // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
+            if (!t->diag && t->d >= 8 && t->d <= TC_MAX_D && !std::getenv("GEOSSS_NO_TC")) {
+                if (!g_sm_count) {
+                    int dev = 0;
+                    CU(cudaGetDevice(&dev));
+                    CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+                }
+                const size_t smem = tc_smem_bytes(t->d);
+                CU(cudaFuncSetAttribute(k_logp_bingham_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(k_logp_bingham_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                // persistent blocks: as many as fit an SM's 228 KB of shared memory (1 KB reserved per block), at most 4
+                int per_sm = (int)((228 * 1024) / (smem + 1024 + 64));
+                if (per_sm < 1) per_sm = 1;
+                if (per_sm > 4) per_sm = 4;  // 64 TMEM columns per block
+                const int64_t n_tiles = (N + TC_ROWS - 1) / TC_ROWS;
+                int64_t grid = (int64_t)g_sm_count * per_sm;
+                if (grid > n_tiles) grid = n_tiles;
+                TcParams tp{t->A.f, t->has_b ? t->b.f : nullptr, t->d};
+                k_logp_bingham_tc<<<(unsigned)grid, TC_ROWS, smem, st>>>(tp, xi, o, N);
+                CU(cudaGetLastError());
+                return 0;
+            }
             p.diag = t->diag; p.a0 = t->diag ? t->Adiag.f : t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
             return launch_logp_tiled<BinghamLp>(p, xi, o, N, st);
         case TGT_CURVED_VMF:

@@ -147,6 +147,31 @@ def test_fast_logprob_tiles_ragged_unaligned_large(golden):
         assert rel_err(pdf2.log_prob(x.astype(F32)), pdf2.log_prob(x)) <= 2e-5
 
 
+def test_dense_bingham_logprob_on_tensor_cores():
+    """Dense Bingham(-Fisher) log_prob, 8 <= d <= 64: tcgen05 3xTF32 kernel vs the float64 literal kernel,
+    ragged tile counts, unaligned input, and the SIMT fallback (GEOSSS_NO_TC) as a second opinion."""
+    import os
+    gen = np.random.default_rng(0)
+    for d in (8, 17, 32, 50, 64):
+        pdf = gs.random_bingham(d, 300.0, 0.0, False, 6982)
+        for n in (1, 127, 128, 129, 128 * 37 + 5):
+            x = gs.radial_projection(gen.standard_normal((n + 1, d)))
+            want = pdf.log_prob(x)
+            xt = torch.as_tensor(x, dtype=torch.float32).cuda()
+            assert rel_err(pdf.log_prob(xt).cpu().numpy(), want) <= 2e-5
+            assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 2e-5  # 4d-byte offset: plain-load path when not 16-byte aligned
+    pf = gs.BinghamFisher(gs.random_bingham(20, 20.0, 0.0, False, 3).A, 4.0 * gs.sample_sphere(19, seed=4))
+    x = gs.radial_projection(gen.standard_normal((1000, 20)))
+    tc = pf.log_prob(x.astype(F32))
+    assert rel_err(tc, pf.log_prob(x)) <= 2e-5
+    os.environ["GEOSSS_NO_TC"] = "1"
+    try:
+        simt = pf.log_prob(x.astype(F32))
+    finally:
+        del os.environ["GEOSSS_NO_TC"]
+    assert rel_err(simt, pf.log_prob(x)) <= 2e-5 and not np.array_equal(simt, tc)
+
+
 # ------------------------------------------------------------------ trajectories under the reference's draws
 def tape_cases(golden):
     g = golden("traj_c1")
