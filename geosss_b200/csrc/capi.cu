@@ -433,7 +433,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
                 int64_t grid = (int64_t)g_sm_count * per_sm;
                 if (grid > n_tiles) grid = n_tiles;
                 TcParams tp{t->A.f, t->has_b ? t->b.f : nullptr, t->d};
-                k_logp_bingham_tc<<<(unsigned)grid, TC_ROWS, smem, st>>>(tp, xi, o, N);
+                k_logp_bingham_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(tp, xi, o, N);
                 CU(cudaGetLastError());
                 return 0;
             }

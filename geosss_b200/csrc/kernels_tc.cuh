@@ -28,7 +28,8 @@
 
 namespace geosss {
 
-constexpr int TC_ROWS = 128;  // UMMA M
+constexpr int TC_ROWS = 128;     // UMMA M
+constexpr int TC_THREADS = 256;  // two threads per row: each splits half of the K steps and reduces half of the columns
 constexpr int TC_N = 64;      // UMMA N: d padded to 64 columns of A
 constexpr int TC_MAX_D = 64;
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ float to_tf32(float v) {
 // element (r, k) lives at  (k / 4) * lbo + (r / 8) * 128 + (r % 8) * 16 + (k % 4) * 4  bytes, lbo = rows * 16.
 __device__ __forceinline__ size_t umma_kstep_floats(int rows) { return (size_t)rows * 8; }
 
-static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams P, const float* __restrict__ x, float* __restrict__ out, int64_t N) {
+static __global__ void __launch_bounds__(TC_THREADS, 2) k_logp_bingham_tc(TcParams P, const float* __restrict__ x, float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(128) unsigned char tc_smem_raw[];
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ __align__(8) uint64_t full;
@@ -66,6 +67,8 @@ static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams 
     const int d = P.d;
     const int ksteps = (d + 7) >> 3;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row_t = tid & (TC_ROWS - 1), half = tid >> 7;  // this thread's row of the tile, and which half of the work it takes
+    __shared__ float q_part[TC_THREADS];
 
     const size_t raw_floats = ((size_t)TC_ROWS * d + 31) & ~(size_t)31;
     float* raw = reinterpret_cast<float*>(tc_smem_raw);                  // (128, d) landing buffer of the bulk copy
@@ -85,7 +88,7 @@ static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams 
         mbar_init(&full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < ksteps * TC_N * 8; i += TC_ROWS) {  // (kk, chunk, n / 8, n % 8, k % 4) <- A[n][8 kk + 4 chunk + k % 4]
+    for (int i = tid; i < ksteps * TC_N * 8; i += TC_THREADS) {  // (kk, chunk, n / 8, n % 8, k % 4) <- A[n][8 kk + 4 chunk + k % 4]
         const int kq = i & 3, r8 = (i >> 2) & 7, g = (i >> 5) % (TC_N / 8), chunk = (i / (32 * (TC_N / 8))) & 1, kk = i / (32 * (TC_N / 8) * 2);
         const int n = g * 8 + r8, k = kk * 8 + chunk * 4 + kq;
         const float v = (n < d && k < d) ? P.A[(size_t)n * d + k] : 0.f;
@@ -122,14 +125,15 @@ static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams 
             full_phase ^= 1;
         } else {  // ragged last tile / unaligned input
             const int64_t n_here = (N - row0 < TC_ROWS ? N - row0 : TC_ROWS) * d;
-            for (int64_t i = tid; i < (int64_t)tile_floats; i += TC_ROWS) raw[i] = i < n_here ? x[row0 * d + i] : 0.f;
+            for (int64_t i = tid; i < (int64_t)tile_floats; i += TC_THREADS) raw[i] = i < n_here ? x[row0 * d + i] : 0.f;
             __syncthreads();
         }
         // split this thread's row into the operand layout: one 16-byte store per (k step, half)
         {
-            const float* row = raw + (size_t)tid * d;
-            const size_t rbase = (size_t)(tid >> 3) * 32 + (size_t)(tid & 7) * 4;  // floats
-            for (int kk = 0; kk < ksteps; ++kk) {
+            const float* row = raw + (size_t)row_t * d;
+            const size_t rbase = (size_t)(row_t >> 3) * 32 + (size_t)(row_t & 7) * 4;  // floats
+            const int k_mid = (ksteps + 1) >> 1;
+            for (int kk = half ? k_mid : 0; kk < (half ? ksteps : k_mid); ++kk) {
 #pragma unroll
                 for (int chunk = 0; chunk < 2; ++chunk) {
                     float v[4], h[4], l[4];
@@ -177,13 +181,14 @@ static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams 
 
         // epilogue: thread <-> row <-> TMEM lane; 64 accumulator columns in four 16-column loads; the row itself
         // is read back as hi + lo from the operand buffers (16-byte loads), `raw` already belongs to the next tile
-        const size_t rbase = (size_t)(tid >> 3) * 32 + (size_t)(tid & 7) * 4;
+        const size_t rbase = (size_t)(row_t >> 3) * 32 + (size_t)(row_t & 7) * 4;
         float q = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < TC_N; c0 += 16) {
+        for (int cc = 0; cc < TC_N / 2; cc += 16) {
+            const int c0 = half * (TC_N / 2) + cc;  // warps 0-3 reduce columns 0..31, warps 4-7 columns 32..63
             if (c0 < 8 * ksteps) {
                 uint32_t r[16];
-                const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                const uint32_t taddr = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -206,9 +211,10 @@ static __global__ void __launch_bounds__(TC_ROWS, 2) k_logp_bingham_tc(TcParams 
                 }
             }
         }
-        if (row0 + tid < N) out[row0 + tid] = q;
+        q_part[tid] = q;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // TMEM accumulator and the tile buffers are free for the next tile
+        __syncthreads();  // TMEM accumulator and the operand buffers are free for the next tile
+        if (half == 0 && row0 + row_t < N) out[row0 + row_t] = q_part[tid] + q_part[tid + TC_ROWS];
     }
 
     if (warp == 0) {
