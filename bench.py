@@ -169,6 +169,8 @@ def main_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from geosss_b200 import distributed as gdist
+    numa_cpus = gdist.bind_host_to_gpu(local)  # pinned host buffers next to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -327,7 +329,8 @@ def main_ours(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs, "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
+                        "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs,
+                        "host_cpus_bound_to_gpu_numa": None if numa_cpus is None else len(numa_cpus), "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
                 "gpu_launches": a.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),

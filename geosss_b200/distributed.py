@@ -69,3 +69,29 @@ def reduce_sum(values, group=None):
     if dist.is_initialized():
         dist.all_reduce(t, group=group)
     return t
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPU cores NVML reports as local to the GPU (same NUMA node), so that the
+    pinned buffers of the host-streaming path are allocated next to the GPU's PCIe root and device->host
+    copies of different ranks do not cross the socket interconnect.  Returns the CPU list, or None when
+    NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = device_index
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[device_index])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
