@@ -656,7 +656,7 @@ struct HostPipe {
 };
 constexpr int MAX_DEVICES = 64;
 HostPipe g_pipes[MAX_DEVICES];
-std::mutex g_pipe_mutex;
+std::mutex g_pipe_mutex[MAX_DEVICES];  // one pipeline per device; calls on different devices do not serialise
 }  // namespace
 
 // n_skip transitions without output, then n_keep transitions whose states stream to the host:
@@ -666,7 +666,7 @@ extern "C" int geosss_sampler_run_host(geosss_sampler_t s, int64_t n_skip, int64
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 0 || dev >= MAX_DEVICES) return fail(GEOSSS_E_UNSUPPORTED, "run_host: device index out of range");
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    std::lock_guard<std::mutex> lock(g_pipe_mutex[dev]);
     HostPipe& h = g_pipes[dev];
     CU(cudaDeviceSynchronize());  // earlier work on other streams (set_state, run) must have landed
     const size_t row = (size_t)s->N * s->t->d * s->esize();  // one retained state of every chain

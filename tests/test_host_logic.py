@@ -141,3 +141,12 @@ def test_public_surface_is_a_superset_of_the_reference(golden):
     assert all(hasattr(mix.pdfs[0], a) for a in ref["attributes"]["VonMisesFisher"])
     smp = gs.ShrinkageSphericalSliceSampler(mix, np.array([1.0, 0, 0]), 1)
     assert all(hasattr(smp, a) for a in ref["attributes"]["sampler"])
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    from geosss_b200 import distributed
+    before = os.sched_getaffinity(0)
+    got = distributed.bind_host_to_gpu(0)
+    assert got is None or set(got) <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
