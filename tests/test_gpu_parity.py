@@ -611,3 +611,21 @@ def test_full_size_configs_properties(golden, cfg, N, steps):
     want = pdf.log_prob(out[idx, -1].double())
     tol = 2e-3 if cfg == "c5" else 3e-4
     assert float(((logp[idx, -1].double() - want).abs() / want.abs().clamp(min=1)).max()) <= tol
+
+
+def test_long_run_stays_on_the_sphere_and_stationary():
+    """2 * 10^5 transitions per chain in fp32: states stay unit and finite, the rejection rate of the second
+    half equals that of the first half (no drift), every chain sits at a mode-like density."""
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    pdf = mixture(100.0 * modes)
+    x0 = torch.as_tensor(gs.sample_sphere(9, 2048, seed=2)).cuda()
+    smp = gs.ShrinkageSphericalSliceSampler(pdf, x0, 99)
+    smp._run_device(100_000, None)
+    r1 = smp.n_reject
+    smp._run_device(100_000, None)
+    r2 = smp.n_reject - r1
+    x = smp.state
+    assert np.all(np.isfinite(x)) and np.max(np.abs(np.linalg.norm(x, axis=1) - 1)) < 1e-5
+    assert abs(r2 / r1 - 1) < 0.01
+    assert np.mean(np.max(x @ modes.T, axis=1)) > 0.95
+    assert smp.rng.steps_done == 200_000

@@ -147,3 +147,16 @@ def test_philox_free_running_matches_oracle_fed_same_draws(lib, golden, kind):
         assert rc == 0
         assert np.array_equal(nrej, want.rejects_per_step)
         assert np.max(np.abs(got - traj[1:])) <= 1e-11
+
+
+def test_philox_step_counter_crosses_32_bits(lib, golden):
+    """The transition index is 48 bits wide in the counter: a chain that has already done 2^32 - 3 transitions
+    keeps following the oracle across the 32-bit boundary (checkpoint / resume of very long runs)."""
+    g = golden("traj_c1")
+    pdf = targets.VMFMixture(g["mus"])
+    x0 = np.array([0.6, -0.64, 0.48])
+    first = 2**32 - 3
+    rng = philox.PhiloxChainRNG(seed=7, chain=11, kind=samplers.SHRINK, d=3, dtype=F64, first_step=first)
+    want = samplers.SliceSampler(samplers.SHRINK, pdf.log_prob, x0.copy(), rng).sample(9)
+    rc, got, _ = hs.run(lib, hs.vmf_mixture(g["mus"]), samplers.SHRINK, x0, 8, F64, seed=7, chain=11, step0=first)
+    assert rc == 0 and np.max(np.abs(got - want[1:])) <= 1e-11
