@@ -34,6 +34,7 @@ from .sphere import (  # noqa: F401
     sample_subsphere,
     spherical_projection,
 )
+from .sphere_tesselation import systematic_search, tessellate_rotations  # noqa: F401
 from .spherical_curve import SlerpCurve, SphericalCurve, brownian_curve  # noqa: F401
 from .utils import SamplerLauncher  # noqa: F401
 

@@ -226,6 +226,18 @@ def golden_misc():
 
 
 
+def golden_tessellation(tgt, src):
+    """600-cell rotation grid (one subdivision) and the reference CPD log-probabilities on it: the
+    'systematic search' of scripts/protein_reg3d3d.py:629-648 at a size that runs in seconds."""
+    from geosss.sphere_tesselation import tessellate_rotations
+    quats = tessellate_rotations(1)
+    cpd = CoherentPointDrift(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(len(src)) / len(src)),
+                             sigma=1.0, k=20, omega=0.4)
+    logp = np.array([cpd.log_prob(q) for q in quats])
+    save("tessellation", quats_n1=quats, logp_n1=logp, n0_count=len(tessellate_rotations(0)),
+         n2_count=len(tessellate_rotations(2)))
+
+
 def golden_api_surface():
     """Names and call signatures of the reference's public interface for the path (drop-in check)."""
     import inspect
@@ -269,9 +281,13 @@ def golden_api_surface():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         golden_api_surface()
+    elif len(sys.argv) > 1 and sys.argv[1] == "tessellation":
+        d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
+        golden_tessellation(d["target"], d["source"])
     else:
         with np.errstate(over="ignore", divide="ignore"):
             t, s = golden_logprob()
             golden_trajectories(t, s)
             golden_misc()
+            golden_tessellation(t, s)
         golden_api_surface()

@@ -629,3 +629,20 @@ def test_long_run_stays_on_the_sphere_and_stationary():
     assert abs(r2 / r1 - 1) < 0.01
     assert np.mean(np.max(x @ modes.T, axis=1)) > 0.95
     assert smp.rng.steps_done == 200_000
+
+
+def test_systematic_rotation_search(golden):
+    """scripts/protein_reg3d3d.py:629-648: log_prob over the 600-cell grid in one batched call; same values
+    and the same best rotation as the reference's Python loop."""
+    g = golden("tessellation")
+    pdf64 = c5_target(golden)  # k = 20, exact truncation
+    q_best, lp_best, quats, logp = gs.systematic_search(pdf64, 1)
+    assert np.max(np.abs(logp - g["logp_n1"])) <= 5e-12
+    best_ref = int(np.argmax(g["logp_n1"]))
+    assert abs(abs(q_best @ g["quats_n1"][best_ref]) - 1) < 1e-12 and abs(lp_best - g["logp_n1"][best_ref]) <= 5e-12
+    c = golden("logprob_cpd")
+    n = len(c["c5_source"])
+    fast = gs.CoherentPointDrift(gs.PointCloud(c["c5_target"]), gs.PointCloud(c["c5_source"], np.ones(n) / n),
+                                 sigma=1.0, k=20, omega=0.4, dense=True)
+    _, _, _, logp32 = gs.systematic_search(fast, quaternions=quats.astype(F32))
+    assert np.max(np.abs(logp32 - g["logp_n1"])) <= 1e-3 and int(np.argmax(logp32)) == best_ref

@@ -150,3 +150,14 @@ def test_numa_binding_helper_is_harmless_without_a_gpu():
     assert got is None or set(got) <= before
     if got is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_rotation_tessellation_matches_reference_grid(golden):
+    """600-cell grid (geosss/sphere_tesselation.py:174-201): same rotations as the reference, in the same order."""
+    g = golden("tessellation")
+    assert len(gs.tessellate_rotations(0)) == int(g["n0_count"])
+    q = gs.tessellate_rotations(1)
+    assert q.shape == g["quats_n1"].shape
+    assert np.max(np.abs(np.abs(np.sum(q * g["quats_n1"], axis=1)) - 1)) < 1e-12  # equal up to the sign of q
+    assert np.allclose(np.linalg.norm(q, axis=1), 1, atol=1e-14)
+    assert len(gs.tessellate_rotations(2)) == int(g["n2_count"])
