@@ -43,6 +43,7 @@ SIGNATURES = {
     "geosss_sampler_get_state_host": (_i, [_p, _pd, _p]),
     "geosss_sampler_run_host": (_i, [_p, _i64, _i64, _p]),
     "geosss_diag_ess_partials": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _p, _p]),
+    "geosss_diag_path_stats": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p]),
     "geosss_sample_host": (_i, [_p, _i, _i, _i, _i64, _pd, _u64, _u64, _i64, _i64, _p, _p]),
 }
 

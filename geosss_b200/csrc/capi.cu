@@ -751,3 +751,30 @@ extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int layo
     CU(cudaGetLastError());
     return 0;
 }
+
+extern "C" int geosss_diag_path_stats(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
+                                      const double* modes, int n_modes, int sign_labels, double* out, void* stream) {
+    if (layout != GEOSSS_STEP_MAJOR && layout != GEOSSS_CHAIN_MAJOR) return fail(GEOSSS_E_INVALID, "diag_path_stats: unknown layout");
+    if (!samples || !out || n_draws < 1 || n_chains < 1 || d < 1 || n_modes < 0 || (n_modes > 0 && !modes))
+        return fail(GEOSSS_E_INVALID, "diag_path_stats: bad arguments");
+    if (n_modes > DIAG_MAX_MODES || (sign_labels && n_modes != 1))
+        return fail(GEOSSS_E_UNSUPPORTED, "diag_path_stats: at most 64 modes; sign labels take exactly one direction");
+    const int64_t step_stride = layout == GEOSSS_STEP_MAJOR ? n_chains * (int64_t)d : d;
+    const int64_t chain_stride = layout == GEOSSS_STEP_MAJOR ? d : n_draws * (int64_t)d;
+    const int n_labels = sign_labels ? 3 : n_modes;
+    const size_t smem = (size_t)n_modes * d * sizeof(double);
+    if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "diag_path_stats: modes do not fit in shared memory");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemsetAsync(out, 0, (size_t)(n_labels + 2) * sizeof(double), st));
+    if (dtype == GEOSSS_F64) {
+        CU(cudaFuncSetAttribute(k_path_stats<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_path_stats<double><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const double*>(samples), n_draws, step_stride, chain_stride,
+                                                                           d, modes, n_modes, sign_labels, out);
+    } else {
+        CU(cudaFuncSetAttribute(k_path_stats<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_path_stats<float><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const float*>(samples), n_draws, step_stride, chain_stride,
+                                                                          d, modes, n_modes, sign_labels, out);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}

@@ -57,4 +57,71 @@ __global__ void __launch_bounds__(DIAG_BLOCK) k_ess_partials(const T* __restrict
     }
 }
 
+// Path statistics of the retained draws: mode populations (argmax_k x . mode_k,
+// scripts/vMF_diagnostics.py:333-342), hops between labels of successive draws of a chain
+// (np.diff(np.sign(x . mode)) != 0, scripts/bingham.py:23-25, when sign_labels; label changes otherwise)
+// and the summed geodesic step arccos(clip(x_t . x_{t+1}, -1, 1)) (geosss/sphere.py:64-68 as used in
+// scripts/curve_vMF.py:379).  One block per chain; out (zeroed by the caller) holds n_labels counts
+// (K, or 3 = {-, 0, +} for sign_labels), then the hop count, then the distance sum.
+constexpr int DIAG_MAX_MODES = 64;
+
+template <typename T>
+__device__ __forceinline__ int path_label(const T* __restrict__ row, const double* __restrict__ modes, int K, int d, bool sign_labels) {
+    if (sign_labels) {
+        double s = 0.0;
+        for (int j = 0; j < d; ++j) s += (double)row[j] * modes[j];
+        return s > 0.0 ? 2 : (s < 0.0 ? 0 : 1);
+    }
+    int best = 0;
+    double bv = 0.0;
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int j = 0; j < d; ++j) s += (double)row[j] * modes[k * d + j];
+        if (k == 0 || s > bv) { bv = s; best = k; }
+    }
+    return best;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DIAG_BLOCK) k_path_stats(const T* __restrict__ samples, int64_t n, int64_t step_stride,
+                                                           int64_t chain_stride, int d, const double* __restrict__ modes, int K,
+                                                           int sign_labels, double* __restrict__ out) {
+    extern __shared__ double modes_s[];  // K * d
+    __shared__ unsigned long long counts[DIAG_MAX_MODES];
+    __shared__ unsigned long long hops_s;
+    __shared__ double red[DIAG_BLOCK / 32];
+    const int n_labels = sign_labels ? 3 : K;
+    for (int i = threadIdx.x; i < K * d; i += blockDim.x) modes_s[i] = modes[i];
+    if (threadIdx.x < DIAG_MAX_MODES) counts[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) hops_s = 0ull;
+    __syncthreads();
+    const T* chain = samples + (int64_t)blockIdx.x * chain_stride;
+    double dist = 0.0;
+    unsigned long long hops = 0ull;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const T* row = chain + t * step_stride;
+        const int lab = K > 0 ? path_label(row, modes_s, K, d, sign_labels != 0) : 0;
+        if (K > 0) atomicAdd(&counts[lab], 1ull);
+        if (t + 1 < n) {
+            const T* nxt = row + step_stride;
+            if (K > 0 && path_label(nxt, modes_s, K, d, sign_labels != 0) != lab) ++hops;
+            double c = 0.0;
+            for (int j = 0; j < d; ++j) c += (double)row[j] * (double)nxt[j];
+            dist += acos(fmin(1.0, fmax(-1.0, c)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dist;
+    if (hops) atomicAdd(&hops_s, hops);
+    __syncthreads();
+    if (threadIdx.x < n_labels && counts[threadIdx.x]) atomicAdd(out + threadIdx.x, (double)counts[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < DIAG_BLOCK / 32; ++w) s += red[w];
+        if (hops_s) atomicAdd(out + n_labels, (double)hops_s);
+        atomicAdd(out + n_labels + 1, s);
+    }
+}
+
 }  // namespace geosss

@@ -84,3 +84,67 @@ def ess(samples, direction=None, max_lag=None, group=None, chain_major=True):
         dist.all_reduce(part, group=group)
         dist.all_reduce(total, group=group)
     return ess_from_partials(part.cpu().numpy(), n, int(total.item()))
+
+
+def path_stats(samples, modes=None, sign_labels=False, group=None, chain_major=True):
+    """One pass over retained draws on the GPU: label populations, hops and geodesic steps.
+
+    ``samples``: CUDA tensor ``(n_chains, n_draws, d)`` (or step-major with ``chain_major=False``).
+    ``modes``: ``(K, d)`` directions; a draw's label is ``argmax_k x . mode_k``
+    (scripts/vMF_diagnostics.py:333-336) or, with ``sign_labels`` and one direction, the sign of
+    ``x . mode`` (scripts/bingham.py:23-25).  Returns a dict with ``counts`` (per label; sign labels
+    are ordered -, 0, +), ``hops``, ``pairs`` (successive draws compared), ``distance_sum``; the sums
+    are all-reduced over ``group`` when torch.distributed is initialised."""
+    import torch.distributed as dist
+    if not (isinstance(samples, torch.Tensor) and samples.is_cuda):
+        raise ValueError("path_stats needs a CUDA tensor; there is no CPU fallback")
+    samples = samples.contiguous()
+    if chain_major:
+        N, n, d = samples.shape
+    else:
+        n, N, d = samples.shape
+    code, _, _ = _device.dtype_code(samples.dtype)
+    K = 0
+    m = None
+    if modes is not None:
+        m = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(np.asarray(modes, dtype=float)))).to(samples.device)
+        K = m.shape[0]
+        if m.shape[1] != d:
+            raise ValueError("modes must have shape (K, d)")
+    if sign_labels and K != 1:
+        raise ValueError("sign labels need exactly one direction")
+    L = 3 if sign_labels else K
+    out = torch.empty(L + 3, dtype=torch.float64, device=samples.device)
+    with torch.cuda.device(samples.device):
+        _lib.check(_lib.lib().geosss_diag_path_stats(samples.data_ptr(), code, _lib.CHAIN_MAJOR if chain_major else _lib.STEP_MAJOR,
+                                                     n, N, d, m.data_ptr() if K else None, K, int(bool(sign_labels)),
+                                                     out.data_ptr(), _device.stream_ptr(samples.device)))
+    out[L + 2] = float(N) * (n - 1)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(out, group=group)
+    o = out.cpu().numpy()
+    return {"counts": o[:L].copy(), "hops": o[L], "pairs": o[L + 2], "distance_sum": o[L + 1]}
+
+
+def mode_kl(samples, pdf, **kwargs):
+    """KL divergence between the sampled mode populations and the mixture weights
+    (scripts/vMF_diagnostics.py:331-342): populations from ``argmax_k x . mu_k``, empty modes at 1e-100."""
+    modes = np.array([p.mu for p in pdf.pdfs])
+    c = path_stats(samples, modes, **kwargs)["counts"]
+    p = np.full(len(modes), 1e-100)
+    p[c > 0] = c[c > 0]
+    p[c > 0] /= p.sum()
+    return float(p @ np.log(p / np.asarray(pdf.weights)))
+
+
+def hopping_frequency(samples, pdf, **kwargs):
+    """Fraction of successive draws on different sides of the Bingham mode
+    (scripts/bingham.py:23-25: ``mean(diff(sign(x . mode)) != 0)``), over all chains."""
+    s = path_stats(samples, np.asarray(pdf.mode, dtype=float)[None], sign_labels=True, **kwargs)
+    return float(s["hops"] / s["pairs"])
+
+
+def mean_geodesic_step(samples, **kwargs):
+    """Average great-circle distance of successive draws (scripts/curve_vMF.py:379-389)."""
+    s = path_stats(samples, **kwargs)
+    return float(s["distance_sum"] / s["pairs"])

@@ -154,6 +154,17 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
 int geosss_diag_ess_partials(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
                              const void* direction, int max_lag, double* out, void* stream);
 
+/* Path statistics of retained draws, same layouts as above.  modes: (n_modes, d) device doubles (NULL
+ * when n_modes = 0).  out (device doubles, additive over chain shards):
+ *   out[0 .. L-1]  draws per label; label = argmax_k x . mode_k, L = n_modes (mode populations of
+ *                  scripts/vMF_diagnostics.py:333-342), or with sign_labels (n_modes = 1) the sign of
+ *                  x . mode as {-, 0, +}, L = 3 (scripts/bingham.py:23-25);
+ *   out[L]         successive draws of one chain whose labels differ ("hops", bingham.py:25);
+ *   out[L + 1]     sum over successive draws of arccos(clip(x_t . x_{t+1}, -1, 1)), the geodesic
+ *                  step of geosss/sphere.py:64-68 (scripts/curve_vMF.py:379). */
+int geosss_diag_path_stats(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
+                           const double* modes, int n_modes, int sign_labels, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,6 +226,35 @@ def golden_misc():
 
 
 
+def golden_pathstats():
+    """Reference runs + the scripts' diagnostic one-liners applied to them: mode populations / KL
+    (scripts/vMF_diagnostics.py:331-342), hopping frequency (scripts/bingham.py:23-25), geodesic steps
+    (scripts/curve_vMF.py:379)."""
+    shrink = gs.ShrinkageSphericalSliceSampler
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    pdf = vmf_mixture(100.0 * modes)
+    xs = np.array([shrink(pdf, gs.sample_sphere(9, seed=50 + c), 60 + c).sample(1000) for c in range(3)])
+    counts, kls, dist = np.zeros(5), [], []
+    for x in xs:
+        m = np.argmax(x @ modes.T, axis=1)
+        i, c = np.unique(m, return_counts=True)
+        counts[i] += c
+        dist.append(gs.distance(x[:-1], x[1:]))
+    x = xs.reshape(-1, 10)  # pooled draws, as the scripts pool their runs
+    m = np.argmax(x @ modes.T, axis=1)
+    i, c = np.unique(m, return_counts=True)
+    p = np.full(len(modes), 1e-100)
+    p[i] = c
+    p[i] /= p.sum()
+    kl = p @ np.log(p / pdf.weights)
+    bing = gs.random_bingham(10, 30, 0, True, 6982)
+    bx = np.array([shrink(bing, bing.mode.copy(), 70 + c).sample(1000) for c in range(3)])
+    hop = np.array([np.mean(np.diff(np.sign(b @ bing.mode)) != 0.0) for b in bx])
+    save("pathstats", vmf_modes=modes, vmf_weights=pdf.weights, vmf_samples=xs, vmf_counts=counts, vmf_kl=kl,
+         vmf_dist=np.array(dist), bingham_A=bing.A, bingham_mode=bing.mode, bingham_samples=bx, bingham_hop=hop,
+         bingham_dist=np.array([gs.distance(b[:-1], b[1:]) for b in bx]))
+
+
 def golden_tessellation(tgt, src):
     """600-cell rotation grid (one subdivision) and the reference CPD log-probabilities on it: the
     'systematic search' of scripts/protein_reg3d3d.py:629-648 at a size that runs in seconds."""
@@ -281,6 +310,8 @@ def golden_api_surface():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         golden_api_surface()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pathstats":
+        golden_pathstats()
     elif len(sys.argv) > 1 and sys.argv[1] == "tessellation":
         d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
         golden_tessellation(d["target"], d["source"])
@@ -289,5 +320,6 @@ if __name__ == "__main__":
             t, s = golden_logprob()
             golden_trajectories(t, s)
             golden_misc()
+            golden_pathstats()
             golden_tessellation(t, s)
         golden_api_surface()

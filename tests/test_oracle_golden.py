@@ -213,3 +213,15 @@ def test_philox_chain_rng_layout():
     aux = philox.philox4x32_10((0, 0, 1, 1), (1, 0))
     assert r4.random() == philox.u01(aux[0], np.float64) and r4.uniform(0, 1) == philox.u01(aux[1], np.float64)
     assert r4.uniform(0, 1) == philox.u01(philox.philox4x32_10((0, 0, 1, 2), (1, 0))[0], np.float64)
+
+
+def test_pathstats_oracle_matches_reference_expressions(golden):
+    from oracle import pathstats
+    g = golden("pathstats")
+    xs = g["vmf_samples"]
+    assert np.array_equal(sum(pathstats.mode_populations(x, g["vmf_modes"]) for x in xs), g["vmf_counts"])
+    assert abs(pathstats.mode_kl(xs.reshape(-1, xs.shape[-1]), g["vmf_modes"], g["vmf_weights"]) - g["vmf_kl"]) < 1e-14
+    for x, want in zip(xs, g["vmf_dist"]):
+        assert np.array_equal(pathstats.geodesic_steps(x), want)
+    for b, hop in zip(g["bingham_samples"], g["bingham_hop"]):
+        assert pathstats.hops(b, g["bingham_mode"]) / (len(b) - 1) == hop
