@@ -255,6 +255,89 @@ def golden_pathstats():
          bingham_dist=np.array([gs.distance(b[:-1], b[1:]) for b in bx]))
 
 
+def record_baseline(make, n_states, adapt):
+    """Run an upstream baseline sampler (mcmc.py:115-332) with the recording shim.  ``adapt`` is the
+    burn-in length handed to ``reset`` (what ``sample(n, burnin)`` does, mcmc.py:171)."""
+    smp = make()
+    rec = TapeRNG(source=smp.rng)
+    smp.rng = rec
+    smp.reset(adapt)
+    traj, steps, acc = [np.array(smp.state)], [smp.stepsize], [0]
+    while len(traj) < n_states:
+        traj.append(np.copy(next(smp)))
+        steps.append(smp.stepsize)
+        acc.append(smp.n_accept)
+    return {"tape": rec.recorded(), "traj": np.array(traj), "stepsize": np.array(steps),
+            "cumacc": np.array(acc, dtype=np.int64), "adapt": adapt}
+
+
+def golden_baselines(tgt, src):
+    """Gradients of every target and draw-taped trajectories of RWMH / independence / mixture / HMC."""
+    from geosss.mcmc import IndependenceSampler, MetropolisHastings, MixtureRWMHIndependenceSampler, SphericalHMC
+    out = {}
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    c1 = vmf_mixture(80.0 * README_MUS)
+    c2 = vmf_mixture(100.0 * modes, np.array([1.0, 2.0, 3.0, 4.0, 5.0]))
+    single = gs.VonMisesFisher(40.0 * modes[0])
+    dense = gs.random_bingham(10, 30, 0, False, 6982)
+    fisher = gs.BinghamFisher(dense.A, 3.0 * modes[1])
+    knots = brownian_curve(10, 100, 0.5, seed=4562)
+    curved = CurvedVonMisesFisher(SlerpCurve(knots), 500.0)
+    n = len(src)
+    cpd = CoherentPointDrift(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(n) / n), sigma=1.0, k=20, omega=0.4)
+    gmm = GaussianMixtureModel(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(n) / n), sigma=1.0, k=20)
+    full = CoherentPointDrift(PointCloud(tgt, np.ones(len(tgt))), PointCloud(src, np.ones(n) / n), sigma=2.0, k=n, omega=0.1, beta=0.5)
+    out.update(c1_mus=80.0 * README_MUS, c2_mus=100.0 * modes, c2_weights=c2.weights, single_mu=single.mu, dense_A=dense.A,
+               fisher_b=fisher.b, knots=knots, kappa=500.0)
+
+    # gradients (distributions.py:88-89,159-160,223-227,277-278; registration.py:55-59)
+    x3, x10, x100 = points(3, 24, 31), points(10, 24, 32), points(100, 12, 33)
+    q = np.vstack([points(4, 10, 34), matrix2quat_ref(tgt, src)])
+    out.update(x3=x3, x10=x10, x100=x100, q=q)
+    out["grad_c1"] = np.array([c1.gradient(x) for x in x3])
+    out["grad_c2"] = np.array([c2.gradient(x) for x in x10])
+    out["grad_single"] = np.array([single.gradient(x) for x in x10])
+    out["grad_dense"] = np.array([dense.gradient(x) for x in x10])
+    out["grad_fisher"] = np.array([fisher.gradient(x) for x in x10])
+    out["grad_curved"] = np.array([curved.gradient(x) for x in x100])
+    out["grad_cpd"] = np.array([cpd.gradient(row) for row in q])
+    out["grad_gmm"] = np.array([gmm.gradient(row) for row in q])
+    out["grad_full"] = np.array([full.gradient(row) for row in q])
+
+    def pack(tag, rec):
+        for k, v in rec.items():
+            out[f"{tag}_{k}"] = v
+
+    x0_3, x0_10 = README_X0, gs.sample_sphere(9, seed=1000)
+    pack("rwmh_c1", record_baseline(lambda: MetropolisHastings(c1, x0_3.copy(), 11, stepsize=1e-1), 401, 100))
+    pack("rwmh_c2", record_baseline(lambda: MetropolisHastings(c2, x0_10.copy(), 12, stepsize=1e-1), 401, 150))
+    pack("rwmh_dense", record_baseline(lambda: MetropolisHastings(dense, dense.mode.copy(), 13, stepsize=0.3), 301, 0))
+    pack("rwmh_curved", record_baseline(lambda: MetropolisHastings(curved, gs.sample_sphere(99, seed=1002), 14), 201, 80))
+    pack("rwmh_cpd", record_baseline(lambda: MetropolisHastings(cpd, gs.sample_sphere(3, seed=1006), 15), 81, 30))
+    pack("indep_c1", record_baseline(lambda: IndependenceSampler(c1, x0_3.copy(), 16), 301, 50))
+    pack("mix_c2", record_baseline(lambda: MixtureRWMHIndependenceSampler(c2, x0_10.copy(), 17, stepsize=1e-1,
+                                                                          mixing_probability=0.5), 401, 150))
+    pack("mix_c1", record_baseline(lambda: MixtureRWMHIndependenceSampler(c1, x0_3.copy(), 18, stepsize=0.2,
+                                                                          mixing_probability=0.8), 301, 100))
+    pack("hmc_c1", record_baseline(lambda: SphericalHMC(c1, x0_3.copy(), 19, stepsize=1e-1), 201, 80))
+    pack("hmc_c2", record_baseline(lambda: SphericalHMC(c2, x0_10.copy(), 20, stepsize=1e-2, n_steps=7), 201, 80))
+    pack("hmc_dense", record_baseline(lambda: SphericalHMC(dense, dense.mode.copy(), 21, stepsize=5e-2), 151, 50))
+    pack("hmc_fisher", record_baseline(lambda: SphericalHMC(fisher, dense.mode.copy(), 22, stepsize=5e-2), 101, 0))
+    pack("hmc_curved", record_baseline(lambda: SphericalHMC(curved, gs.sample_sphere(99, seed=1002), 23, stepsize=1e-3), 61, 20))
+    pack("hmc_cpd", record_baseline(lambda: SphericalHMC(cpd, gs.sample_sphere(3, seed=1006), 24, stepsize=1e-3), 41, 15))
+    # what the documented calls return
+    out["rwmh_c1_sample"] = MetropolisHastings(c1, x0_3.copy(), 25).sample(200, 0.2)
+    pos, mom = SphericalHMC(c1, x0_3.copy(), 26, stepsize=1e-1).sample(100, 20, return_momenta=True)
+    out["hmc_c1_positions"], out["hmc_c1_momenta"] = pos, mom
+    save("baselines", **out)
+
+
+def matrix2quat_ref(tgt, src):
+    """Quaternion of the true rotation of the registration data set (data file, 'rotation')."""
+    from geosss.pointcloud import matrix2quat
+    return matrix2quat(np.load(os.path.join(REF, "data", "protein_registration.npz"))["rotation"])
+
+
 def golden_tessellation(tgt, src):
     """600-cell rotation grid (one subdivision) and the reference CPD log-probabilities on it: the
     'systematic search' of scripts/protein_reg3d3d.py:629-648 at a size that runs in seconds."""
@@ -312,6 +395,9 @@ if __name__ == "__main__":
         golden_api_surface()
     elif len(sys.argv) > 1 and sys.argv[1] == "pathstats":
         golden_pathstats()
+    elif len(sys.argv) > 1 and sys.argv[1] == "baselines":
+        d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
+        golden_baselines(d["target"], d["source"])
     elif len(sys.argv) > 1 and sys.argv[1] == "tessellation":
         d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
         golden_tessellation(d["target"], d["source"])
@@ -321,5 +407,6 @@ if __name__ == "__main__":
             golden_trajectories(t, s)
             golden_misc()
             golden_pathstats()
+            golden_baselines(t, s)
             golden_tessellation(t, s)
         golden_api_surface()

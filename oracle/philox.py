@@ -112,3 +112,54 @@ class PhiloxChainRNG:
 
     def uniform(self, a, b):
         return a + (b - a) * self._next_uniform()
+
+
+class PhiloxSeqRNG:
+    """Sequential reader of one chain's Philox stream, as the baseline-sampler kernels
+    (csrc/kernels_mh.cuh: PhiloxSeq) consume it: within a transition the words of blocks 0, 1, ...
+    are used in order; ``random()`` takes one word, normals come in Box-Muller pairs (two words, the
+    second normal is kept for the next request), ``gamma(d/2)`` is half the sum of squares of ``d``
+    normals.  ``begin_step()`` moves to the next transition and drops the kept normal."""
+
+    def __init__(self, seed, chain, dtype=np.float64, first_step=0):
+        self.key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        self.chain = int(chain)
+        self.dtype = np.dtype(dtype)
+        self.step = first_step - 1
+        self.begin_step()
+        self.step = first_step - 1
+
+    def begin_step(self):
+        self.step += 1
+        self.word, self.block, self.spare = 0, None, None
+
+    def _next_word(self):
+        b, i = divmod(self.word, 4)
+        if i == 0 or self.block is None:
+            assert b < 65536
+            ctr = (self.chain & 0xFFFFFFFF, self.chain >> 32, self.step & 0xFFFFFFFF, ((self.step >> 32) << 16) | b)
+            self.block = philox4x32_10(ctr, self.key)
+        self.word += 1
+        return self.block[i]
+
+    def _normal(self):
+        if self.spare is not None:
+            z, self.spare = self.spare, None
+            return z
+        wa = self._next_word()
+        wb = self._next_word()
+        z, self.spare = box_muller(wa, wb, self.dtype)
+        return z
+
+    def standard_normal(self, n):
+        return np.array([self._normal() for _ in range(n)], dtype=float)
+
+    def random(self):
+        return float(u01(self._next_word(), self.dtype))
+
+    def gamma(self, shape):
+        z = np.array([self._normal() for _ in range(int(round(2 * shape)))], dtype=self.dtype)
+        acc = self.dtype.type(0)
+        for v in z:  # same left-to-right accumulation as the kernel
+            acc = acc + v * v
+        return float(self.dtype.type(0.5) * acc)

@@ -1,5 +1,5 @@
 """
-Record / replay shim for the three RNG calls the slice samplers make
+Record / replay shim for the RNG calls the samplers make
 (oracle; test infrastructure only).
 
 Assigned to ``sampler.rng`` of the upstream samplers it reproduces their own
@@ -41,6 +41,17 @@ class TapeRNG:
         u = self.tape[self.cursor]
         self.cursor += 1
         return u
+
+    def gamma(self, shape):
+        """Radius draw of the random-walk proposal (geosss/mcmc.py:142): the gamma variate itself goes on
+        the tape."""
+        if self.source is not None:
+            g = self.source.gamma(shape)
+            self.values.append(g)
+            return g
+        g = self.tape[self.cursor]
+        self.cursor += 1
+        return g
 
     def uniform(self, a, b):
         return a + (b - a) * self.random()

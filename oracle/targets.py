@@ -46,6 +46,14 @@ class VMFMixture:
         p = p + np.log(self.weights)
         return logsumexp(p, axis=-1)
 
+    def gradient(self, x):
+        """sum_k exp(p_k) mu_k / exp(logsumexp(p)) (distributions.py:223-227; component gradient = mu,
+        :159-160).  The un-shifted exp underflows to 0/0 far from every mode, as upstream."""
+        x = np.asarray(x, dtype=float)
+        p = np.array([self.component_log_prob(k, x) for k in range(len(self.mus))]) + np.log(self.weights)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.sum(np.exp(p) * self.mus.T, axis=1) / np.exp(logsumexp(p, axis=-1))
+
     def log_consts(self):
         """log w_k - log 2pi - log i0(kappa_k): what the device kernels precompute."""
         with np.errstate(over="ignore"):
@@ -61,6 +69,9 @@ class SingleVMF(VMFMixture):
 
     def log_prob(self, x):
         return self.component_log_prob(0, np.asarray(x, dtype=float))
+
+    def gradient(self, x):
+        return self.mus[0]
 
 
 class Bingham:
@@ -81,6 +92,11 @@ class Bingham:
     @property
     def mode(self):
         return self.U[:, 0]
+
+    def gradient(self, x):
+        """2 A x (distributions.py:88-89).  BinghamFisher inherits it unchanged upstream, so the
+        Fisher term b does NOT enter the gradient; kept."""
+        return 2 * self.A @ np.asarray(x, dtype=float)
 
     def log_prob(self, x):
         x = np.asarray(x, dtype=float)
@@ -154,6 +170,10 @@ class CurvedVMF:
             return self.kappa * (x @ self.nearest(x))
         return np.array([self.log_prob(row) for row in x])
 
+    def gradient(self, x):
+        """kappa * nearest curve point (distributions.py:277-278)."""
+        return self.kappa * self.nearest(np.asarray(x, dtype=float))
+
 
 def quat_to_matrix(q):
     """scipy Rotation.from_quat(q).as_matrix(): scalar-last, q normalised first
@@ -171,6 +191,28 @@ def quat_to_matrix_closed_form(q):
             [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
         ]
     )
+
+
+def rotation_jacobian(q):
+    """MINUS dR/dq for R(q) = the rotation of q / |q|, scalar-last, shape (3, 3, 4)
+    (pointcloud.py:135-203; the sign flip is upstream's and cancels the one in ``grad_R``).
+    Written as the quotient rule on R = N / r, N the homogeneous quadratic form, r = |q|^2 + 1e-300."""
+    x, y, z, w = np.asarray(q, dtype=float)
+    r = w**2 + x**2 + y**2 + z**2 + 1e-300
+    N = np.array(
+        [
+            [w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+            [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+            [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z],
+        ]
+    )
+    dN = np.zeros((3, 3, 4))
+    dN[..., 0] = 2 * np.array([[x, y, z], [y, -x, -w], [z, w, -x]])
+    dN[..., 1] = 2 * np.array([[-y, x, w], [x, y, z], [-w, z, -y]])
+    dN[..., 2] = 2 * np.array([[-z, -w, x], [w, -z, y], [x, y, z]])
+    dN[..., 3] = 2 * np.array([[w, -z, y], [z, w, -x], [-y, x, w]])
+    dr = 2 * np.array([x, y, z, w])
+    return -(dN / r - N[..., None] * dr / r**2)
 
 
 class CPD:
@@ -230,6 +272,34 @@ class CPD:
         R = q if q.shape == (3, 3) else quat_to_matrix(q)
         return self.beta * self.log_prob_R(R)
 
+    def _row_log_norm(self, log_p):
+        """log p_l that the responsibilities are taken against (registration.py:217-247: outlier
+        column included)."""
+        col = np.full((len(self.target), 1), self.log_outlier)
+        return logsumexp(np.hstack((log_p, col)), axis=1)
+
+    def _log_terms(self, dist, ind):
+        return np.log(self.w_s[ind]) + (-0.5 * dist**2 / self.sigma**2) + self.log_constant
+
+    def grad_R(self, q):
+        """d log p / d R as a 3x3 array (registration.py:261-293): responsibilities
+        gamma = exp(clip(log p_lk - log p_l, -20, 0)), residuals y_l - R x_k, outer products with
+        the un-rotated source points."""
+        moved = self.source @ quat_to_matrix(q).T
+        dist, ind = self._neighbours(moved)
+        log_p = self._log_terms(dist, ind)
+        gamma = np.exp(np.clip(log_p - self._row_log_norm(log_p)[:, None], -20, 0))
+        resid = self.target[:, None, :] - moved[ind]
+        coeff = (self.w_t[:, None] * gamma) / self.sigma**2
+        return -np.einsum("lk,lkj,lki->ji", coeff, resid, self.source[ind])
+
+    def gradient(self, q):
+        """Chain rule through the (sign-flipped) Jacobian of R(q) (registration.py:55-59,
+        pointcloud.py:135-203)."""
+        q = np.asarray(q, dtype=float)
+        g = (self.beta * self.grad_R(q)).ravel()
+        return rotation_jacobian(q).reshape(9, 4).T @ g
+
 
 class GMM(CPD):
     """Parent model without the outlier column / (1-omega) factor
@@ -242,7 +312,13 @@ class GMM(CPD):
     def log_prob_R(self, R):
         moved = self.source @ R.T
         dist, ind = self._neighbours(moved)
+        return logsumexp(self._log_terms(dist, ind), axis=1) @ self.w_t
+
+    def _log_terms(self, dist, ind):
         D = self.target.shape[1]
         log_phi = -0.5 * dist**2 / self.sigma**2
-        log_p = log_phi - D / 2 * np.log(2 * np.pi * self.sigma**2) + np.log(self.w_s[ind])
-        return logsumexp(log_p, axis=1) @ self.w_t
+        return log_phi - D / 2 * np.log(2 * np.pi * self.sigma**2) + np.log(self.w_s[ind])
+
+    def _row_log_norm(self, log_p):
+        # registration.py:134-135: no outlier column in the parent model
+        return logsumexp(log_p, axis=1)
