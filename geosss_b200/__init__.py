@@ -20,7 +20,11 @@ from .distributions import (  # noqa: F401
     random_bingham,
 )
 from .mcmc import (  # noqa: F401
+    IndependenceSampler,
+    MetropolisHastings,
+    MixtureRWMHIndependenceSampler,
     RejectionSphericalSliceSampler,
+    SphericalHMC,
     ShrinkageSphericalSliceSampler,
     determine_burnin,
 )

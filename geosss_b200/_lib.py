@@ -10,6 +10,7 @@ import os
 
 F32, F64 = 0, 1
 REJECT, SHRINK = 0, 1
+RWMH, INDEPENDENCE, MIXTURE, HMC = 2, 3, 4, 5
 PATH_LITERAL, PATH_FAST = 0, 1
 STEP_MAJOR, CHAIN_MAJOR = 0, 1
 
@@ -43,6 +44,11 @@ SIGNATURES = {
     "geosss_sampler_get_state_host": (_i, [_p, _pd, _p]),
     "geosss_sampler_run_host": (_i, [_p, _i64, _i64, _p]),
     "geosss_diag_ess_partials": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _p, _p]),
+    "geosss_sampler_mh_configure": (_i, [_p, C.c_double, C.c_double, _i]),
+    "geosss_sampler_mh_reset": (_i, [_p, _i64]),
+    "geosss_sampler_mh_momenta_out": (_i, [_p, _p]),
+    "geosss_sampler_mh_get_host": (_i, [_p, _pd, _p, _pd]),
+    "geosss_gradient": (_i, [_p, _i, _p, _p, _i64, _p]),
     "geosss_diag_path_stats": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p]),
     "geosss_sample_host": (_i, [_p, _i, _i, _i, _i64, _pd, _u64, _u64, _i64, _i64, _p, _p]),
 }

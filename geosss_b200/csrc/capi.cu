@@ -17,6 +17,7 @@
 #include "kernels_logp_fast.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_literal.cuh"
+#include "kernels_mh.cuh"
 
 using namespace geosss;
 
@@ -103,9 +104,25 @@ struct geosss_sampler {
     uint64_t seed = 0, chain0 = 0, step = 0;
     void* state = nullptr;  // (N, d) dtype
     void* ws = nullptr;     // literal path scratch (3, d, N)
-    unsigned long long* n_reject = nullptr;
+    unsigned long long* n_reject = nullptr;  // baseline samplers: accepted proposals
+    // baseline samplers (kind >= GEOSSS_RWMH)
+    double* stepsize = nullptr;
+    int64_t* adapt_count = nullptr;
+    unsigned long long* n_walk = nullptr;
+    void* momentum = nullptr;
+    void* momenta_out = nullptr;
+    int64_t adapt_total = 0;
+    double alpha = 0.5;
+    int n_leap = 10;
+    bool is_mh() const { return kind >= GEOSSS_RWMH; }
     size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
 };
+
+static int fill_stepsize(geosss_sampler* s, double value) {
+    std::vector<double> h((size_t)s->N, value);
+    CU(cudaMemcpy(s->stepsize, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
 
 // ------------------------------------------------------------------ fast-path dispatch
 // the normals stay in shared memory for d < 64 and for dense Bingham (kernels_gc.cuh, STORE); measured on
@@ -471,7 +488,9 @@ extern "C" int geosss_log_prob(geosss_target_t t, int dtype, int path, const voi
 extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int path, int64_t N, uint64_t seed,
                                      uint64_t chain_offset, geosss_sampler_t* out) {
     if (!t || !out || N < 1) return fail(GEOSSS_E_INVALID, "sampler_create: bad arguments");
-    if (kind != GEOSSS_REJECT && kind != GEOSSS_SHRINK) return fail(GEOSSS_E_INVALID, "sampler_create: kind must be reject or shrink");
+    if (kind < GEOSSS_REJECT || kind > GEOSSS_HMC) return fail(GEOSSS_E_INVALID, "sampler_create: unknown sampler kind");
+    const bool mh = kind >= GEOSSS_RWMH;
+    if (mh && path == GEOSSS_PATH_FAST) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the baseline samplers run on the literal path");
     if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "sampler_create: dtype must be f32 or f64");
     if (path == GEOSSS_PATH_FAST) {
         if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the fast path is float32 only");
@@ -484,7 +503,15 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     cudaError_t e = cudaMalloc(&s->state, (size_t)N * t->d * es);
     if (e == cudaSuccess) e = cudaMalloc(&s->n_reject, (size_t)N * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(s->n_reject, 0, (size_t)N * sizeof(unsigned long long));
-    if (e == cudaSuccess && path == GEOSSS_PATH_LITERAL && t->kind != TGT_CPD) e = cudaMalloc(&s->ws, (size_t)3 * N * t->d * es);
+    if (e == cudaSuccess && path == GEOSSS_PATH_LITERAL && t->kind != TGT_CPD) e = cudaMalloc(&s->ws, (size_t)(mh ? 5 : 3) * N * t->d * es);
+    if (e == cudaSuccess && mh) e = cudaMalloc(&s->stepsize, (size_t)N * sizeof(double));
+    if (e == cudaSuccess && mh) e = cudaMalloc(&s->adapt_count, (size_t)N * sizeof(int64_t));
+    if (e == cudaSuccess && mh) e = cudaMemset(s->adapt_count, 0, (size_t)N * sizeof(int64_t));
+    if (e == cudaSuccess && mh) e = cudaMalloc(&s->n_walk, (size_t)N * sizeof(unsigned long long));
+    if (e == cudaSuccess && mh) e = cudaMemset(s->n_walk, 0, (size_t)N * sizeof(unsigned long long));
+    if (e == cudaSuccess && mh) e = cudaMalloc(&s->momentum, (size_t)N * t->d * es);
+    if (e == cudaSuccess && mh) e = cudaMemset(s->momentum, 0, (size_t)N * t->d * es);  // mcmc.py:268: zero momenta
+    if (e == cudaSuccess && mh && fill_stepsize(s, kind == GEOSSS_HMC ? 1e-3 : 1e-1)) e = cudaErrorUnknown;  // mcmc.py:116,248
     if (e != cudaSuccess) {
         geosss_sampler_destroy(s);
         return fail(e == cudaErrorMemoryAllocation ? GEOSSS_E_NOMEM : GEOSSS_E_CUDA, "sampler_create: %s", cudaGetErrorString(e));
@@ -498,6 +525,10 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     if (s->state) cudaFree(s->state);
     if (s->ws) cudaFree(s->ws);
     if (s->n_reject) cudaFree(s->n_reject);
+    if (s->stepsize) cudaFree(s->stepsize);
+    if (s->adapt_count) cudaFree(s->adapt_count);
+    if (s->n_walk) cudaFree(s->n_walk);
+    if (s->momentum) cudaFree(s->momentum);
     delete s;
     return 0;
 }
@@ -538,7 +569,23 @@ template <typename T, int KIND, bool TAPE> static int launch_literal(geosss_samp
     return 0;
 }
 
+template <typename T> static int dispatch_mh(geosss_sampler* s, bool tape, const RunArgs& a, cudaStream_t st) {
+    geosss_target* t = s->t;
+    int rc;
+    switch (t->kind) {
+        case TGT_VMF_MIX: rc = launch_mh<T>(t->vmf<T>(), s->kind, tape, a, st); break;
+        case TGT_BINGHAM: rc = launch_mh<T>(t->bingham<T>(), s->kind, tape, a, st); break;
+        case TGT_CURVED_VMF: rc = launch_mh<T>(t->curved<T>(), s->kind, tape, a, st); break;
+        case TGT_CPD: rc = launch_mh<T>(t->cpd<T>(), s->kind, tape, a, st); break;
+        default: return fail(GEOSSS_E_INVALID, "unknown target kind");
+    }
+    if (rc < 0) return fail(GEOSSS_E_UNSUPPORTED, "cpd: source cloud too large for shared memory");
+    if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
 template <bool TAPE> static int dispatch_literal(geosss_sampler* s, const RunArgs& a, cudaStream_t st) {
+    if (s->is_mh()) return s->dtype == GEOSSS_F64 ? dispatch_mh<double>(s, TAPE, a, st) : dispatch_mh<float>(s, TAPE, a, st);
     if (s->dtype == GEOSSS_F64)
         return s->kind == GEOSSS_SHRINK ? launch_literal<double, SHRINK, TAPE>(s, a, st) : launch_literal<double, REJECT, TAPE>(s, a, st);
     return s->kind == GEOSSS_SHRINK ? launch_literal<float, SHRINK, TAPE>(s, a, st) : launch_literal<float, REJECT, TAPE>(s, a, st);
@@ -548,6 +595,8 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     RunArgs a{};
     a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
     a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
+    a.stepsize = s->stepsize; a.adapt_count = s->adapt_count; a.n_walk = s->n_walk; a.momentum = s->momentum;
+    a.momenta_out = s->momenta_out; a.adapt_total = s->adapt_total; a.alpha = s->alpha; a.n_leap = s->n_leap;
     // quorum of the persistent bracket loop (kernels_fast.cuh); tuned on B200, see DESIGN.md
     a.ss_step = s->N * (int64_t)s->t->d; a.ss_chain = s->t->d; a.sl_step = s->N; a.sl_chain = 1;  // step-major
     a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 20;
@@ -710,6 +759,7 @@ extern "C" int geosss_sample_host(geosss_target_t t, int kind, int dtype, int pa
     int rc = geosss_sampler_create(t, kind, dtype, path, N, seed, chain_offset, &s);
     if (rc) return rc;
     rc = geosss_sampler_set_state_host(s, x0_host);
+    if (!rc && s->is_mh()) s->adapt_total = burnin;  // MetropolisHastings.sample: reset(burnin), mcmc.py:171
     // the first retained state is the initial state itself when there is no burn-in (mcmc.py:67-77)
     unsigned char* out = static_cast<unsigned char*>(samples_host);
     int64_t n_skip = burnin - 1, n_keep = n_samples;
@@ -725,6 +775,76 @@ extern "C" int geosss_sample_host(geosss_target_t t, int kind, int dtype, int pa
     if (!rc && n_reject_host) rc = geosss_sampler_get_state_host(s, nullptr, n_reject_host);
     geosss_sampler_destroy(s);
     return rc;
+}
+
+// ------------------------------------------------------------------ baseline samplers: parameters
+extern "C" int geosss_sampler_mh_configure(geosss_sampler_t s, double stepsize, double mixing_probability, int n_leapfrog) {
+    if (!s || !s->is_mh()) return fail(GEOSSS_E_INVALID, "mh_configure: not a baseline sampler");
+    if (stepsize > 0) { int rc = fill_stepsize(s, stepsize); if (rc) return rc; }
+    else if (stepsize != 0) return fail(GEOSSS_E_INVALID, "mh_configure: stepsize must be positive (0 keeps the current values)");  // mcmc.py:98
+    if (mixing_probability >= 0) {
+        if (mixing_probability > 1) return fail(GEOSSS_E_INVALID, "mh_configure: mixing probability must lie in [0, 1]");
+        s->alpha = mixing_probability;
+    }
+    if (n_leapfrog > 0) s->n_leap = n_leapfrog;
+    return 0;
+}
+
+extern "C" int geosss_sampler_mh_reset(geosss_sampler_t s, int64_t adapt_steps) {
+    if (!s || !s->is_mh() || adapt_steps < 0) return fail(GEOSSS_E_INVALID, "mh_reset: need a baseline sampler and adapt_steps >= 0");
+    CU(cudaMemset(s->adapt_count, 0, (size_t)s->N * sizeof(int64_t)));
+    s->adapt_total = adapt_steps;
+    return 0;
+}
+
+extern "C" int geosss_sampler_mh_momenta_out(geosss_sampler_t s, void* momenta_out) {
+    if (!s || s->kind != GEOSSS_HMC) return fail(GEOSSS_E_INVALID, "mh_momenta_out: not an HMC sampler");
+    s->momenta_out = momenta_out;
+    return 0;
+}
+
+extern "C" int geosss_sampler_mh_get_host(geosss_sampler_t s, double* stepsize_host, uint64_t* n_walk_host, double* momentum_host) {
+    if (!s || !s->is_mh()) return fail(GEOSSS_E_INVALID, "mh_get_host: not a baseline sampler");
+    CU(cudaDeviceSynchronize());
+    if (stepsize_host) CU(cudaMemcpy(stepsize_host, s->stepsize, (size_t)s->N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n_walk_host) CU(cudaMemcpy(n_walk_host, s->n_walk, (size_t)s->N * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (momentum_host) {
+        const size_t n = (size_t)s->N * s->t->d;
+        if (s->dtype == GEOSSS_F64) {
+            CU(cudaMemcpy(momentum_host, s->momentum, n * 8, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<float> f(n);
+            CU(cudaMemcpy(f.data(), s->momentum, n * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i) momentum_host[i] = (double)f[i];
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ gradient
+template <typename T> static int gradient_any(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
+    const T* xi = static_cast<const T*>(x);
+    T* o = static_cast<T*>(out);
+    int rc;
+    switch (t->kind) {
+        case TGT_VMF_MIX: rc = launch_grad<T>(t->vmf<T>(), xi, o, N, st); break;
+        case TGT_BINGHAM: rc = launch_grad<T>(t->bingham<T>(), xi, o, N, st); break;
+        case TGT_CURVED_VMF: rc = launch_grad<T>(t->curved<T>(), xi, o, N, st); break;
+        case TGT_CPD: rc = launch_grad<T>(t->cpd<T>(), xi, o, N, st); break;
+        default: return fail(GEOSSS_E_INVALID, "unknown target kind");
+    }
+    if (rc < 0) return fail(GEOSSS_E_UNSUPPORTED, "cpd: source cloud too large for shared memory");
+    if (rc > 0) return fail(GEOSSS_E_CUDA, "gradient: %s", cudaGetErrorString((cudaError_t)rc));
+    return 0;
+}
+
+extern "C" int geosss_gradient(geosss_target_t t, int dtype, const void* x, void* out, int64_t N, void* stream) {
+    if (!t || N < 0) return fail(GEOSSS_E_INVALID, "gradient: bad arguments");
+    if (N == 0) return 0;
+    if (!x || !out) return fail(GEOSSS_E_INVALID, "gradient: null buffer");
+    if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "gradient: dtype must be f32 or f64");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dtype == GEOSSS_F64 ? gradient_any<double>(t, x, out, N, st) : gradient_any<float>(t, x, out, N, st);
 }
 
 // ------------------------------------------------------------------ diagnostics

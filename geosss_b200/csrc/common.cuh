@@ -50,6 +50,7 @@ template <> struct Const<float> {
     static GEOSSS_HD float two_pi() { return 6.283185307179586f; }
     static GEOSSS_HD float log_two_pi() { return 1.8378770664093453f; }
     static GEOSSS_HD float tiny() { return 0.0f; }  // 1e-100 is 0 in fp32
+    static GEOSSS_HD float tiny_r() { return 0.0f; }
     static GEOSSS_HD float neg_inf() { return -INFINITY; }
     static GEOSSS_HD float bracket_floor() { return 1e-9f; }  // |theta| below fp32 resolution of a unit vector
 };
@@ -57,6 +58,7 @@ template <> struct Const<double> {
     static GEOSSS_HD double two_pi() { return 6.283185307179586; }       // 2*np.pi
     static GEOSSS_HD double log_two_pi() { return 1.8378770664093453; }  // np.log(2*np.pi)
     static GEOSSS_HD double tiny() { return 1e-100; }                    // geosss/sphere.py:14
+    static GEOSSS_HD double tiny_r() { return 1e-300; }                  // geosss/pointcloud.py:152
     static GEOSSS_HD double neg_inf() { return -INFINITY; }
     static GEOSSS_HD double bracket_floor() { return 1e-18; }
 };

@@ -76,6 +76,15 @@ struct RunArgs {
     // output layout in elements: kept state k of chain c goes to samples[k * ss_step + c * ss_chain + j],
     // scalars to [k * sl_step + c * sl_chain]  (step-major: (N d, d, N, 1); chain-major: (d, n_keep d, 1, n_keep))
     int64_t ss_step, ss_chain, sl_step, sl_chain;
+    // baseline samplers (kernels_mh.cuh); n_reject then counts ACCEPTED proposals
+    double* stepsize;              // (N) per-chain step size
+    int64_t* adapt_count;          // (N) adaptation steps already taken
+    unsigned long long* n_walk;    // (N) random-walk proposals of the mixture sampler
+    void* momentum;                // (N, d) HMC momenta, in/out
+    void* momenta_out;             // like samples, or null
+    int64_t adapt_total;           // burn-in length of the step-size adaptation
+    double alpha;                  // mixture: probability of a random-walk proposal
+    int n_leap;                    // HMC leapfrog steps
 };
 
 template <typename T, int KIND, bool TAPE> struct DrawsOf;

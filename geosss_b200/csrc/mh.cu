@@ -1,0 +1,59 @@
+// Launchers of the baseline-sampler and gradient kernels (kernels_mh.cuh); a translation unit of its own
+// so that it builds in parallel with capi.cu.
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "kernels_mh.cuh"
+
+namespace geosss {
+
+template <typename T, class P> int launch_mh(const P& p, int kind, bool tape, const RunArgs& a, cudaStream_t st) {
+    if constexpr (std::is_same<P, CpdP<T>>::value) {
+        const size_t smem = (size_t)CPD_WARPS * 3 * p.ns * sizeof(T);
+        if (smem > 200 * 1024) return -1;
+        const unsigned grid = (unsigned)((a.N + CPD_WARPS - 1) / CPD_WARPS);
+        cudaError_t e;
+        if (tape) {
+            e = cudaFuncSetAttribute(k_mh_cpd<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            k_mh_cpd<T, true><<<grid, CPD_WARPS * 32, smem, st>>>(p, kind, a);
+        } else {
+            e = cudaFuncSetAttribute(k_mh_cpd<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            k_mh_cpd<T, false><<<grid, CPD_WARPS * 32, smem, st>>>(p, kind, a);
+        }
+    } else {
+        const unsigned grid = (unsigned)((a.N + LANE_BLOCK - 1) / LANE_BLOCK);
+        if (tape) k_mh_lane<T, true><<<grid, LANE_BLOCK, 0, st>>>(p, kind, a);
+        else k_mh_lane<T, false><<<grid, LANE_BLOCK, 0, st>>>(p, kind, a);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <typename T, class P> int launch_grad(const P& p, const T* x, T* out, int64_t N, cudaStream_t st) {
+    if constexpr (std::is_same<P, CpdP<T>>::value) {
+        const size_t smem = (size_t)CPD_WARPS * 3 * p.ns * sizeof(T);
+        if (smem > 200 * 1024) return -1;
+        cudaError_t e = cudaFuncSetAttribute(k_grad_cpd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k_grad_cpd<T><<<(unsigned)((N + CPD_WARPS - 1) / CPD_WARPS), CPD_WARPS * 32, smem, st>>>(p, x, out, N);
+    } else {
+        k_grad_lane<T><<<(unsigned)((N + LANE_BLOCK - 1) / LANE_BLOCK), LANE_BLOCK, 0, st>>>(p, x, out, N);
+    }
+    return (int)cudaGetLastError();
+}
+
+#define GEOSSS_MH_INSTANCES(T)                                                                        \
+    template int launch_mh<T, VmfMixP<T>>(const VmfMixP<T>&, int, bool, const RunArgs&, cudaStream_t);   \
+    template int launch_mh<T, BinghamP<T>>(const BinghamP<T>&, int, bool, const RunArgs&, cudaStream_t); \
+    template int launch_mh<T, CurvedP<T>>(const CurvedP<T>&, int, bool, const RunArgs&, cudaStream_t);   \
+    template int launch_mh<T, CpdP<T>>(const CpdP<T>&, int, bool, const RunArgs&, cudaStream_t);         \
+    template int launch_grad<T, VmfMixP<T>>(const VmfMixP<T>&, const T*, T*, int64_t, cudaStream_t);     \
+    template int launch_grad<T, BinghamP<T>>(const BinghamP<T>&, const T*, T*, int64_t, cudaStream_t);   \
+    template int launch_grad<T, CurvedP<T>>(const CurvedP<T>&, const T*, T*, int64_t, cudaStream_t);     \
+    template int launch_grad<T, CpdP<T>>(const CpdP<T>&, const T*, T*, int64_t, cudaStream_t);
+GEOSSS_MH_INSTANCES(float)
+GEOSSS_MH_INSTANCES(double)
+
+}  // namespace geosss

@@ -54,6 +54,29 @@ template <typename T> struct VmfMixP {
             }
         return lse_finish(a_max, s, n_max);
     }
+    // distributions.py:159-160 (component: mu) and :223-227 (mixture: responsibilities times mu).  The
+    // reference forms exp(p_k) / exp(logsumexp p) without a shift, which is 0/0 far from every mode;
+    // the shifted softmax here is the same number wherever that is finite.
+    template <class Vec, class Out> GEOSSS_HD void grad(Vec v, Out g) const {
+        if (single) {
+            for (int j = 0; j < d; ++j) g[j] = mu[j];
+            return;
+        }
+        T a_max = Const<T>::neg_inf();
+        for (int k = 0; k < K; ++k) {
+            T a = comp(k, v) + logw[k];
+            if (a > a_max) a_max = a;
+        }
+        for (int j = 0; j < d; ++j) g[j] = T(0);
+        T tot = 0;
+        for (int k = 0; k < K; ++k) {
+            T e = m_exp((comp(k, v) + logw[k]) - a_max);
+            tot += e;
+            const T* m = mu + (int64_t)k * d;
+            for (int j = 0; j < d; ++j) g[j] += e * m[j];
+        }
+        for (int j = 0; j < d; ++j) g[j] = g[j] / tot;
+    }
 };
 
 // ------------------------------------------------------------------ Bingham (+ Fisher term)
@@ -75,6 +98,14 @@ template <typename T> struct BinghamP {
             tot += lin;
         }
         return tot;
+    }
+    // 2 A x (distributions.py:88-89); BinghamFisher inherits it, so b does not enter (kept as upstream)
+    template <class Vec, class Out> GEOSSS_HD void grad(Vec v, Out g) const {
+        for (int i = 0; i < d; ++i) {
+            T row = 0;
+            for (int j = 0; j < d; ++j) row += (T(2) * A[(int64_t)i * d + j]) * v[j];
+            g[i] = row;
+        }
     }
 };
 
@@ -114,6 +145,24 @@ template <typename T> struct CurvedP {
             ga = gb;
         }
         return kappa * best_dot;
+    }
+    // kappa * nearest curve point (distributions.py:277-278, spherical_curve.py:27-32,95-102)
+    template <class Vec, class Out> GEOSSS_HD void grad(Vec v, Out g) const {
+        T ga = knot_dot(0, v);
+        T best_dist = 0, best_t = 0;
+        int best = 0;
+        for (int j = 0; j + 1 < M; ++j) {
+            T gb = knot_dot(j + 1, v);
+            T t = m_clip(m_atan2(gb - ga * cosang[j], ga * sinang[j]), T(0), ang[j]);
+            T dot = (m_sin(ang[j] - t) * ga + m_sin(t) * gb) / (sinang[j] + T(1e-10));
+            T dist = m_acos(m_clip(dot, T(-1), T(1)));
+            if (j == 0 || dist < best_dist) { best_dist = dist; best_t = t; best = j; }
+            ga = gb;
+        }
+        const T ca = m_sin(ang[best] - best_t), cb = m_sin(best_t), den = sinang[best] + T(1e-10);
+        const T* a = knots + (int64_t)best * d;
+        const T* b = a + d;
+        for (int j = 0; j < d; ++j) g[j] = kappa * ((ca * a[j] + cb * b[j]) / den);
     }
 };
 
@@ -201,6 +250,88 @@ template <typename T> GEOSSS_HD T cpd_row(const CpdP<T>& p, const T* moved, int 
     }
     if (n_max == 0) n_max = 1;
     return lse_finish(a_max, s, n_max) * p.wt[l];
+}
+
+// ---- gradient of the registration log-likelihood (registration.py:55-59, :261-293) -------------
+// Row l adds  w_l / sigma^2 * sum_k gamma_lk (y_l - R x_k) x_k^T  to G (3x3, row-major), with
+// gamma_lk = exp(clip(log p_lk - log p_l, -20, 0)) and log p_l the row's logsumexp (outlier column
+// included for CPD).  G = -grad_R of the reference; the two minus signs of upstream (grad_R and the
+// Jacobian) cancel in cpd_grad_finish.
+template <typename T> GEOSSS_HD void cpd_row_grad(const CpdP<T>& p, const T* moved, int l, T G[9]) {
+    const T t0 = p.tgt[3 * l], t1 = p.tgt[3 * l + 1], t2 = p.tgt[3 * l + 2];
+    const bool dense = p.k <= 0 || p.k >= p.ns;
+    T a_max = p.outlier ? p.log_outlier : Const<T>::neg_inf();
+    int n_max = p.outlier ? 1 : 0;
+    T s = 0;
+    T bd[CPD_KMAX];
+    int bi[CPD_KMAX];
+    int cnt = 0;
+    if (dense) {
+        for (int k = 0; k < p.ns; ++k) {
+            T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+            T a = cpd_term(p, e0 * e0 + e1 * e1 + e2 * e2, p.logws[k]);
+            if (a > a_max) { a_max = a; n_max = 1; } else if (a == a_max) ++n_max;
+        }
+        for (int k = 0; k < p.ns; ++k) {
+            T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+            T a = cpd_term(p, e0 * e0 + e1 * e1 + e2 * e2, p.logws[k]);
+            if (a != a_max) s += m_exp(a - a_max);
+        }
+    } else {
+        const int kk = p.k;
+        for (int k = 0; k < p.ns; ++k) {
+            T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+            T d2 = e0 * e0 + e1 * e1 + e2 * e2;
+            if (cnt < kk || d2 < bd[cnt - 1]) {
+                int i = cnt < kk ? cnt++ : kk - 1;
+                while (i > 0 && bd[i - 1] > d2) { bd[i] = bd[i - 1]; bi[i] = bi[i - 1]; --i; }
+                bd[i] = d2; bi[i] = k;
+            }
+        }
+        for (int i = 0; i < cnt; ++i) {
+            T a = cpd_term(p, bd[i], p.logws[bi[i]]);
+            bd[i] = a;
+            if (a > a_max) { a_max = a; n_max = 1; } else if (a == a_max) ++n_max;
+        }
+        for (int i = 0; i < cnt; ++i)
+            if (bd[i] != a_max) s += m_exp(bd[i] - a_max);
+    }
+    if (p.outlier && p.log_outlier != a_max) s += m_exp(p.log_outlier - a_max);
+    if (n_max == 0) n_max = 1;
+    const T log_pl = lse_finish(a_max, s, n_max);
+    const T wl = p.wt[l];
+    const int n = dense ? p.ns : cnt;
+    for (int i = 0; i < n; ++i) {
+        const int k = dense ? i : bi[i];
+        const T e0 = t0 - moved[3 * k], e1 = t1 - moved[3 * k + 1], e2 = t2 - moved[3 * k + 2];
+        const T a = dense ? cpd_term(p, e0 * e0 + e1 * e1 + e2 * e2, p.logws[k]) : bd[i];
+        const T c = (wl * m_exp(m_clip(a - log_pl, T(-20), T(0)))) / p.sigma2;
+        const T s0 = p.src[3 * k], s1 = p.src[3 * k + 1], s2 = p.src[3 * k + 2];
+        G[0] += c * e0 * s0; G[1] += c * e0 * s1; G[2] += c * e0 * s2;
+        G[3] += c * e1 * s0; G[4] += c * e1 * s1; G[5] += c * e1 * s2;
+        G[6] += c * e2 * s0; G[7] += c * e2 * s1; G[8] += c * e2 * s2;
+    }
+}
+
+// grad_q[c] = beta * sum_ji G[j][i] dR[j][i]/dq_c for R(q) = N(q) / r, r = |q|^2 + 1e-300 (the quotient-rule
+// form of pointcloud.py:135-203; q is not assumed to be a unit vector)
+template <typename T, class Out> GEOSSS_HD void cpd_grad_finish(const CpdP<T>& p, T x, T y, T z, T w, const T G[9], Out g) {
+    const T r = ((w * w + x * x) + y * y) + z * z + Const<T>::tiny_r();
+    const T Nm[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+                     2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+    const T dN[4][9] = {{x, y, z, y, -x, -w, z, w, -x},
+                        {-y, x, w, x, y, z, -w, z, -y},
+                        {-z, -w, x, w, -z, y, x, y, z},
+                        {w, -z, y, z, w, -x, -y, x, w}};
+    const T q[4] = {x, y, z, w};
+    T GN = 0;
+    for (int i = 0; i < 9; ++i) GN += G[i] * Nm[i];
+    for (int c = 0; c < 4; ++c) {
+        T acc = 0;
+        for (int i = 0; i < 9; ++i) acc += G[i] * (T(2) * dN[c][i]);
+        g[c] = p.beta * (acc / r - GN * (T(2) * q[c]) / (r * r));
+    }
 }
 
 }  // namespace geosss

@@ -10,7 +10,7 @@ GPU through libgeosss_cuda (no CPU fallback).
 ``log_prob(x)`` accepts a point ``(d,)`` or rows ``(N, d)`` as a numpy array or a torch tensor
 (host or CUDA) and returns the same kind.  The arithmetic runs in the input's precision:
 float64 input takes the float64 "literal" kernels (reference operation order), anything else
-float32.  ``gradient`` belongs to the HMC baseline and is outside this engine's scope.
+float32.  ``gradient`` (used by the spherical HMC baseline) is batched the same way.
 """
 
 from abc import ABC, abstractmethod
@@ -35,7 +35,8 @@ class Distribution(ABC):
         ...
 
     def gradient(self, x):
-        raise NotImplementedError("gradient is only used by the HMC baseline (out of scope, SURVEY.md section 8)")
+        """Gradient of ``log_prob`` in the ambient space, batched on the GPU like ``log_prob``."""
+        return self._evaluate(x, gradient=True)
 
     # ---- device handle -------------------------------------------------------------------
     def _create_handle(self, lib):
@@ -70,7 +71,7 @@ class Distribution(ABC):
         if len(shape) not in (1, 2) or shape[-1] != self.d:
             raise ValueError(f"expected a point ({self.d},) or rows (N, {self.d}), got {tuple(shape)}")
 
-    def _evaluate(self, x, device=None):
+    def _evaluate(self, x, device=None, gradient=False):
         is_torch = isinstance(x, torch.Tensor)
         if not is_torch:
             x = np.asarray(x)
@@ -83,15 +84,18 @@ class Distribution(ABC):
         code, tdt, _ = _device.dtype_code("float64" if is64 else "float32")
         single = x.ndim == 1
         xd = _device.to_device(x, tdt, dev).reshape(-1, self.d)
-        out = torch.empty(xd.shape[0], dtype=tdt, device=dev)
+        out = torch.empty(xd.shape if gradient else xd.shape[0], dtype=tdt, device=dev)
         with torch.cuda.device(dev):
             if xd.shape[0] == 0:
                 return out if is_torch else out.cpu().numpy()
             lib, h, args = _lib.lib(), self._handle(dev), (xd.data_ptr(), out.data_ptr(), xd.shape[0], _device.stream_ptr(dev))
-            # float32: bandwidth-bound tiled kernels where one exists for the target, else the literal kernel
-            rc = lib.geosss_log_prob(h, code, _lib.PATH_FAST, *args) if code == _lib.F32 else _lib.E_UNSUPPORTED
-            if rc == _lib.E_UNSUPPORTED:
-                rc = lib.geosss_log_prob(h, code, _lib.PATH_LITERAL, *args)
+            if gradient:
+                rc = lib.geosss_gradient(h, code, *args)
+            else:
+                # float32: bandwidth-bound tiled kernels where one exists for the target, else the literal kernel
+                rc = lib.geosss_log_prob(h, code, _lib.PATH_FAST, *args) if code == _lib.F32 else _lib.E_UNSUPPORTED
+                if rc == _lib.E_UNSUPPORTED:
+                    rc = lib.geosss_log_prob(h, code, _lib.PATH_LITERAL, *args)
             _lib.check(rc)
         if is_torch:
             res = out if x.is_cuda else out.cpu()
@@ -134,6 +138,10 @@ class VonMisesFisher(Distribution):
     def log_prob(self, x):
         return self._evaluate(x)
 
+    @counted
+    def gradient(self, x):
+        return self._evaluate(x, gradient=True)
+
 
 class MixtureModel(Distribution):
     """Mixture of components; weights are normalised, uniform by default (distributions.py:211-216).
@@ -170,6 +178,13 @@ class MixtureModel(Distribution):
         # upstream evaluates every component through its own counted log_prob (distributions.py:219)
         VonMisesFisher.log_prob.num_calls += len(self.pdfs)
         return self._evaluate(x)
+
+    @counted
+    def gradient(self, x):
+        """Responsibility-weighted component gradients (distributions.py:223-227)."""
+        VonMisesFisher.log_prob.num_calls += len(self.pdfs)
+        VonMisesFisher.gradient.num_calls += len(self.pdfs)
+        return self._evaluate(x, gradient=True)
 
 
 class Bingham(Distribution):
@@ -211,6 +226,10 @@ class Bingham(Distribution):
     def log_prob(self, x):
         return self._evaluate(x)
 
+    @counted
+    def gradient(self, x):
+        return self._evaluate(x, gradient=True)
+
 
 class BinghamFisher(Bingham):
     """exp(x^T A x + x . b)  (distributions.py:106-114)."""
@@ -226,6 +245,10 @@ class BinghamFisher(Bingham):
     @counted
     def log_prob(self, x):
         return self._evaluate(x)
+
+    @counted
+    def gradient(self, x):
+        return self._evaluate(x, gradient=True)
 
 
 def random_bingham(d=2, vmax=None, vmin=None, eigensystem=False, seed=None):
@@ -266,3 +289,7 @@ class CurvedVonMisesFisher(Distribution):
     @counted
     def log_prob(self, x):
         return self._evaluate(x)
+
+    @counted
+    def gradient(self, x):
+        return self._evaluate(x, gradient=True)

@@ -5,6 +5,10 @@ Geodesic slice samplers with the reference's interface, running N chains at once
     Sampler.__init__/__next__/sample       geosss/mcmc.py:28-77
     RejectionSphericalSliceSampler         geosss/mcmc.py:335-374
     ShrinkageSphericalSliceSampler         geosss/mcmc.py:377-401
+    MetropolisHastings (+ AdaptiveStepsize) geosss/mcmc.py:78-173
+    IndependenceSampler                    geosss/mcmc.py:176-179
+    MixtureRWMHIndependenceSampler         geosss/mcmc.py:182-234
+    SphericalHMC                           geosss/mcmc.py:237-332
 
 Drop-in use is unchanged::
 
@@ -121,6 +125,10 @@ class Sampler:
             self._host_state = buf
         return self._host_state[0] if self._single else self._host_state
 
+    def _positions(self):
+        """(N, d) float64 positions (``state`` of the HMC subclass also carries momenta)."""
+        return Sampler.state.fget(self).reshape(self.N, self.d)
+
     @state.setter
     def state(self, value):
         value = np.array(value, dtype=float).reshape(self.N, self.d)
@@ -201,7 +209,7 @@ class Sampler:
         if on_device:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, device=self.device)
             if keeps_current:
-                buf[:, 0] = torch.as_tensor(self.state.reshape(self.N, self.d), dtype=self._tdtype, device=self.device)
+                buf[:, 0] = torch.as_tensor(self._positions(), dtype=self._tdtype, device=self.device)
             if n_skip:
                 self._run_device(n_skip, None)
             if n_new:  # every chain appends its rows behind its own slot 0: (N, n_out, d) chain-major
@@ -210,7 +218,7 @@ class Sampler:
         else:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
             if keeps_current:
-                cur = self._host_state if self.rng.steps_done == 0 else self.state.reshape(self.N, self.d)
+                cur = self._host_state if self.rng.steps_done == 0 else self._positions()
                 buf[0] = torch.as_tensor(cur, dtype=self._tdtype)
             dst = buf[1:] if keeps_current else buf
             with torch.cuda.device(self.device):
@@ -258,3 +266,198 @@ class ShrinkageSphericalSliceSampler(RejectionSphericalSliceSampler):
     """GeoSSS-shrink: the proposal bracket shrinks towards the current state on rejections."""
 
     KIND = _lib.SHRINK
+
+
+class MetropolisHastings(Sampler):
+    """Random-walk Metropolis-Hastings on the sphere with burn-in step-size adaptation
+    (mcmc.py:78-173): radius ``sqrt(2 Gamma(d/2))``, isotropic Gaussian perturbation of scale
+    ``stepsize``, projection back to the sphere; during the first ``burnin`` transitions of ``sample``
+    every chain multiplies its own step size by 1.02 (accepted) or 0.98 (rejected)."""
+
+    KIND = _lib.RWMH
+
+    def __init__(self, distribution, initial_state, seed=None, stepsize=1e-1, **kwargs):
+        super().__init__(distribution, initial_state, seed, **kwargs)
+        stepsize = float(stepsize)
+        assert stepsize > 0.0
+        self._cfg = {"stepsize": stepsize, "alpha": -1.0, "n_leap": 0}
+        self._adapt = 0
+        self._n_accept = 0
+
+    # ---- device sampler ------------------------------------------------------------------
+    def _sampler(self):
+        fresh = self._h is None
+        h = super()._sampler()
+        if fresh:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_mh_configure(h, self._cfg["stepsize"], self._cfg["alpha"], self._cfg["n_leap"]))
+                _lib.check(_lib.lib().geosss_sampler_mh_reset(h, self._adapt))
+        return h
+
+    def _mh_host(self, want):
+        """Host copies of per-chain step sizes / random-walk counts / momenta."""
+        step = np.empty(self.N) if want == "stepsize" else None
+        walk = np.empty(self.N, dtype=np.uint64) if want == "n_walk" else None
+        mom = np.empty((self.N, self.d)) if want == "momentum" else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_mh_get_host(
+                self._h, None if step is None else _lib.dptr(step), None if walk is None else walk.ctypes.data_as(C.c_void_p),
+                None if mom is None else _lib.dptr(mom)))
+        return step if step is not None else (walk if walk is not None else mom)
+
+    # ---- reference attributes --------------------------------------------------------------
+    @property
+    def stepsize(self):
+        """Current step size: a float for one chain, ``(N,)`` otherwise (each chain adapts its own)."""
+        if self._h is None:
+            return self._cfg["stepsize"] if self._single else np.full(self.N, self._cfg["stepsize"])
+        s = self._mh_host("stepsize")
+        return float(s[0]) if self._single else s
+
+    @stepsize.setter
+    def stepsize(self, value):
+        value = float(value)
+        assert value > 0.0
+        self._cfg["stepsize"] = value
+        if self._h is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_mh_configure(self._h, value, -1.0, 0))
+
+    def reset(self, burnin):
+        """Restart the adaptation window (AdaptiveStepsize.reset, mcmc.py:101-104)."""
+        self._adapt = int(burnin)
+        assert self._adapt >= 0
+        if self._h is not None:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_mh_reset(self._h, self._adapt))
+
+    @property
+    def n_accept_per_chain(self):
+        return self.n_reject_per_chain  # the device counter holds accepted proposals for these kinds
+
+    @property
+    def n_accept(self):
+        """Accepted proposals so far, summed over chains (mcmc.py:133,158)."""
+        self._sync_counters()
+        return self._n_accept
+
+    @property
+    def n_reject(self):
+        raise AttributeError("n_reject belongs to the slice samplers; this sampler counts n_accept")
+
+    _GRADS_PER_STEP = 0
+
+    def _sync_counters(self):
+        if self._h is None:
+            return
+        self._n_accept = int(self.n_reject_per_chain.sum())
+        steps = self.rng.steps_done
+        new = (steps - self._steps_counted) * self.N
+        # upstream evaluates log_prob twice per transition (mcmc.py:149-153,287-289) and, for HMC,
+        # the gradient n_steps + 1 times (mcmc.py:298-311)
+        lp, gr = getattr(self.target, "log_prob", None), getattr(self.target, "gradient", None)
+        if new and hasattr(lp, "add_calls"):
+            lp.add_calls(2 * new)
+        if new and self._GRADS_PER_STEP and hasattr(gr, "add_calls"):
+            gr.add_calls(self._GRADS_PER_STEP * new)
+        self._steps_counted = steps
+
+    def sample(self, n_samples, burnin=0, return_all_samples=False, *, out=None):
+        """As ``Sampler.sample``; the burn-in is also the adaptation window (mcmc.py:164-173)."""
+        self.reset(determine_burnin(n_samples, burnin))
+        return super().sample(n_samples, burnin, return_all_samples, out=out)
+
+
+class IndependenceSampler(MetropolisHastings):
+    """Metropolis-Hastings with uniform proposals on the sphere (mcmc.py:176-179)."""
+
+    KIND = _lib.INDEPENDENCE
+
+
+class MixtureRWMHIndependenceSampler(MetropolisHastings):
+    """With probability ``mixing_probability`` a random-walk proposal, else a uniform one; only the
+    random-walk proposals adapt the step size (mcmc.py:182-234).  ``rwmh_stepsize_vals`` (the per-step
+    trace upstream appends to) is not kept; ``stepsize`` holds the current values."""
+
+    KIND = _lib.MIXTURE
+
+    def __init__(self, distribution, initial_state, seed=None, stepsize=1e-1, mixing_probability=0.5, **kwargs):
+        super().__init__(distribution, initial_state, seed, stepsize=stepsize, **kwargs)
+        self.alpha = float(mixing_probability)
+        assert 0.0 <= self.alpha <= 1.0
+        self._cfg["alpha"] = self.alpha
+
+    @property
+    def rwmh_counter(self):
+        return 0 if self._h is None else int(self._mh_host("n_walk").sum())
+
+    @property
+    def indep_counter(self):
+        return self.rng.steps_done * self.N - self.rwmh_counter
+
+
+class SphericalHMC(MetropolisHastings):
+    """Spherical Hamiltonian Monte Carlo (mcmc.py:237-332): tangent Gaussian momenta, ``n_steps``
+    geodesic leapfrog steps of size ``stepsize`` driven by ``target.gradient``, Metropolis correction.
+    ``state`` is ``[x, v]`` stacked as upstream; ``sample`` returns positions (and momenta on request)."""
+
+    KIND = _lib.HMC
+
+    def __init__(self, distribution, initial_state, seed=None, stepsize=1e-3, n_steps=10, **kwargs):
+        super().__init__(distribution, initial_state, seed, stepsize=stepsize, **kwargs)
+        self.n_steps = int(n_steps)
+        assert self.n_steps > 0
+        self._cfg["n_leap"] = self.n_steps
+        self._GRADS_PER_STEP = self.n_steps + 1
+
+    @property
+    def state(self):
+        x = self._positions()
+        v = np.zeros_like(x) if self._h is None else self._mh_host("momentum")
+        xv = np.hstack([x, v])
+        return xv[0] if self._single else xv
+
+    @state.setter
+    def state(self, value):
+        value = np.array(value, dtype=float).reshape(self.N, -1)
+        Sampler.state.fset(self, value[:, :self.d])  # momenta are redrawn at every transition
+
+    def __next__(self):
+        self._run_device(1, None)
+        return self.state.copy()
+
+    def sample(self, n_samples, burnin=0, return_momenta=False, return_all_samples=False, *, out=None):
+        if not return_momenta:
+            return super().sample(n_samples, burnin, return_all_samples, out=out)
+        assert n_samples > 0
+        burnin = determine_burnin(n_samples, burnin)
+        self.reset(burnin)
+        n_out = n_samples + burnin if return_all_samples else n_samples
+        keeps_current = return_all_samples or burnin == 0
+        n_skip = 0 if keeps_current else burnin - 1
+        n_new = n_out - 1 if keeps_current else n_out
+        h = self._sampler()
+        pos = torch.empty((self.N, n_out, self.d), dtype=self._tdtype, device=self.device)
+        mom = torch.empty_like(pos)
+        if keeps_current:
+            xv = self.state.reshape(self.N, 2 * self.d)
+            pos[:, 0] = torch.as_tensor(xv[:, :self.d], dtype=self._tdtype, device=self.device)
+            mom[:, 0] = torch.as_tensor(xv[:, self.d:], dtype=self._tdtype, device=self.device)
+        if n_skip:
+            self._run_device(n_skip, None)
+        if n_new:
+            first = 1 if keeps_current else 0
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().geosss_sampler_mh_momenta_out(h, mom[:, first:].data_ptr()))
+            try:
+                self._run_device(n_new, pos[:, first:], chain_major=True, chain_stride=n_out * self.d)
+                torch.cuda.synchronize(self.device)
+            finally:
+                with torch.cuda.device(self.device):
+                    _lib.check(_lib.lib().geosss_sampler_mh_momenta_out(h, None))
+        self._sync_counters()
+        if not (self._torch_io and self._device_req is not None):
+            pos, mom = pos.cpu(), mom.cpu()
+            if not self._torch_io:
+                pos, mom = pos.numpy(), mom.numpy()
+        return (pos[0], mom[0]) if self._single else (pos, mom)

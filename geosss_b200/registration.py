@@ -68,6 +68,13 @@ class GaussianMixtureModel(Registration):
             raise NotImplementedError("translations are not sampled by the reference's experiments")
         return self._evaluate(self._quaternions(rotation))
 
+    @counted
+    def gradient(self, rotation, translation=None):
+        """d log_prob / d q for scalar-last quaternions (registration.py:55-59, pointcloud.py:135-203)."""
+        if translation is not None:
+            raise NotImplementedError("translations are not sampled by the reference's experiments")
+        return self._evaluate(self._quaternions(rotation), gradient=True)
+
 
 class CoherentPointDrift(GaussianMixtureModel):
     """GMM plus a uniform outlier component of weight omega (registration.py:166-259)."""
@@ -84,3 +91,10 @@ class CoherentPointDrift(GaussianMixtureModel):
         if translation is not None:
             raise NotImplementedError("translations are not sampled by the reference's experiments")
         return self._evaluate(self._quaternions(rotation))
+
+    @counted
+    def gradient(self, rotation, translation=None):
+        """d log_prob / d q for scalar-last quaternions (registration.py:55-59, pointcloud.py:135-203)."""
+        if translation is not None:
+            raise NotImplementedError("translations are not sampled by the reference's experiments")
+        return self._evaluate(self._quaternions(rotation), gradient=True)

@@ -47,7 +47,7 @@ class counted:
 
 class SamplerLauncher:
     """Method name -> sampler dispatch (utils.py:188-232); keeps the sampler on ``.rsss`` /
-    ``.ssss``.  'rwmh' and 'hmc' are baselines outside this engine's scope."""
+    ``.ssss`` / ``.rwmh`` / ``.hmc``."""
 
     def __init__(self, pdf, initial, n_samples, burnin=0.2, seed=None, **sampler_kwargs):
         self.pdf, self.initial = pdf, initial
@@ -66,11 +66,25 @@ class SamplerLauncher:
         self.ssss = ShrinkageSphericalSliceSampler(self.pdf, self.initial, self.seed, **self.sampler_kwargs)
         return self.ssss.sample(self.n_samples, burnin=self.burnin)
 
+    def run_rwmh(self):
+        from .mcmc import MetropolisHastings
+
+        self.rwmh = MetropolisHastings(self.pdf, self.initial, self.seed, stepsize=1e-1, **self.sampler_kwargs)
+        return self.rwmh.sample(self.n_samples, burnin=self.burnin)
+
+    def run_hmc(self):
+        from .mcmc import SphericalHMC
+
+        self.hmc = SphericalHMC(self.pdf, self.initial, self.seed, stepsize=1e-1, **self.sampler_kwargs)
+        return self.hmc.sample(self.n_samples, burnin=self.burnin)
+
     def run(self, method):
         if method == "sss-reject":
             return self.run_sss_reject()
         if method == "sss-shrink":
             return self.run_sss_shrink()
-        if method in ("rwmh", "hmc"):
-            raise NotImplementedError(f"{method}: baseline sampler, not part of the B200 slice-sampling engine")
+        if method == "rwmh":
+            return self.run_rwmh()
+        if method == "hmc":
+            return self.run_hmc()
         raise ValueError(f"method {method} not known")

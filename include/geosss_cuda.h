@@ -42,7 +42,14 @@ extern "C" {
 #define GEOSSS_VERSION 100 /* 0.1.0 */
 
 enum { GEOSSS_F32 = 0, GEOSSS_F64 = 1 };
-enum { GEOSSS_REJECT = 0, GEOSSS_SHRINK = 1 };
+enum {
+    GEOSSS_REJECT = 0,       /* RejectionSphericalSliceSampler  (geosss/mcmc.py:335-374) */
+    GEOSSS_SHRINK = 1,       /* ShrinkageSphericalSliceSampler  (:377-401) */
+    GEOSSS_RWMH = 2,         /* MetropolisHastings              (:115-173) */
+    GEOSSS_INDEPENDENCE = 3, /* IndependenceSampler             (:176-179) */
+    GEOSSS_MIXTURE = 4,      /* MixtureRWMHIndependenceSampler  (:182-234) */
+    GEOSSS_HMC = 5           /* SphericalHMC                    (:237-332) */
+};
 /* LITERAL: reference operation order (any target, either dtype).
  * FAST:    float32 throughput kernels that use the great-circle algebra. */
 enum { GEOSSS_PATH_LITERAL = 0, GEOSSS_PATH_FAST = 1 };
@@ -142,6 +149,30 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
                        const double* x0_host, uint64_t seed, uint64_t chain_offset,
                        int64_t n_samples, int64_t burnin, void* samples_host,
                        uint64_t* n_reject_host);
+
+/* ---- baseline samplers of the reference's comparison ("next" row f3) ------------------------ */
+/* Kinds GEOSSS_RWMH .. GEOSSS_HMC are created with geosss_sampler_create (literal path) and driven by
+ * the same run / run_layout / run_tape / run_host / sample_host entry points.  For them the counter
+ * reported as n_reject counts ACCEPTED proposals (MetropolisHastings.n_accept, mcmc.py:133,158) and
+ * the per-transition output of run() is 1 if the transition accepted.  Tape order per transition:
+ * [mixture: choice uniform,] [random walk: the Gamma(d/2) variate,] d normals, acceptance uniform. */
+
+/* stepsize > 0 sets every chain's step size (0 keeps them; defaults 1e-1, HMC 1e-3: mcmc.py:116,248);
+ * mixing_probability in [0,1] (< 0 keeps; mcmc.py:194); n_leapfrog > 0 (<= 0 keeps; default 10). */
+int geosss_sampler_mh_configure(geosss_sampler_t s, double stepsize, double mixing_probability, int n_leapfrog);
+/* AdaptiveStepsize.reset(burnin) (mcmc.py:101-104): the next adapt_steps adapting transitions of every
+ * chain multiply its step size by 1.02 (accepted) or 0.98 (rejected). */
+int geosss_sampler_mh_reset(geosss_sampler_t s, int64_t adapt_steps);
+/* HMC: device buffer (same dtype / layout as the samples of the following run calls) that receives the
+ * momenta of the retained states (SphericalHMC.sample(return_momenta=True), mcmc.py:320-332); NULL stops. */
+int geosss_sampler_mh_momenta_out(geosss_sampler_t s, void* momenta_out);
+/* Host copies (any may be NULL): stepsize (N), random-walk proposals of the mixture sampler (N,
+ * rwmh_counter of mcmc.py:199,217), current momenta (N, d). */
+int geosss_sampler_mh_get_host(geosss_sampler_t s, double* stepsize_host, uint64_t* n_walk_host, double* momentum_host);
+
+/* Distribution.gradient(x) for x of shape (N, d) (distributions.py:88-89, :159-160, :223-227, :277-278;
+ * registration.py:55-59 with pointcloud.py:135-203).  x, out: (N, d) device, `dtype`. */
+int geosss_gradient(geosss_target_t t, int dtype, const void* x, void* out, int64_t N, void* stream);
 
 /* ---- diagnostics ("next" row of the scope table: ESS half of the metric) --------------------- */
 

@@ -1,4 +1,4 @@
-// TEST-ONLY host build of the device math (targets.cuh, transition.cuh, philox.cuh).
+// TEST-ONLY host build of the device math (targets.cuh, transition.cuh, transition_mh.cuh, philox.cuh).
 //
 // Compiled with g++ by tests/test_hostsim.py so that the per-chain arithmetic the CUDA kernels
 // run can be checked against the golden vectors on a machine without a GPU.  It is not part of
@@ -11,6 +11,7 @@
 #include "philox.cuh"
 #include "targets.cuh"
 #include "transition.cuh"
+#include "transition_mh.cuh"
 
 using namespace geosss;
 
@@ -86,6 +87,85 @@ template <typename T> struct HostLogP {
     }
 };
 
+// value + gradient as the baseline-sampler kernels see them (kernels_mh.cuh: LaneTarget / CpdWarpTarget)
+template <typename T> struct HostTarget {
+    HostLogP<T> lp;
+    template <class Vec> T logp(Vec v) const { return lp(v); }
+    template <class Vec, class Out> void grad(Vec v, Out g) const {
+        const Built<T>* b = lp.b;
+        switch (lp.s->kind) {
+            case TGT_VMF_MIX: b->vmf.grad(v, g); break;
+            case TGT_BINGHAM: b->bing.grad(v, g); break;
+            case TGT_CURVED_VMF: b->curved.grad(v, g); break;
+            default: {
+                T R[9];
+                quat_to_matrix<T>(v[0], v[1], v[2], v[3], R);
+                lp.moved.resize((size_t)3 * b->cpd.ns);
+                cpd_move_source(b->cpd, R, lp.moved.data(), 0, 1);
+                T part[32][9] = {};
+                for (int l = 0; l < b->cpd.nt; ++l) cpd_row_grad(b->cpd, lp.moved.data(), l, part[l & 31]);
+                T G[9];
+                for (int i = 0; i < 9; ++i) {
+                    double s[32];
+                    for (int k = 0; k < 32; ++k) s[k] = (double)part[k][i];
+                    for (int o = 16; o > 0; o >>= 1)
+                        for (int k = 0; k < 32; ++k) if ((k & o) == 0) { double t = s[k] + s[k ^ o]; s[k] = s[k ^ o] = t; }
+                    G[i] = (T)s[0];
+                }
+                cpd_grad_finish(b->cpd, v[0], v[1], v[2], v[3], G, g);
+            }
+        }
+    }
+};
+
+template <typename T> void grad_all(const Spec& s, const double* x, double* out, int64_t N) {
+    Built<T> b(s);
+    HostTarget<T> f{{&s, &b, {}}};
+    std::vector<T> row(s.d), g(s.d);
+    for (int64_t i = 0; i < N; ++i) {
+        for (int j = 0; j < s.d; ++j) row[j] = (T)x[i * s.d + j];
+        f.grad(SVec<T>{row.data(), 1}, SVec<T>{g.data(), 1});
+        for (int j = 0; j < s.d; ++j) out[i * s.d + j] = (double)g[j];
+    }
+}
+
+// baseline samplers: per transition the position, momentum, step size and whether it accepted
+template <typename T, class Draws>
+int run_mh_chain(const Spec& s, int kind, Draws& dr, const double* x0, int64_t n_steps, uint64_t step0, double stepsize,
+                 MhParams mp, double* samples, double* momenta, double* stepsizes, int32_t* accepted, int64_t* n_walk) {
+    Built<T> b(s);
+    HostTarget<T> f{{&s, &b, {}}};
+    const int d = s.d;
+    std::vector<T> buf((size_t)5 * d, T(0));
+    SVec<T> x{buf.data(), 1}, v{buf.data() + d, 1}, xp{buf.data() + 2 * d, 1}, vp{buf.data() + 3 * d, 1}, g{buf.data() + 4 * d, 1};
+    for (int j = 0; j < d; ++j) x[j] = (T)x0[j];
+    MhChain ch{stepsize, 0, 0ull};
+    T lp = f.logp(x);
+    for (int64_t t = 0; t < n_steps; ++t) {
+        dr.begin_step(step0 + t);
+        const bool ok = mh_transition<T>(kind, d, x, v, xp, vp, g, dr, f, ch, mp, lp);
+        if (!dr.ok()) return 1;
+        for (int j = 0; j < d; ++j) { samples[t * d + j] = (double)x[j]; momenta[t * d + j] = (double)v[j]; }
+        stepsizes[t] = ch.stepsize;
+        accepted[t] = ok ? 1 : 0;
+    }
+    *n_walk = (int64_t)ch.n_walk;
+    return 0;
+}
+
+template <typename T> int run_mh_any(const Spec& s, int kind, const double* tape, int64_t tape_len, uint64_t seed, uint64_t chain,
+                                     const double* x0, int64_t n_steps, uint64_t step0, double stepsize, MhParams mp, double* samples,
+                                     double* momenta, double* stepsizes, int32_t* accepted, int64_t* n_walk) {
+    if (tape) {
+        TapeSeq<T> dr;
+        dr.t.init(tape, 0, tape_len);
+        return run_mh_chain<T>(s, kind, dr, x0, n_steps, step0, stepsize, mp, samples, momenta, stepsizes, accepted, n_walk);
+    }
+    PhiloxSeq<T> dr;
+    dr.init(seed, chain);
+    return run_mh_chain<T>(s, kind, dr, x0, n_steps, step0, stepsize, mp, samples, momenta, stepsizes, accepted, n_walk);
+}
+
 template <typename T> void logp_all(const Spec& s, const double* x, double* out, int64_t N) {
     Built<T> b(s);
     HostLogP<T> f{&s, &b, {}};
@@ -148,6 +228,21 @@ int hs_run(const Spec* s, int dtype, int kind, const double* tape, int64_t tape_
            const double* x0, int64_t n_steps, uint64_t step0, double* samples, int32_t* nrej) {
     return dtype == F64 ? run_any<double>(*s, kind, tape, tape_len, seed, chain, x0, n_steps, step0, samples, nrej)
                         : run_any<float>(*s, kind, tape, tape_len, seed, chain, x0, n_steps, step0, samples, nrej);
+}
+
+void hs_grad(const Spec* s, int dtype, const double* x, double* out, int64_t N) {
+    if (dtype == F64) grad_all<double>(*s, x, out, N); else grad_all<float>(*s, x, out, N);
+}
+
+// one chain of a baseline sampler (kind 2..5); outputs per transition
+int hs_run_mh(const Spec* s, int dtype, int kind, const double* tape, int64_t tape_len, uint64_t seed, uint64_t chain,
+              const double* x0, int64_t n_steps, uint64_t step0, double stepsize, double alpha, int n_leap, int64_t adapt_total,
+              double* samples, double* momenta, double* stepsizes, int32_t* accepted, int64_t* n_walk) {
+    MhParams mp{alpha, n_leap, adapt_total};
+    return dtype == F64 ? run_mh_any<double>(*s, kind, tape, tape_len, seed, chain, x0, n_steps, step0, stepsize, mp, samples, momenta,
+                                             stepsizes, accepted, n_walk)
+                        : run_mh_any<float>(*s, kind, tape, tape_len, seed, chain, x0, n_steps, step0, stepsize, mp, samples, momenta,
+                                            stepsizes, accepted, n_walk);
 }
 
 int hs_spec_size(void) { return (int)sizeof(Spec); }

@@ -47,6 +47,11 @@ def load():
     lib.hs_run.argtypes = [C.POINTER(Spec), C.c_int, C.c_int, _pd, C.c_int64, C.c_uint64, C.c_uint64, _pd, C.c_int64,
                            C.c_uint64, _pd, C.POINTER(C.c_int32)]
     lib.hs_run.restype = C.c_int
+    lib.hs_grad.argtypes = [C.POINTER(Spec), C.c_int, _pd, _pd, C.c_int64]
+    lib.hs_run_mh.argtypes = [C.POINTER(Spec), C.c_int, C.c_int, _pd, C.c_int64, C.c_uint64, C.c_uint64, _pd, C.c_int64,
+                              C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int64, _pd, _pd, _pd, C.POINTER(C.c_int32),
+                              C.POINTER(C.c_int64)]
+    lib.hs_run_mh.restype = C.c_int
     return lib
 
 
@@ -124,3 +129,25 @@ def run(lib, tgt, kind, x0, n_steps, dtype, tape=None, seed=0, chain=0, step0=0)
                     0 if tp is None else len(tp), seed, chain, _p(x0), n_steps, step0, _p(samples),
                     nrej.ctypes.data_as(C.POINTER(C.c_int32)))
     return rc, samples, nrej
+
+
+def grad(lib, tgt, x, dtype):
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=float)
+    out = np.empty_like(x)
+    lib.hs_grad(C.byref(tgt.spec), 1 if dtype == np.float64 else 0, _p(x), _p(out), len(x))
+    return out
+
+
+def run_mh(lib, tgt, kind, x0, n_steps, dtype, stepsize, tape=None, seed=0, chain=0, step0=0, alpha=0.5, n_leap=10, adapt=0):
+    """One chain of a baseline sampler (kind 2 RWMH, 3 independence, 4 mixture, 5 HMC).
+    Returns rc, positions, momenta, step sizes, accepted flags, random-walk proposal count."""
+    x0 = np.ascontiguousarray(x0, dtype=float)
+    d = tgt.spec.d
+    samples, momenta = np.empty((n_steps, d)), np.empty((n_steps, d))
+    steps, acc = np.empty(n_steps), np.empty(n_steps, dtype=np.int32)
+    n_walk = C.c_int64(0)
+    tp = None if tape is None else np.ascontiguousarray(tape, dtype=float)
+    rc = lib.hs_run_mh(C.byref(tgt.spec), 1 if dtype == np.float64 else 0, kind, None if tp is None else _p(tp),
+                       0 if tp is None else len(tp), seed, chain, _p(x0), n_steps, step0, stepsize, alpha, n_leap, adapt,
+                       _p(samples), _p(momenta), _p(steps), acc.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n_walk))
+    return rc, samples, momenta, steps, acc, n_walk.value
