@@ -51,6 +51,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--baselines", action="store_true", help="also time the RWMH / HMC baselines (literal fp32 kernels)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     for name, pdf, N, T, n_lp in cases(a.quick):
@@ -69,6 +70,22 @@ def main():
             rej = (int(smp.n_reject_per_chain.sum()) - r0) / (3 * T * N)
             print(json.dumps({"case": name, "sampler": tag, "path": smp.path, "chains": N, "transitions": T,
                               "samples_per_s": N * T / dt, "ms": dt * 1e3, "rejections_per_transition": rej}), flush=True)
+        if a.baselines:
+            Nb = min(N, 1 << 16)
+            for cls, tag, kw, Tb in ((gs.MetropolisHastings, "rwmh", dict(stepsize=0.1), T),
+                                     (gs.SphericalHMC, "hmc", dict(stepsize=0.02 if d > 4 else 1e-3, n_steps=10), max(T // 10, 2))):
+                smp = cls(pdf, x0[:Nb], 11, **kw)
+                smp.reset(10)
+                smp._run_device(10, None)
+                torch.cuda.synchronize()
+                a0 = int(smp.n_accept_per_chain.sum())
+                dt = timed(lambda: smp._run_device(Tb, None), 2)
+                acc = (int(smp.n_accept_per_chain.sum()) - a0) / (3 * Tb * Nb)
+                print(json.dumps({"case": name, "sampler": tag, "path": smp.path, "chains": Nb, "transitions": Tb,
+                                  "samples_per_s": Nb * Tb / dt, "ms": dt * 1e3, "acceptance": acc}), flush=True)
+            xg = torch.as_tensor(gs.sample_sphere(d - 1, min(n_lp, 1 << 20), seed=3), dtype=torch.float32).to(dev)
+            dt = timed(lambda: pdf.gradient(xg), 3)
+            print(json.dumps({"case": name, "op": "gradient fp32", "points": len(xg), "points_per_s": len(xg) / dt, "ms": dt * 1e3}), flush=True)
         # standalone batched log_prob (fp32): algorithmic bytes = (d + 1) * 4 per point
         x = torch.as_tensor(gs.sample_sphere(d - 1, n_lp, seed=2), dtype=torch.float32).to(dev)
         dt = timed(lambda: pdf.log_prob(x), 5)

@@ -362,6 +362,8 @@ def golden_api_surface():
     items = {
         "ShrinkageSphericalSliceSampler": mcmc.ShrinkageSphericalSliceSampler,
         "RejectionSphericalSliceSampler": mcmc.RejectionSphericalSliceSampler,
+        "MetropolisHastings": mcmc.MetropolisHastings, "IndependenceSampler": mcmc.IndependenceSampler,
+        "MixtureRWMHIndependenceSampler": mcmc.MixtureRWMHIndependenceSampler, "SphericalHMC": mcmc.SphericalHMC,
         "VonMisesFisher": distributions.VonMisesFisher, "MixtureModel": distributions.MixtureModel,
         "Bingham": distributions.Bingham, "BinghamFisher": distributions.BinghamFisher,
         "CurvedVonMisesFisher": distributions.CurvedVonMisesFisher,
@@ -371,7 +373,7 @@ def golden_api_surface():
     surface = {"classes": {}, "functions": {}}
     for name, cls in items.items():
         entry = {"init": params(cls.__init__)}
-        for meth in ("sample", "log_prob", "run", "find_nearest", "transform_positions"):
+        for meth in ("sample", "log_prob", "gradient", "run", "run_rwmh", "run_hmc", "reset", "find_nearest", "transform_positions"):
             if hasattr(cls, meth):
                 fn = getattr(cls, meth)
                 entry[meth] = params(getattr(fn, "__wrapped__", fn))
@@ -380,11 +382,14 @@ def golden_api_surface():
                      "brownian_curve": spherical_curve.brownian_curve, "sample_sphere": sphere.sample_sphere,
                      "radial_projection": sphere.radial_projection, "orthogonal_projection": sphere.orthogonal_projection,
                      "spherical_projection": sphere.spherical_projection, "sample_subsphere": sphere.sample_subsphere,
-                     "distance": sphere.distance, "quat2matrix": pointcloud.quat2matrix}.items():
+                     "distance": sphere.distance, "quat2matrix": pointcloud.quat2matrix,
+                     "tessellate_rotations": __import__("geosss.sphere_tesselation", fromlist=["x"]).tessellate_rotations}.items():
         surface["functions"][name] = params(fn)
     surface["attributes"] = {"Bingham": ["A", "v", "U", "d", "mode", "max_log_prob"], "MixtureModel": ["pdfs", "weights"],
                              "VonMisesFisher": ["mu", "d", "kappa", "mode", "max_log_prob"], "CurvedVonMisesFisher": ["curve", "kappa", "d"],
-                             "sampler": ["state", "rng", "target", "n_reject"]}
+                             "sampler": ["state", "rng", "target", "n_reject"],
+                             "MetropolisHastings": ["state", "rng", "target", "n_accept", "stepsize"],
+                             "MixtureRWMHIndependenceSampler": ["alpha", "rwmh_counter", "indep_counter"], "SphericalHMC": ["n_steps"]}
     with open(os.path.join(OUT, "api_surface.json"), "w") as f:
         json.dump(surface, f, indent=1, sort_keys=True)
     print("api_surface.json written")

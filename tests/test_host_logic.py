@@ -141,6 +141,11 @@ def test_public_surface_is_a_superset_of_the_reference(golden):
     assert all(hasattr(mix.pdfs[0], a) for a in ref["attributes"]["VonMisesFisher"])
     smp = gs.ShrinkageSphericalSliceSampler(mix, np.array([1.0, 0, 0]), 1)
     assert all(hasattr(smp, a) for a in ref["attributes"]["sampler"])
+    x0 = np.array([1.0, 0, 0])
+    assert all(hasattr(gs.MetropolisHastings(mix, x0, 1), a) for a in ref["attributes"]["MetropolisHastings"])
+    assert all(hasattr(gs.MixtureRWMHIndependenceSampler(mix, x0, 1), a) for a in ref["attributes"]["MixtureRWMHIndependenceSampler"])
+    hmc = gs.SphericalHMC(mix, x0, 1)
+    assert all(hasattr(hmc, a) for a in ref["attributes"]["SphericalHMC"]) and hmc.state.shape == (6,)
 
 
 def test_numa_binding_helper_is_harmless_without_a_gpu():
