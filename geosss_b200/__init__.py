@@ -29,6 +29,7 @@ from .mcmc import (  # noqa: F401
     determine_burnin,
 )
 from .pointcloud import PointCloud, matrix2quat, quat2matrix  # noqa: F401
+from .rand import bfind, sample_bingham, sample_bingham_2d, sample_bingham_3d, sample_vMF  # noqa: F401
 from .registration import CoherentPointDrift, GaussianMixtureModel  # noqa: F401
 from .sphere import (  # noqa: F401
     distance,

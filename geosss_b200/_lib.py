@@ -49,6 +49,8 @@ SIGNATURES = {
     "geosss_sampler_mh_momenta_out": (_i, [_p, _p]),
     "geosss_sampler_mh_get_host": (_i, [_p, _pd, _p, _pd]),
     "geosss_gradient": (_i, [_p, _i, _p, _p, _i64, _p]),
+    "geosss_exact_vmf": (_i, [_i, _pd, _u64, _u64, _i, _p, _i64, C.POINTER(_u64), _p]),
+    "geosss_exact_bingham": (_i, [_i, _pd, _pd, _dbl, _dbl, _u64, _u64, _i, _p, _i64, _i, C.POINTER(_u64), _p]),
     "geosss_diag_path_stats": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _i, _p, _p]),
     "geosss_sample_host": (_i, [_p, _i, _i, _i, _i64, _pd, _u64, _u64, _i64, _i64, _p, _p]),
 }

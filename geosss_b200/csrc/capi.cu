@@ -17,6 +17,7 @@
 #include "kernels_logp_fast.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_literal.cuh"
+#include "kernels_exact.cuh"
 #include "kernels_mh.cuh"
 
 using namespace geosss;
@@ -845,6 +846,79 @@ extern "C" int geosss_gradient(geosss_target_t t, int dtype, const void* x, void
     if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "gradient: dtype must be f32 or f64");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dtype == GEOSSS_F64 ? gradient_any<double>(t, x, out, N, st) : gradient_any<float>(t, x, out, N, st);
+}
+
+// ------------------------------------------------------------------ exact i.i.d. samplers (geosss/rand.py)
+namespace {
+struct DevBuf {  // small scratch freed on scope exit (after the stream has been synchronised)
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" int geosss_exact_vmf(int d, const double* mu_host, uint64_t seed, uint64_t offset, int dtype, void* out, int64_t N,
+                                uint64_t* attempts_host, void* stream) {
+    if (d < 2 || !mu_host || N < 0 || (N > 0 && !out)) return fail(GEOSSS_E_INVALID, "exact_vmf: need d >= 2, mu and an output buffer");
+    if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "exact_vmf: dtype must be f32 or f64");
+    if (attempts_host) *attempts_host = 0;
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double kap = 0;
+    for (int j = 0; j < d; ++j) kap += mu_host[j] * mu_host[j];
+    kap = std::sqrt(kap);
+    const double p = d - 1;
+    ExactVmfArgs a{};
+    a.d = d; a.kappa = kap; a.max_attempts = 1 << 14;
+    a.b0 = (-2 * kap + std::sqrt(4 * kap * kap + p * p)) / p;  // rand.py:49-51
+    a.x0 = (1 - a.b0) / (1 + a.b0);
+    a.c = kap * a.x0 + p * std::log(1 - a.x0 * a.x0);
+    DevBuf mu, cnt;
+    CU(cudaMalloc(&mu.p, (size_t)d * sizeof(double)));
+    CU(cudaMalloc(&cnt.p, sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(mu.p, mu_host, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+    a.mu = static_cast<const double*>(mu.p);
+    auto* c = static_cast<unsigned long long*>(cnt.p);
+    const int rc = dtype == GEOSSS_F64 ? launch_exact_vmf<double>(a, seed, offset, static_cast<double*>(out), N, c, st)
+                                       : launch_exact_vmf<float>(a, seed, offset, static_cast<float*>(out), N, c, st);
+    if (rc) return fail(GEOSSS_E_CUDA, "exact_vmf: %s", cudaGetErrorString((cudaError_t)rc));
+    unsigned long long tried = 0;
+    CU(cudaMemcpyAsync(&tried, cnt.p, sizeof tried, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (attempts_host) *attempts_host = tried;
+    return 0;
+}
+
+extern "C" int geosss_exact_bingham(int d, const double* v_host, const double* U_host, double b, double log_m, uint64_t seed,
+                                    uint64_t offset, int dtype, void* out, int64_t N, int max_attempts, uint64_t* attempts_host,
+                                    void* stream) {
+    if (d < 2 || !v_host || N < 0 || (N > 0 && !out) || !(b > 0) || max_attempts < 1)
+        return fail(GEOSSS_E_INVALID, "exact_bingham: need d >= 2, eigenvalues, b > 0 and an output buffer");
+    if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "exact_bingham: dtype must be f32 or f64");
+    if (attempts_host) *attempts_host = 0;
+    if (N == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevBuf v, U, ws, cnt;
+    CU(cudaMalloc(&v.p, (size_t)d * sizeof(double)));
+    CU(cudaMalloc(&cnt.p, sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(v.p, v_host, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), st));
+    if (U_host) {
+        CU(cudaMalloc(&U.p, (size_t)d * d * sizeof(double)));
+        CU(cudaMalloc(&ws.p, (size_t)N * d * sizeof(double)));
+        CU(cudaMemcpyAsync(U.p, U_host, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    ExactBinghamArgs a{static_cast<const double*>(v.p), static_cast<const double*>(U.p), b, log_m, d, max_attempts};
+    auto* c = static_cast<unsigned long long*>(cnt.p);
+    const int rc = dtype == GEOSSS_F64
+                       ? launch_exact_bingham<double>(a, seed, offset, static_cast<double*>(out), static_cast<double*>(ws.p), N, c, st)
+                       : launch_exact_bingham<float>(a, seed, offset, static_cast<float*>(out), static_cast<double*>(ws.p), N, c, st);
+    if (rc) return fail(GEOSSS_E_CUDA, "exact_bingham: %s", cudaGetErrorString((cudaError_t)rc));
+    unsigned long long tried = 0;
+    CU(cudaMemcpyAsync(&tried, cnt.p, sizeof tried, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (attempts_host) *attempts_host = tried;
+    return 0;
 }
 
 // ------------------------------------------------------------------ diagnostics

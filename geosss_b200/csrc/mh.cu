@@ -4,6 +4,7 @@
 
 #include <type_traits>
 
+#include "kernels_exact.cuh"
 #include "kernels_mh.cuh"
 
 namespace geosss {
@@ -43,6 +44,23 @@ template <typename T, class P> int launch_grad(const P& p, const T* x, T* out, i
     }
     return (int)cudaGetLastError();
 }
+
+template <typename T> int launch_exact_vmf(const ExactVmfArgs& a, uint64_t seed, uint64_t offset, T* out, int64_t N, unsigned long long* attempts,
+                                           cudaStream_t st) {
+    k_exact_vmf<T><<<(unsigned)((N + LANE_BLOCK - 1) / LANE_BLOCK), LANE_BLOCK, 0, st>>>(a, seed, offset, out, N, attempts);
+    return (int)cudaGetLastError();
+}
+
+template <typename T> int launch_exact_bingham(const ExactBinghamArgs& a, uint64_t seed, uint64_t offset, T* out, double* ws, int64_t N,
+                                               unsigned long long* attempts, cudaStream_t st) {
+    k_exact_bingham<T><<<(unsigned)((N + LANE_BLOCK - 1) / LANE_BLOCK), LANE_BLOCK, 0, st>>>(a, seed, offset, out, ws, N, attempts);
+    return (int)cudaGetLastError();
+}
+
+template int launch_exact_vmf<float>(const ExactVmfArgs&, uint64_t, uint64_t, float*, int64_t, unsigned long long*, cudaStream_t);
+template int launch_exact_vmf<double>(const ExactVmfArgs&, uint64_t, uint64_t, double*, int64_t, unsigned long long*, cudaStream_t);
+template int launch_exact_bingham<float>(const ExactBinghamArgs&, uint64_t, uint64_t, float*, double*, int64_t, unsigned long long*, cudaStream_t);
+template int launch_exact_bingham<double>(const ExactBinghamArgs&, uint64_t, uint64_t, double*, double*, int64_t, unsigned long long*, cudaStream_t);
 
 #define GEOSSS_MH_INSTANCES(T)                                                                        \
     template int launch_mh<T, VmfMixP<T>>(const VmfMixP<T>&, int, bool, const RunArgs&, cudaStream_t);   \

@@ -174,6 +174,21 @@ int geosss_sampler_mh_get_host(geosss_sampler_t s, double* stepsize_host, uint64
  * registration.py:55-59 with pointcloud.py:135-203).  x, out: (N, d) device, `dtype`. */
 int geosss_gradient(geosss_target_t t, int dtype, const void* x, void* out, int64_t N, void* stream);
 
+/* ---- exact i.i.d. samplers used as ground truth ("next" row f4; geosss/rand.py) ----------------- */
+/* Both are synchronous on `stream` (they return the number of proposals tried).  Draw i uses the Philox
+ * stream (seed, offset + i), so results do not depend on how a request is split into calls or GPUs. */
+
+/* sample_vMF (rand.py:31-66, Wood 1994): N draws from vMF(mu), mu: (d) host doubles; out: (N, d) device. */
+int geosss_exact_vmf(int d, const double* mu_host, uint64_t seed, uint64_t offset, int dtype, void* out, int64_t N,
+                     uint64_t* attempts_host, void* stream);
+/* sample_bingham (rand.py:132-193, Kent, Ganeiber & Mardia): rejection from the angular central Gaussian
+ * envelope.  v_host: (d) eigenvalues of -A shifted so the smallest is 0; U_host: (d, d) row-major matrix with
+ * the eigenvectors in its columns, or NULL when A was given by its diagonal; b: root of sum 1/(b + 2 v_j) = 1;
+ * log_m: log of the envelope bound.  max_attempts per draw (upstream: n_iter). */
+int geosss_exact_bingham(int d, const double* v_host, const double* U_host, double b, double log_m, uint64_t seed,
+                         uint64_t offset, int dtype, void* out, int64_t N, int max_attempts, uint64_t* attempts_host,
+                         void* stream);
+
 /* ---- diagnostics ("next" row of the scope table: ESS half of the metric) --------------------- */
 
 /* Partial sums for the multi-chain ESS of f(x) = x . direction over samples in STEP_MAJOR

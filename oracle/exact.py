@@ -55,3 +55,41 @@ def wood_vmf_mixture(mus, weights, size, seed=None):
         if idx.size:
             out[idx] = wood_vmf(mus[k], idx.size, seed=gen.integers(2**63))
     return out
+
+
+def kent_envelope(A):
+    """Parameters of the angular-central-Gaussian envelope of Kent, Ganeiber & Mardia for
+    Bingham(A) ~ exp(x^T A x) (geosss/rand.py:132-158): eigenvalues of -A shifted to start at 0,
+    eigenvectors, the root b of sum_j 1 / (b + 2 v_j) = 1 and the log of the bound M."""
+    from scipy.optimize import brentq
+    A = np.asarray(A, dtype=float)
+    if A.ndim == 1:
+        v, U = -A, None
+    else:
+        v, U = np.linalg.eigh(-A)
+    v = v - np.min(v)
+    d = len(v)
+    b = float(d) if np.allclose(v, 0.0) else brentq(lambda t: 1 - np.sum(1 / (t + 2 * v)), 1, d)
+    log_m = -(d - b) / 2 + (d / 2) * np.log(d / b)
+    return v, U, b, log_m
+
+
+def kent_bingham(A, size, seed=None, return_efficiency=False):
+    """size i.i.d. draws from Bingham(A) by ACG rejection (geosss/rand.py:145-193), seeded."""
+    gen = np.random.default_rng(seed)
+    v, U, b, log_m = kent_envelope(A)
+    d = len(v)
+    out, tried = [], 0
+    need = size
+    while need > 0:
+        x = gen.standard_normal((need, d)) / np.sqrt(1 + 2 * v / b)
+        x /= np.linalg.norm(x, axis=-1)[:, None]
+        u = np.sum(np.square(x) * v, axis=-1)
+        ok = np.log(gen.random(need)) < -u + (d / 2) * np.log(1 + 2 * u / b) - log_m
+        out.append(x[ok])
+        tried += need
+        need -= int(ok.sum())
+    x = np.concatenate(out, 0)[:size]
+    if U is not None:
+        x = x @ U.T
+    return (x, size / tried) if return_efficiency else x

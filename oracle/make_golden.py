@@ -338,6 +338,27 @@ def matrix2quat_ref(tgt, src):
     return matrix2quat(np.load(os.path.join(REF, "data", "protein_registration.npz"))["rotation"])
 
 
+def golden_exact():
+    """Moments of the reference's exact samplers (geosss/rand.py: Wood vMF, Kent Bingham) under a fixed
+    global numpy seed: the statistical pin for the device versions."""
+    from geosss.rand import sample_bingham, sample_bingham_2d, sample_bingham_3d, sample_vMF
+    np.random.seed(20240607)
+    out = {}
+    modes = gs.sample_sphere(9, 5, seed=1234)
+    for tag, mu in (("d10", 40.0 * modes[0]), ("d3", 80.0 * README_MUS[0]), ("d2", np.array([3.0, -4.0]))):
+        x = sample_vMF(gs.VonMisesFisher(mu), 20000)
+        out[f"vmf_{tag}_mu"], out[f"vmf_{tag}_mean"], out[f"vmf_{tag}_n"] = mu, x.mean(0), len(x)
+        out[f"vmf_{tag}_cos_quantiles"] = np.quantile(x @ mu / np.linalg.norm(mu), [0.05, 0.25, 0.5, 0.75, 0.95])
+    for tag, pdf in (("d10", gs.random_bingham(10, 30, 0, False, 6982)), ("d50", gs.random_bingham(50, 300, 0, True, 6982)),
+                     ("d3", gs.random_bingham(3, 12, 0, False, 11)), ("d2", gs.random_bingham(2, 5, 0, False, 12))):
+        x, eff = sample_bingham(pdf.A, 200000, return_efficiency=True)
+        out[f"bing_{tag}_A"], out[f"bing_{tag}_second"], out[f"bing_{tag}_eff"], out[f"bing_{tag}_n"] = pdf.A, x.T @ x / len(x), eff, len(x)
+    x2 = sample_bingham_2d(gs.random_bingham(2, 5, 0, False, 12), 200000)
+    x3 = sample_bingham_3d(gs.random_bingham(3, 12, 0, False, 11), 20000)
+    out["bing_d2_second_2d"], out["bing_d3_second_gibbs"] = x2.T @ x2 / len(x2), x3.T @ x3 / len(x3)
+    save("exact", **out)
+
+
 def golden_tessellation(tgt, src):
     """600-cell rotation grid (one subdivision) and the reference CPD log-probabilities on it: the
     'systematic search' of scripts/protein_reg3d3d.py:629-648 at a size that runs in seconds."""
@@ -403,6 +424,8 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "baselines":
         d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
         golden_baselines(d["target"], d["source"])
+    elif len(sys.argv) > 1 and sys.argv[1] == "exact":
+        golden_exact()
     elif len(sys.argv) > 1 and sys.argv[1] == "tessellation":
         d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
         golden_tessellation(d["target"], d["source"])
@@ -412,6 +435,7 @@ if __name__ == "__main__":
             golden_trajectories(t, s)
             golden_misc()
             golden_pathstats()
+            golden_exact()
             golden_baselines(t, s)
             golden_tessellation(t, s)
         golden_api_surface()

@@ -225,3 +225,19 @@ def test_pathstats_oracle_matches_reference_expressions(golden):
         assert np.array_equal(pathstats.geodesic_steps(x), want)
     for b, hop in zip(g["bingham_samples"], g["bingham_hop"]):
         assert pathstats.hops(b, g["bingham_mode"]) / (len(b) - 1) == hop
+
+
+def test_exact_samplers_oracle_matches_reference_moments(golden):
+    """oracle/exact.py (Wood vMF, Kent Bingham) vs moments of the reference's own exact samplers
+    (geosss/rand.py run under a fixed numpy seed).  5-sigma bounds: both sides are Monte-Carlo estimates."""
+    from oracle import exact
+    g = golden("exact")
+    for tag in ("d10", "d3", "d2"):
+        mu = g[f"vmf_{tag}_mu"]
+        x = exact.wood_vmf(mu, 100000, seed=1)
+        se = np.sqrt(1.0 / int(g[f"vmf_{tag}_n"]) + 1e-5)
+        assert np.max(np.abs(x.mean(0) - g[f"vmf_{tag}_mean"])) < 5 * se
+    for tag in ("d10", "d3", "d2"):
+        x, eff = exact.kent_bingham(g[f"bing_{tag}_A"], 100000, seed=2, return_efficiency=True)
+        assert np.max(np.abs(x.T @ x / len(x) - g[f"bing_{tag}_second"])) < 5 * np.sqrt(1.5e-5)
+        assert abs(eff - g[f"bing_{tag}_eff"]) < 0.06
