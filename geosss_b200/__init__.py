@@ -28,7 +28,14 @@ from .mcmc import (  # noqa: F401
     ShrinkageSphericalSliceSampler,
     determine_burnin,
 )
-from .pointcloud import PointCloud, matrix2quat, quat2matrix  # noqa: F401
+from .pointcloud import (  # noqa: F401
+    PointCloud,
+    RotationMatrix,
+    RotationProjection,
+    jacobian_rotation_matrix,
+    matrix2quat,
+    quat2matrix,
+)
 from .rand import bfind, sample_bingham, sample_bingham_2d, sample_bingham_3d, sample_vMF  # noqa: F401
 from .registration import CoherentPointDrift, GaussianMixtureModel  # noqa: F401
 from .sphere import (  # noqa: F401

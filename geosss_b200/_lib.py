@@ -29,6 +29,8 @@ SIGNATURES = {
     "geosss_target_create_bingham": (_i, [_i, _pd, _pd, C.POINTER(_p)]),
     "geosss_target_create_curved_vmf": (_i, [_i, _i, _pd, _dbl, C.POINTER(_p)]),
     "geosss_target_create_cpd": (_i, [_i, _i, _pd, _pd, _pd, _pd, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_p)]),
+    "geosss_target_create_cpd_projected": (_i, [_i, _i, _pd, _pd, _pd, _pd, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_p)]),
+    "geosss_target_cpd_set_translation": (_i, [_p, _pd]),
     "geosss_target_dim": (_i, [_p]),
     "geosss_target_destroy": (_i, [_p]),
     "geosss_log_prob": (_i, [_p, _i, _i, _p, _p, _i64, _p]),

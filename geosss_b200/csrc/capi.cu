@@ -82,6 +82,8 @@ struct geosss_target {
     // CPD
     int nt = 0, ns = 0, k = 0, outlier = 1;
     double sigma2 = 1, log_const = 0, log_outlier = 0, beta = 1, max_logw = 0;
+    double shift[3] = {0, 0, 0};
+    int dim = 3;
     Arr tgt, wt, src, logws;
 
     template <typename T> VmfMixP<T> vmf() const { return {mu.get<T>(), logw.get<T>(), logi0.get<T>(), K, d, single}; }
@@ -91,7 +93,7 @@ struct geosss_target {
     }
     template <typename T> CpdP<T> cpd() const {
         return {tgt.get<T>(), wt.get<T>(), src.get<T>(), logws.get<T>(), (T)sigma2, (T)log_const,
-                (T)log_outlier, (T)beta, nt, ns, k, outlier};
+                (T)log_outlier, (T)beta, nt, ns, k, outlier, {(T)shift[0], (T)shift[1], (T)shift[2]}, dim};
     }
     void release() {
         for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
@@ -298,22 +300,29 @@ extern "C" int geosss_target_create_curved_vmf(int d, int n_knots, const double*
     return 0;
 }
 
-extern "C" int geosss_target_create_cpd(int n_t, int n_s, const double* target, const double* w_t, const double* source,
-                                        const double* w_s, double sigma, double omega, double beta, int k, int outlier,
-                                        geosss_target_t* out) {
-    if (!out || !target || !source || n_t < 1 || n_s < 1) return fail(GEOSSS_E_INVALID, "cpd: need target and source clouds");
+static int create_cpd(int dim, int n_t, int n_s, const double* target_in, const double* w_t, const double* source,
+                      const double* w_s, double sigma, double omega, double beta, int k, int outlier, geosss_target_t* out) {
+    if (!out || !target_in || !source || n_t < 1 || n_s < 1) return fail(GEOSSS_E_INVALID, "cpd: need target and source clouds");
+    // 2-D targets are stored as (x, y, 0) rows
+    std::vector<double> padded;
+    const double* target = target_in;
+    if (dim == 2) {
+        padded.assign((size_t)n_t * 3, 0.0);
+        for (int l = 0; l < n_t; ++l) { padded[(size_t)l * 3] = target_in[(size_t)l * 2]; padded[(size_t)l * 3 + 1] = target_in[(size_t)l * 2 + 1]; }
+        target = padded.data();
+    }
     if (k > 0 && k < n_s && k > CPD_KMAX) return fail(GEOSSS_E_UNSUPPORTED, "cpd: k-nearest truncation supports k <= %d", CPD_KMAX);
     if (!(sigma > 0)) return fail(GEOSSS_E_INVALID, "cpd: sigma must be positive");
     auto* t = new (std::nothrow) geosss_target();
     if (!t) return fail(GEOSSS_E_NOMEM, "out of host memory");
     t->kind = TGT_CPD; t->d = 4; t->nt = n_t; t->ns = n_s; t->k = k; t->outlier = outlier ? 1 : 0;
-    t->sigma2 = sigma * sigma; t->beta = beta;
-    const double D = 3.0;
+    t->sigma2 = sigma * sigma; t->beta = beta; t->dim = dim;
+    const double D = (double)dim;  // target.dim (registration.py:116, 213)
     const double gauss = D / 2 * std::log(2 * M_PI * sigma * sigma);
     if (outlier) {
         // registration.py:205-215, 237-238
         double vol = 0;
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < dim; ++a) {
             double lo = target[a], hi = target[a];
             for (int l = 1; l < n_t; ++l) { double v = target[(size_t)l * 3 + a]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
             vol += std::log(hi - lo);
@@ -335,6 +344,24 @@ extern "C" int geosss_target_create_cpd(int n_t, int n_s, const double* target, 
     if (!rc) rc = t->logws.upload(lws.data(), n_s);
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
+    return 0;
+}
+
+extern "C" int geosss_target_create_cpd(int n_t, int n_s, const double* target, const double* w_t, const double* source,
+                                        const double* w_s, double sigma, double omega, double beta, int k, int outlier,
+                                        geosss_target_t* out) {
+    return create_cpd(3, n_t, n_s, target, w_t, source, w_s, sigma, omega, beta, k, outlier, out);
+}
+
+extern "C" int geosss_target_create_cpd_projected(int n_t, int n_s, const double* target_xy, const double* w_t, const double* source,
+                                                  const double* w_s, double sigma, double omega, double beta, int k, int outlier,
+                                                  geosss_target_t* out) {
+    return create_cpd(2, n_t, n_s, target_xy, w_t, source, w_s, sigma, omega, beta, k, outlier, out);
+}
+
+extern "C" int geosss_target_cpd_set_translation(geosss_target_t t, const double* translation) {
+    if (!t || t->kind != TGT_CPD) return fail(GEOSSS_E_INVALID, "cpd_set_translation: not a registration target");
+    for (int a = 0; a < 3; ++a) t->shift[a] = (translation && a < t->dim) ? translation[a] : 0.0;
     return 0;
 }
 

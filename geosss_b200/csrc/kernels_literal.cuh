@@ -223,9 +223,9 @@ struct CpdWarpLogPFast {
         for (int k = lane; k < p.ns; k += 32) {  // moved_k = R s_k (pointcloud.py:258-262); w stays
             const float s0 = p.src[3 * k], s1 = p.src[3 * k + 1], s2 = p.src[3 * k + 2];
             float* m = reinterpret_cast<float*>(mv + k);
-            m[0] = s0 * R[0] + s1 * R[1] + s2 * R[2];
-            m[1] = s0 * R[3] + s1 * R[4] + s2 * R[5];
-            m[2] = s0 * R[6] + s1 * R[7] + s2 * R[8];
+            m[0] = (s0 * R[0] + s1 * R[1] + s2 * R[2]) + p.shift[0];
+            m[1] = (s0 * R[3] + s1 * R[4] + s2 * R[5]) + p.shift[1];
+            m[2] = p.dim == 2 ? 0.0f : (s0 * R[6] + s1 * R[7] + s2 * R[8]) + p.shift[2];
         }
         __syncwarp();
         double acc = 0.0;

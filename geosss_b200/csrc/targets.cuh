@@ -176,6 +176,8 @@ template <typename T> struct CpdP {
     const T* logws;  // (ns) log source weights
     T sigma2, log_const, log_outlier, beta;
     int nt, ns, k, outlier;  // k <= 0 or k >= ns: all source points; outlier 0: GMM parent
+    T shift[3];              // translation added after the rotation (pointcloud.py:260-264)
+    int dim;                 // 3, or 2: rotate then drop z (RotationProjection, pointcloud.py:273-293)
 };
 
 // scipy Rotation.from_quat(q).as_matrix(): scalar-last, q normalised first (pointcloud.py:115)
@@ -187,13 +189,15 @@ template <typename T> GEOSSS_HD void quat_to_matrix(T qx, T qy, T qz, T qw, T R[
     R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
 }
 
-// moved_k = R s_k  (positions @ R.T, pointcloud.py:258-262), k = first, first+step, ...
+// moved_k = R s_k + t  (positions @ R.T + translation, pointcloud.py:258-264), k = first, first+step, ...
+// 2-D targets: positions @ R[:-1].T + t (pointcloud.py:288-293); z is held at 0 like the zero-padded
+// target rows, so the same 3-D distance code serves both.
 template <typename T> GEOSSS_HD void cpd_move_source(const CpdP<T>& p, const T R[9], T* moved, int first, int step) {
     for (int k = first; k < p.ns; k += step) {
         T s0 = p.src[3 * k], s1 = p.src[3 * k + 1], s2 = p.src[3 * k + 2];
-        moved[3 * k]     = s0 * R[0] + s1 * R[1] + s2 * R[2];
-        moved[3 * k + 1] = s0 * R[3] + s1 * R[4] + s2 * R[5];
-        moved[3 * k + 2] = s0 * R[6] + s1 * R[7] + s2 * R[8];
+        moved[3 * k]     = (s0 * R[0] + s1 * R[1] + s2 * R[2]) + p.shift[0];
+        moved[3 * k + 1] = (s0 * R[3] + s1 * R[4] + s2 * R[5]) + p.shift[1];
+        moved[3 * k + 2] = p.dim == 2 ? T(0) : (s0 * R[6] + s1 * R[7] + s2 * R[8]) + p.shift[2];
     }
 }
 

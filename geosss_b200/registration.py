@@ -1,12 +1,15 @@
 """
-Rigid 3D-3D registration likelihoods on S^3 (geosss/registration.py:19-259).
+Rigid 3D-3D and 3D-2D registration likelihoods on S^3 (geosss/registration.py:19-293).
 
 ``log_prob`` takes a unit quaternion (x, y, z, w) -- or rows of them, or a 3x3 rotation
 matrix -- and evaluates the coherent-point-drift log-likelihood on the GPU: the source cloud
 is rotated, every target point sees a Gaussian mixture over its k nearest rotated source
 points plus (CPD) a uniform outlier term.  The reference rebuilds a KDTree per call; the
 kernels evaluate all pairs and select the k nearest per row exactly (csrc/targets.cuh).
-Translations and the 3D->2D projection model are outside this engine's scope.
+A 2-D target with a ``RotationProjection`` source scores the rotated source projected onto its
+first two coordinates (pointcloud.py:273-293).  ``translation`` is a fixed shift added after the
+rotation, per call as upstream or persistently through the ``translation`` attribute (which the
+samplers then see).
 """
 
 import ctypes as C
@@ -16,13 +19,34 @@ import torch
 
 from . import _lib
 from .distributions import Distribution
-from .pointcloud import PointCloud, matrix2quat
+from .pointcloud import PointCloud, RotationProjection, matrix2quat
 from .utils import counted
 
 
 class Registration(Distribution):
     beta = 1.0
     d = 4
+    translation = None  # fixed shift applied after the rotation; None = no shift
+
+    def _handle(self, dev):
+        h = super()._handle(dev)
+        t = None if self.translation is None else np.ascontiguousarray(self.translation, dtype=float)
+        if t is not None and t.shape != (self.target.dim,):
+            raise ValueError(f"translation must have shape ({self.target.dim},)")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().geosss_target_cpd_set_translation(h, None if t is None else _lib.dptr(t)))
+        return h
+
+    def _shifted(self, translation, rotation, gradient):
+        """Evaluate with the per-call ``translation`` of upstream's signature (registration.py:47-59)."""
+        if translation is None:
+            return self._evaluate(self._quaternions(rotation), gradient=gradient)
+        keep = self.translation
+        self.translation = translation
+        try:
+            return self._evaluate(self._quaternions(rotation), gradient=gradient)
+        finally:
+            self.translation = keep
 
     def _quaternions(self, rotation):
         if isinstance(rotation, torch.Tensor):
@@ -44,8 +68,10 @@ class GaussianMixtureModel(Registration):
                  dense: bool = False):
         """``dense=True`` sums every source point instead of the k nearest (an extension: it is what the
         float32 throughput kernels evaluate; at the shipped sigma = 1 it equals k = 20 to 5e-12, tested)."""
-        if target.dim != 3 or source.dim != 3:
-            raise NotImplementedError("the device engine handles 3D-3D registration")
+        if source.dim != 3 or target.dim not in (2, 3):
+            raise NotImplementedError("the device engine handles 3D-3D and 3D-2D registration")
+        if (target.dim == 2) != isinstance(source, RotationProjection):
+            raise ValueError("a 2-D target needs a RotationProjection source, a 3-D target a plain PointCloud")
         self.target, self.source = target, source
         self.sigma, self.k, self.beta = float(sigma), int(k), float(beta)
         self.dense = bool(dense)
@@ -57,23 +83,19 @@ class GaussianMixtureModel(Registration):
         wt = np.ascontiguousarray(self.target.weights, dtype=float)
         ws = np.ascontiguousarray(self.source.weights, dtype=float)
         h = C.c_void_p()
-        _lib.check(lib.geosss_target_create_cpd(len(tgt), len(src), _lib.dptr(tgt), _lib.dptr(wt), _lib.dptr(src),
-                                                _lib.dptr(ws), self.sigma, self.omega, self.beta,
-                                                0 if self.dense else self.k, self._outlier, C.byref(h)))
+        create = lib.geosss_target_create_cpd if self.target.dim == 3 else lib.geosss_target_create_cpd_projected
+        _lib.check(create(len(tgt), len(src), _lib.dptr(tgt), _lib.dptr(wt), _lib.dptr(src), _lib.dptr(ws), self.sigma,
+                          self.omega, self.beta, 0 if self.dense else self.k, self._outlier, C.byref(h)))
         return h
 
     @counted
     def log_prob(self, rotation, translation=None):
-        if translation is not None:
-            raise NotImplementedError("translations are not sampled by the reference's experiments")
-        return self._evaluate(self._quaternions(rotation))
+        return self._shifted(translation, rotation, False)
 
     @counted
     def gradient(self, rotation, translation=None):
         """d log_prob / d q for scalar-last quaternions (registration.py:55-59, pointcloud.py:135-203)."""
-        if translation is not None:
-            raise NotImplementedError("translations are not sampled by the reference's experiments")
-        return self._evaluate(self._quaternions(rotation), gradient=True)
+        return self._shifted(translation, rotation, True)
 
 
 class CoherentPointDrift(GaussianMixtureModel):
@@ -88,13 +110,9 @@ class CoherentPointDrift(GaussianMixtureModel):
 
     @counted
     def log_prob(self, rotation, translation=None):
-        if translation is not None:
-            raise NotImplementedError("translations are not sampled by the reference's experiments")
-        return self._evaluate(self._quaternions(rotation))
+        return self._shifted(translation, rotation, False)
 
     @counted
     def gradient(self, rotation, translation=None):
         """d log_prob / d q for scalar-last quaternions (registration.py:55-59, pointcloud.py:135-203)."""
-        if translation is not None:
-            raise NotImplementedError("translations are not sampled by the reference's experiments")
-        return self._evaluate(self._quaternions(rotation), gradient=True)
+        return self._shifted(translation, rotation, True)

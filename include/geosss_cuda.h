@@ -91,6 +91,15 @@ int geosss_target_create_curved_vmf(int d, int n_knots, const double* knots, dou
 int geosss_target_create_cpd(int n_t, int n_s, const double* target, const double* w_t,
                              const double* source, const double* w_s, double sigma, double omega,
                              double beta, int k, int outlier, geosss_target_t* out);
+/* 3D -> 2D registration (source = RotationProjection, geosss/pointcloud.py:273-293): target_xy: (n_t, 2);
+ * the rotated source is projected onto its first two coordinates; constants use target.dim = 2. */
+int geosss_target_create_cpd_projected(int n_t, int n_s, const double* target_xy, const double* w_t,
+                                       const double* source, const double* w_s, double sigma, double omega,
+                                       double beta, int k, int outlier, geosss_target_t* out);
+/* Fixed translation added to the rotated (projected) source in later log_prob / gradient / sampler calls:
+ * (3) or (2) host doubles, NULL = none (the `translation` argument of Registration.log_prob / gradient,
+ * registration.py:47-59; pointcloud.py:260-264). */
+int geosss_target_cpd_set_translation(geosss_target_t t, const double* translation);
 int geosss_target_dim(geosss_target_t t); /* ambient dimension d of the state */
 int geosss_target_destroy(geosss_target_t t);
 

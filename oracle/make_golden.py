@@ -359,6 +359,31 @@ def golden_exact():
     save("exact", **out)
 
 
+def golden_projection():
+    """3D-3D with a translation and 3D-2D (RotationProjection) registration on the toy cube of the
+    reference's tests/test_cpd.py: log_prob and gradient at several rotations, omega in {0, 0.2, 0.4}."""
+    from geosss.pointcloud import RotationMatrix, RotationProjection, matrix2quat
+    gen = np.random.default_rng(77)
+    cube = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=float)
+    R_true = RotationMatrix().rotation3d(euler_angles=np.array([0.2, 0.3, 0.1]))
+    q = np.vstack([matrix2quat(R_true), points(4, 9, 35, scale_some=False)])
+    out = {"cube": cube, "R_true": R_true, "q": q}
+    for tag, src, t_true, D in (("p3", PointCloud(cube), np.array([0.5, -0.3, 0.2]), 3), ("p2", RotationProjection(cube), np.array([0.5, -0.3]), 2)):
+        tgt = src.transform_positions(R_true, t_true) + gen.normal(0, 0.05, (8, D))
+        tgt = np.vstack([tgt, gen.uniform(-3, 3, (4, D))])
+        out[f"{tag}_target"], out[f"{tag}_t"] = tgt, t_true
+        for om in (0, 2, 4):
+            cpd = CoherentPointDrift(PointCloud(tgt), src, sigma=0.5, k=8, beta=1.0, omega=om / 10)
+            out[f"{tag}_logp_om{om}"] = np.array([cpd.log_prob(row, t_true) for row in q])
+            out[f"{tag}_grad_om{om}"] = np.array([cpd.gradient(row, t_true) for row in q])
+            out[f"{tag}_logp0_om{om}"] = np.array([cpd.log_prob(row) for row in q])
+        out[f"{tag}_logp_matrix"] = CoherentPointDrift(PointCloud(tgt), src, sigma=0.5, k=8, omega=0.2).log_prob(R_true, t_true)
+        gmm = GaussianMixtureModel(PointCloud(tgt), src, sigma=0.5, k=8)
+        out[f"{tag}_logp_gmm"] = np.array([gmm.log_prob(row, t_true) for row in q])
+        out[f"{tag}_grad_gmm"] = np.array([gmm.gradient(row, t_true) for row in q])
+    save("projection", **out)
+
+
 def golden_tessellation(tgt, src):
     """600-cell rotation grid (one subdivision) and the reference CPD log-probabilities on it: the
     'systematic search' of scripts/protein_reg3d3d.py:629-648 at a size that runs in seconds."""
@@ -424,6 +449,8 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "baselines":
         d = np.load(os.path.join(REF, "data", "protein_registration.npz"))
         golden_baselines(d["target"], d["source"])
+    elif len(sys.argv) > 1 and sys.argv[1] == "projection":
+        golden_projection()
     elif len(sys.argv) > 1 and sys.argv[1] == "exact":
         golden_exact()
     elif len(sys.argv) > 1 and sys.argv[1] == "tessellation":
@@ -436,6 +463,7 @@ if __name__ == "__main__":
             golden_misc()
             golden_pathstats()
             golden_exact()
+            golden_projection()
             golden_baselines(t, s)
             golden_tessellation(t, s)
         golden_api_surface()

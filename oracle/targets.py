@@ -225,7 +225,10 @@ class CPD:
     """
 
     def __init__(self, target, source, sigma=1.0, k=20, beta=1.0, omega=0.0,
-                 target_weights=None, source_weights=None):
+                 target_weights=None, source_weights=None, translation=None):
+        # a 2-D target scores the rotated source projected onto xy (RotationProjection,
+        # pointcloud.py:273-293); translation: fixed shift after the rotation (pointcloud.py:260-264)
+        self.translation = None if translation is None else np.asarray(translation, dtype=float)
         self.target = np.asarray(target, dtype=float)
         self.source = np.asarray(source, dtype=float)
         self.w_t = (np.ones(len(self.target)) if target_weights is None
@@ -256,8 +259,13 @@ class CPD:
             dist, ind = dist[:, None], ind[:, None]
         return dist, ind
 
+    def _move(self, R):
+        D = self.target.shape[1]
+        moved = self.source @ R[:D].T
+        return moved if self.translation is None else moved + self.translation
+
     def log_prob_R(self, R):
-        moved = self.source @ R.T
+        moved = self._move(R)
         dist, ind = self._neighbours(moved)
         log_phi = -0.5 * dist**2 / self.sigma**2
         log_p = np.log(self.w_s[ind]) + log_phi + self.log_constant
@@ -285,11 +293,13 @@ class CPD:
         """d log p / d R as a 3x3 array (registration.py:261-293): responsibilities
         gamma = exp(clip(log p_lk - log p_l, -20, 0)), residuals y_l - R x_k, outer products with
         the un-rotated source points."""
-        moved = self.source @ quat_to_matrix(q).T
+        moved = self._move(quat_to_matrix(q))
         dist, ind = self._neighbours(moved)
         log_p = self._log_terms(dist, ind)
         gamma = np.exp(np.clip(log_p - self._row_log_norm(log_p)[:, None], -20, 0))
         resid = self.target[:, None, :] - moved[ind]
+        pad = self.source.shape[1] - self.target.shape[1]  # registration.py:277-283: zero-pad to the source dimension
+        resid = np.pad(resid, ((0, 0), (0, 0), (0, pad)))
         coeff = (self.w_t[:, None] * gamma) / self.sigma**2
         return -np.einsum("lk,lkj,lki->ji", coeff, resid, self.source[ind])
 
@@ -306,11 +316,11 @@ class GMM(CPD):
     (registration.py:111-119)."""
 
     def __init__(self, target, source, sigma=1.0, k=20, beta=1.0,
-                 target_weights=None, source_weights=None):
-        super().__init__(target, source, sigma, k, beta, 0.0, target_weights, source_weights)
+                 target_weights=None, source_weights=None, translation=None):
+        super().__init__(target, source, sigma, k, beta, 0.0, target_weights, source_weights, translation)
 
     def log_prob_R(self, R):
-        moved = self.source @ R.T
+        moved = self._move(R)
         dist, ind = self._neighbours(moved)
         return logsumexp(self._log_terms(dist, ind), axis=1) @ self.w_t
 

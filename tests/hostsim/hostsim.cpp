@@ -34,6 +34,7 @@ struct Spec {
     int M; double kappa; const double *knots, *ang, *cosang, *sinang;
     // cpd
     int nt, ns, k, outlier; double sigma2, log_const, log_outlier, beta; const double *tgt, *wt, *src, *logws;
+    double shift[3]; int dim;
 };
 
 template <typename T> struct Built {
@@ -59,7 +60,7 @@ template <typename T> struct Built {
                 a0 = cast<T>(s.tgt, (size_t)s.nt * 3); a1 = cast<T>(s.wt, s.nt);
                 a2 = cast<T>(s.src, (size_t)s.ns * 3); a3 = cast<T>(s.logws, s.ns);
                 cpd = {a0.data(), a1.data(), a2.data(), a3.data(), (T)s.sigma2, (T)s.log_const, (T)s.log_outlier,
-                       (T)s.beta, s.nt, s.ns, s.k, s.outlier};
+                       (T)s.beta, s.nt, s.ns, s.k, s.outlier, {(T)s.shift[0], (T)s.shift[1], (T)s.shift[2]}, s.dim};
         }
     }
 };

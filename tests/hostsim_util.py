@@ -29,6 +29,7 @@ class Spec(C.Structure):
         ("nt", C.c_int), ("ns", C.c_int), ("k", C.c_int), ("outlier", C.c_int),
         ("sigma2", C.c_double), ("log_const", C.c_double), ("log_outlier", C.c_double), ("beta", C.c_double),
         ("tgt", _pd), ("wt", _pd), ("src", _pd), ("logws", _pd),
+        ("shift", C.c_double * 3), ("dim", C.c_int),
     ]
 
 
@@ -96,20 +97,26 @@ def curved(knots, kappa):
     return HostTarget(s, (knots, ang, ca, sa))
 
 
-def cpd(target, source, sigma, k, omega, beta=1.0, wt=None, ws=None, outlier=True):
+def cpd(target, source, sigma, k, omega, beta=1.0, wt=None, ws=None, outlier=True, translation=None):
     tgt = np.ascontiguousarray(target, dtype=float)
     src = np.ascontiguousarray(source, dtype=float)
+    dim = tgt.shape[1]
+    if dim == 2:  # 3D -> 2D projection: (x, y, 0) rows
+        tgt = np.ascontiguousarray(np.hstack([tgt, np.zeros((len(tgt), 1))]))
     wt = np.ones(len(tgt)) if wt is None else np.ascontiguousarray(wt, dtype=float)
     lws = np.zeros(len(src)) if ws is None else np.log(np.asarray(ws, float))
-    gauss = 1.5 * np.log(2 * np.pi * sigma**2)
+    gauss = dim / 2 * np.log(2 * np.pi * sigma**2)
     if outlier:
-        lo = np.log(omega + 1e-308) - np.sum(np.log(np.ptp(tgt, 0)))
+        lo = np.log(omega + 1e-308) - np.sum(np.log(np.ptp(tgt[:, :dim], 0)))
         with np.errstate(divide="ignore"):
             lc = np.log(1 - omega) - gauss
     else:
         lo, lc = -np.inf, -gauss
     s = Spec(kind=3, d=4, nt=len(tgt), ns=len(src), k=int(k), outlier=int(outlier), sigma2=float(sigma) ** 2,
-             log_const=float(lc), log_outlier=float(lo), beta=float(beta), tgt=_p(tgt), wt=_p(wt), src=_p(src), logws=_p(lws))
+             log_const=float(lc), log_outlier=float(lo), beta=float(beta), tgt=_p(tgt), wt=_p(wt), src=_p(src), logws=_p(lws), dim=dim)
+    if translation is not None:
+        for a, v in enumerate(translation):
+            s.shift[a] = float(v)
     return HostTarget(s, (tgt, wt, src, lws))
 
 
