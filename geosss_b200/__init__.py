@@ -38,8 +38,14 @@ from .pointcloud import (  # noqa: F401
 )
 from .rand import bfind, sample_bingham, sample_bingham_2d, sample_bingham_3d, sample_vMF  # noqa: F401
 from .registration import CoherentPointDrift, GaussianMixtureModel  # noqa: F401
+from . import io  # noqa: F401
 from .sphere import (  # noqa: F401
+    cartesian2polar,
+    cartesian2spherical,
     distance,
+    givens,
+    polar2cartesian,
+    spherical2cartesian,
     orthogonal_projection,
     radial_projection,
     sample_sphere,
@@ -48,6 +54,6 @@ from .sphere import (  # noqa: F401
 )
 from .sphere_tesselation import systematic_search, tessellate_rotations  # noqa: F401
 from .spherical_curve import SlerpCurve, SphericalCurve, brownian_curve  # noqa: F401
-from .utils import SamplerLauncher  # noqa: F401
+from .utils import IAT, SamplerLauncher, acf, acf_fft, colors, counter, n_eff, take_time  # noqa: F401
 
 __version__ = "0.1.0"

@@ -47,3 +47,34 @@ def sample_subsphere(v, seed=None):
 def distance(x, y):
     """Geodesic distance between unit vectors  (sphere.py:64-68)."""
     return np.arccos(np.clip(np.sum(x * y, axis=-1), -1, 1))
+
+
+# ---- coordinate changes and plane rotations (geosss/sphere.py:74-130); host helpers of the scripts
+def cartesian2polar(x):
+    """Angle in [0, 2 pi) of points (n, 2) on the circle."""
+    x = np.asarray(x)
+    return np.mod(np.arctan2(x[:, 1], x[:, 0]), 2 * np.pi)
+
+
+def polar2cartesian(theta):
+    return np.stack([np.cos(theta), np.sin(theta)], axis=-1)
+
+
+def spherical2cartesian(phi, theta):
+    """Azimuth phi, polar angle theta -> points on S^2."""
+    return np.stack([np.cos(phi) * np.sin(theta), np.sin(phi) * np.sin(theta), np.cos(theta)], axis=-1)
+
+
+def cartesian2spherical(x):
+    x = np.asarray(x)
+    return cartesian2polar(x), np.mod(np.arccos(x[:, 2]), np.pi)
+
+
+def givens(u, v, x):
+    """Function of theta rotating ``x`` by theta in the plane spanned by the orthonormal pair u, v."""
+    ux, vx = u @ x, v @ x
+
+    def rotate(theta):
+        return x + (np.cos(theta) - 1) * (ux * u + vx * v) + np.sin(theta) * (ux * v - vx * u)
+
+    return rotate

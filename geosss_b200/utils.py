@@ -8,7 +8,59 @@ class-level wrapper.  The device samplers evaluate densities inside kernels, so 
 number of evaluations the reference would have made (2 + rejections per transition).
 """
 
+import contextlib
 import functools
+import logging
+import time
+
+import numpy as np
+
+# the plotting palette of the scripts (utils.py:21-27)
+colors = [(0.85, 0.3, 0.1), (0.15, 0.35, 0.6), (0.95, 0.7, 0.1), (0.0, 0.0, 0.0), (0.8, 0.8, 0.8)]
+
+
+@contextlib.contextmanager
+def take_time(desc, mute=False):
+    """Log the CPU time of the enclosed block (utils.py:40-46)."""
+    t0 = time.process_time()
+    yield
+    dt = time.process_time() - t0
+    if not mute:
+        scale, unit = next(((s, u) for s, u in ((1.0, "s"), (1e-3, "ms"), (1e-6, "us")) if dt > s), (1e-9, "ns"))
+        logging.info("%s took %.1f %s", desc, dt / scale, unit)
+
+
+def acf(x, n_max=None):
+    """Autocorrelation by direct lagged products, normalised by lag 0 (utils.py:91-106)."""
+    x = np.asarray(x, dtype=float)
+    n_max = n_max or len(x) // 2
+    x = x - x.mean()
+    ac = np.array([np.mean(x[i:] * x[:len(x) - i]) for i in range(n_max)])
+    return ac / ac[0]
+
+
+def acf_fft(x):
+    """Circular autocorrelation by the convolution theorem (utils.py:109-112)."""
+    x = np.asarray(x, dtype=float)
+    X = np.fft.rfft((x - x.mean()) / x.std())
+    return np.real(np.fft.irfft(X.conj() * X))[:len(x) // 2] / len(x)
+
+
+def IAT(x, n=None):
+    """Integrated autocorrelation time with Gelman's pair-sum truncation (utils.py:115-129)."""
+    ac = acf_fft(x)
+    if n:
+        ac = ac[:n]
+    body = ac[2:-1] if len(ac) % 2 != 0 else ac[2:]
+    pairs = body.reshape(-1, 2).sum(1)
+    neg = np.nonzero(pairs < 0)[0]
+    L = 1 + 2 * neg[0] if len(neg) else len(ac) - 1  # upstream indexes neg[0] first and fails without a negative pair
+    return 1.0 + max(2 * np.sum(ac[1:L + 1]), 0.0)
+
+
+def n_eff(x, n=None):
+    """Effective sample size len(x) / IAT (utils.py:132-134).  Multi-chain ESS on the GPU: diagnostics.ess."""
+    return len(x) / IAT(x, n)
 
 
 class _BoundCounted:
@@ -43,6 +95,22 @@ class counted:
 
     def reset_counters(self):
         self.num_calls = 0
+
+
+def counter(method_names):
+    """Class decorator with upstream's name and arguments (utils.py:162-185): the named methods get
+    ``.num_calls`` / ``.reset_counters()``."""
+    if isinstance(method_names, str):
+        method_names = [method_names]
+
+    def class_decorator(cls):
+        for name in method_names:
+            raw = cls.__dict__.get(name) or getattr(cls, name, None)
+            if raw is not None and not isinstance(raw, counted):
+                setattr(cls, name, counted(raw))
+        return cls
+
+    return class_decorator
 
 
 class SamplerLauncher:

@@ -414,12 +414,14 @@ def golden_api_surface():
         "Bingham": distributions.Bingham, "BinghamFisher": distributions.BinghamFisher,
         "CurvedVonMisesFisher": distributions.CurvedVonMisesFisher,
         "CoherentPointDrift": registration.CoherentPointDrift, "GaussianMixtureModel": registration.GaussianMixtureModel,
+        "RotationProjection": pointcloud.RotationProjection, "RotationMatrix": pointcloud.RotationMatrix,
         "PointCloud": pointcloud.PointCloud, "SlerpCurve": spherical_curve.SlerpCurve, "SamplerLauncher": utils.SamplerLauncher,
     }
     surface = {"classes": {}, "functions": {}}
     for name, cls in items.items():
         entry = {"init": params(cls.__init__)}
-        for meth in ("sample", "log_prob", "gradient", "run", "run_rwmh", "run_hmc", "reset", "find_nearest", "transform_positions"):
+        for meth in ("sample", "log_prob", "gradient", "run", "run_rwmh", "run_hmc", "reset", "find_nearest", "transform_positions",
+                     "create", "rotation2d", "rotation3d"):
             if hasattr(cls, meth):
                 fn = getattr(cls, meth)
                 entry[meth] = params(getattr(fn, "__wrapped__", fn))
@@ -429,6 +431,15 @@ def golden_api_surface():
                      "radial_projection": sphere.radial_projection, "orthogonal_projection": sphere.orthogonal_projection,
                      "spherical_projection": sphere.spherical_projection, "sample_subsphere": sphere.sample_subsphere,
                      "distance": sphere.distance, "quat2matrix": pointcloud.quat2matrix,
+                     "cartesian2polar": sphere.cartesian2polar, "polar2cartesian": sphere.polar2cartesian,
+                     "spherical2cartesian": sphere.spherical2cartesian, "cartesian2spherical": sphere.cartesian2spherical,
+                     "givens": sphere.givens, "acf": utils.acf, "acf_fft": utils.acf_fft, "IAT": utils.IAT, "n_eff": utils.n_eff,
+                     "counter": utils.counter, "take_time": utils.take_time,
+                     "jacobian_rotation_matrix": pointcloud.jacobian_rotation_matrix,
+                     "sample_vMF": __import__("geosss.rand", fromlist=["x"]).sample_vMF,
+                     "sample_bingham": __import__("geosss.rand", fromlist=["x"]).sample_bingham,
+                     "sample_bingham_2d": __import__("geosss.rand", fromlist=["x"]).sample_bingham_2d,
+                     "sample_bingham_3d": __import__("geosss.rand", fromlist=["x"]).sample_bingham_3d,
                      "tessellate_rotations": __import__("geosss.sphere_tesselation", fromlist=["x"]).tessellate_rotations}.items():
         surface["functions"][name] = params(fn)
     surface["attributes"] = {"Bingham": ["A", "v", "U", "d", "mode", "max_log_prob"], "MixtureModel": ["pdfs", "weights"],

@@ -166,3 +166,35 @@ def test_rotation_tessellation_matches_reference_grid(golden):
     assert np.max(np.abs(np.abs(np.sum(q * g["quats_n1"], axis=1)) - 1)) < 1e-12  # equal up to the sign of q
     assert np.allclose(np.linalg.norm(q, axis=1), 1, atol=1e-14)
     assert len(gs.tessellate_rotations(2)) == int(g["n2_count"])
+
+
+def test_host_helpers_match_reference_values(golden, tmp_path):
+    """acf_fft / IAT / n_eff vs values computed by the reference (misc.npz); coordinate helpers; io round trip."""
+    g = golden("misc")
+    assert np.allclose(gs.acf_fft(g["ar1"]), g["ar1_acf"], rtol=0, atol=1e-13)
+    assert abs(gs.IAT(g["ar1"]) - float(g["ar1_iat"])) < 1e-10 and abs(gs.n_eff(g["ar1"]) - float(g["ar1_neff"])) < 1e-7
+    assert np.allclose(gs.acf(g["ar1"], 50)[:5], gs.acf_fft(g["ar1"])[:5], atol=5e-3)
+    th = np.array([0.1, 2.0, 4.0, 6.0])
+    assert np.allclose(gs.cartesian2polar(gs.polar2cartesian(th)), th)
+    phi, theta = np.array([0.3, 3.0, 5.5]), np.array([0.2, 1.5, 3.0])
+    p2, t2 = gs.cartesian2spherical(gs.spherical2cartesian(phi, theta))
+    assert np.allclose(p2, phi) and np.allclose(t2, theta)
+    u, v, x = np.eye(3)[0], np.eye(3)[1], np.array([1.0, 0.0, 2.0])
+    assert np.allclose(gs.givens(u, v, x)(np.pi / 2), [0.0, 1.0, 2.0])
+    obj = {"samples": np.arange(24.0).reshape(2, 3, 4), "method": "sss-shrink"}
+    for gz in (False, True):
+        f = str(tmp_path / f"run{int(gz)}.pkl")
+        gs.io.dump(obj, f, gzip=gz, lock=True, timeout=1.0)
+        back = gs.io.load(f, lock=True)  # gzip is detected
+        assert back["method"] == "sss-shrink" and np.array_equal(back["samples"], obj["samples"])
+        assert not os.path.exists(f + ".lock")
+
+    @gs.counter(["evaluate"])
+    class Thing:
+        def evaluate(self, x):
+            return 2 * x
+
+    t = Thing()
+    assert t.evaluate(2) == 4 and t.evaluate(3) == 6 and t.evaluate.num_calls == 2
+    t.evaluate.reset_counters()
+    assert Thing.evaluate.num_calls == 0
