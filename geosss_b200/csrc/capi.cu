@@ -399,7 +399,7 @@ template <typename T> static int logp_literal(geosss_target* t, const void* x, v
 static int g_sm_count = 0;
 
 template <class Policy, int ROWS> static int launch_logp_tiled_rows(const typename Policy::Params& p, const float* x, float* out, int64_t N, cudaStream_t st) {
-    const size_t smem = ((size_t)LP_STAGES * ROWS * Policy::dim(p) + Policy::smem_floats(p)) * sizeof(float);
+    const size_t smem = ((size_t)LP_STAGES * ROWS * lp_row_stride(Policy::dim(p)) + Policy::smem_floats(p)) * sizeof(float);
     if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: tile does not fit shared memory");
     if (!g_sm_count) {
         int dev = 0;

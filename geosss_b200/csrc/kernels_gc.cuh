@@ -146,6 +146,17 @@ struct CurvedGc {
             c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]); c.gu[4 * q + 3] = fmaf(k.w, uj, c.gu[4 * q + 3]);
         }
     }
+    // knots . x only (standalone log_prob: no direction)
+    __device__ __forceinline__ void accumulate_x(Coef& c, int j, float xj) const {
+        const int nq = (M + 3) >> 2;
+        const float4* col = reinterpret_cast<const float4*>(knotsT + j * (nq << 2));
+#pragma unroll
+        for (int q = 0; q < GC_MAX_KNOTS / 4; ++q) if (q < nq) {
+            const float4 k = col[q];
+            c.gx[4 * q] = fmaf(k.x, xj, c.gx[4 * q]);         c.gx[4 * q + 1] = fmaf(k.y, xj, c.gx[4 * q + 1]);
+            c.gx[4 * q + 2] = fmaf(k.z, xj, c.gx[4 * q + 2]); c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]);
+        }
+    }
     // coefficients were accumulated against the raw normals z; the direction is u = inp (z - zx x)
     __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
 #pragma unroll

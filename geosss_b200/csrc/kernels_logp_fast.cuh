@@ -87,36 +87,59 @@ template <int K, int D> struct VmfLpConst {
     }
 };
 
+// Rows are read with 16-byte shared loads whenever d is a multiple of 4.  With lane-per-row access the row
+// stride decides the bank conflicts: a stride of 4 * odd floats is conflict-free for 16-byte loads, so rows
+// whose d is a multiple of 8 are landed with a padded stride of d + 4 (one bulk copy per row instead of one
+// per tile); other d keep the contiguous tile (stride d: at most 2-way conflicts for scalar loads).
+__host__ __device__ inline int lp_row_stride(int d) { return (d & 7) == 0 ? d + 4 : d; }
+
 struct VmfLp {
     using Params = LpParams;
     static __host__ __device__ int dim(const Params& p) { return p.d; }
-    const float* mu;  // shared (K, d), times log2(e)
-    const float* c;   // shared (K), times log2(e)
+    const float* muT;  // shared (d, KP): component-minor, times log2(e); KP = K rounded up to 4
+    const float* c;    // shared (KP), times log2(e); padding components sit at -inf
     int d, K;
-    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)p.K * p.d + p.K; }
+    static __host__ __device__ size_t smem_floats(const LpParams& p) { return (size_t)((p.K + 3) & ~3) * (p.d + 1); }
     __device__ void stage(const LpParams& p, float* sm) {
         d = p.d; K = p.K;
+        const int KP = (K + 3) & ~3;
         constexpr float L2E = 1.4426950408889634f;
-        for (int i = threadIdx.x; i < K * d; i += blockDim.x) sm[i] = p.a0[i] * L2E;
-        for (int i = threadIdx.x; i < K; i += blockDim.x) sm[K * d + i] = p.a1[i] * L2E;
-        mu = sm; c = sm + K * d;
+        for (int i = threadIdx.x; i < KP * d; i += blockDim.x) {
+            const int j = i / KP, k = i - j * KP;
+            sm[i] = k < K ? p.a0[k * d + j] * L2E : 0.f;
+        }
+        for (int i = threadIdx.x; i < KP; i += blockDim.x) sm[KP * d + i] = i < K ? p.a1[i] * L2E : -INFINITY;
+        muT = sm; c = sm + KP * d;
+    }
+    __device__ __forceinline__ void add(float (&s)[LP_MAX_K], int j, float xj, int nq) const {
+        const float4* col = reinterpret_cast<const float4*>(muT + j * (nq << 2));
+#pragma unroll
+        for (int q = 0; q < LP_MAX_K / 4; ++q) if (q < nq) {
+            const float4 m = col[q];  // one broadcast load feeds four components
+            s[4 * q] = fmaf(m.x, xj, s[4 * q]);         s[4 * q + 1] = fmaf(m.y, xj, s[4 * q + 1]);
+            s[4 * q + 2] = fmaf(m.z, xj, s[4 * q + 2]); s[4 * q + 3] = fmaf(m.w, xj, s[4 * q + 3]);
+        }
     }
     __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
+        const int nq = (K + 3) >> 2;
         float s[LP_MAX_K];
 #pragma unroll
         for (int k = 0; k < LP_MAX_K; ++k) s[k] = 0.f;
-        for (int j = 0; j < d; ++j) {
-            const float xj = row[j];
-#pragma unroll
-            for (int k = 0; k < LP_MAX_K; ++k) if (k < K) s[k] = fmaf(mu[k * d + j], xj, s[k]);
+        if ((d & 3) == 0) {
+            for (int j = 0; j < d; j += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(row + j);
+                add(s, j, xv.x, nq); add(s, j + 1, xv.y, nq); add(s, j + 2, xv.z, nq); add(s, j + 3, xv.w, nq);
+            }
+        } else {
+            for (int j = 0; j < d; ++j) add(s, j, row[j], nq);
         }
         float m = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < LP_MAX_K; ++k) if (k < K) { s[k] += c[k]; m = fmaxf(m, s[k]); }
+        for (int k = 0; k < LP_MAX_K; ++k) if (k < 4 * nq) { s[k] += c[k]; m = fmaxf(m, s[k]); }
         if (!(m > -INFINITY)) return m;  // i0 overflow: every component is -inf, like the reference
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < LP_MAX_K; ++k) if (k < K) acc += fast_ex2(s[k] - m);
+        for (int k = 0; k < LP_MAX_K; ++k) if (k < 4 * nq) acc += fast_ex2(s[k] - m);
         return (m + fast_lg2(acc)) * 0.6931471805599453f;
     }
 };
@@ -135,17 +158,33 @@ struct BinghamLp {
     }
     __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
         const int d = g.d;
+        const bool vec = (d & 3) == 0;
         float q = 0.f;
         if (g.diag) {
-            for (int j = 0; j < d; ++j) q = fmaf(g.A[j] * row[j], row[j], q);
+            if (vec) {
+                for (int j = 0; j < d; j += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(row + j), a = *reinterpret_cast<const float4*>(g.A + j);
+                    q = fmaf(a.x * xv.x, xv.x, q); q = fmaf(a.y * xv.y, xv.y, q);
+                    q = fmaf(a.z * xv.z, xv.z, q); q = fmaf(a.w * xv.w, xv.w, q);
+                }
+            } else {
+                for (int j = 0; j < d; ++j) q = fmaf(g.A[j] * row[j], row[j], q);
+            }
         } else {
             for (int i = 0; i < g.dp; i += 4) {  // four rows of A x at a time (A symmetric: column block = row block)
                 float ax[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int j = 0; j < d; ++j) {
+                auto col = [&](int j, float xj) {
                     const float4 a4 = *reinterpret_cast<const float4*>(g.A + j * g.dp + i);
-                    const float xj = row[j];
                     ax[0] = fmaf(a4.x, xj, ax[0]); ax[1] = fmaf(a4.y, xj, ax[1]);
                     ax[2] = fmaf(a4.z, xj, ax[2]); ax[3] = fmaf(a4.w, xj, ax[3]);
+                };
+                if (vec) {
+                    for (int j = 0; j < d; j += 4) {
+                        const float4 xv = *reinterpret_cast<const float4*>(row + j);
+                        col(j, xv.x); col(j + 1, xv.y); col(j + 2, xv.z); col(j + 3, xv.w);
+                    }
+                } else {
+                    for (int j = 0; j < d; ++j) col(j, row[j]);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (i + k < d) q = fmaf(row[i + k], ax[k], q);
@@ -169,7 +208,14 @@ struct CurvedLp {
     __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
         CurvedGc::Coef co;
         g.begin(co);
-        for (int j = 0; j < g.d; ++j) g.accumulate(co, j, row[j], 0.f);
+        if ((g.d & 3) == 0) {
+            for (int j = 0; j < g.d; j += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(row + j);
+                g.accumulate_x(co, j, xv.x); g.accumulate_x(co, j + 1, xv.y); g.accumulate_x(co, j + 2, xv.z); g.accumulate_x(co, j + 3, xv.w);
+            }
+        } else {
+            for (int j = 0; j < g.d; ++j) g.accumulate_x(co, j, row[j]);
+        }
         return g.kappa * g.best_dot(co, 1.f, 0.f);
     }
 };
@@ -181,15 +227,17 @@ __global__ void __launch_bounds__(ROWS) k_logp_tiled(const __grid_constant__ typ
     float* lp_smem = reinterpret_cast<float*>(lp_smem_raw);
     __shared__ __align__(8) uint64_t full[LP_STAGES];
     const int d = Policy::dim(P);
+    const int ds = lp_row_stride(d);         // row stride in shared memory
+    const bool per_row = ds != d;            // padded rows: every thread copies its own row
     const size_t tile_floats = (size_t)ROWS * d;
     float* stage_buf[LP_STAGES];
 #pragma unroll
-    for (int s = 0; s < LP_STAGES; ++s) stage_buf[s] = lp_smem + s * tile_floats;
+    for (int s = 0; s < LP_STAGES; ++s) stage_buf[s] = lp_smem + s * (size_t)ROWS * ds;
     Policy pol;
-    pol.stage(P, lp_smem + LP_STAGES * tile_floats);
+    pol.stage(P, lp_smem + LP_STAGES * (size_t)ROWS * ds);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < LP_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < LP_STAGES; ++s) mbar_init(&full[s], per_row ? ROWS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -199,7 +247,12 @@ __global__ void __launch_bounds__(ROWS) k_logp_tiled(const __grid_constant__ typ
     // a tile can use the bulk engine when it is complete (byte count a multiple of 16) and x is 16-byte aligned
     auto bulk_ok = [&](int64_t tile) { return aligned && (tile + 1) * ROWS <= N; };
     auto issue = [&](int64_t tile, int s) {
-        if (tile < n_tiles && bulk_ok(tile) && threadIdx.x == 0) {
+        if (!(tile < n_tiles && bulk_ok(tile))) return;
+        if (per_row) {  // one arrival + d * 4 bytes per thread; the barrier counts ROWS arrivals
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full[s], (uint32_t)(d * sizeof(float)));
+            bulk_g2s(stage_buf[s] + (size_t)threadIdx.x * ds, x + tile * tile_floats + (size_t)threadIdx.x * d, (uint32_t)(d * sizeof(float)), &full[s]);
+        } else if (threadIdx.x == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&full[s], (uint32_t)(tile_floats * sizeof(float)));
             bulk_g2s(stage_buf[s], x + tile * tile_floats, (uint32_t)(tile_floats * sizeof(float)), &full[s]);
@@ -218,11 +271,11 @@ __global__ void __launch_bounds__(ROWS) k_logp_tiled(const __grid_constant__ typ
             phase[s] ^= 1;
         } else {  // ragged last tile / unaligned input: plain coalesced loads
             const int64_t n_here = (N - row0 < ROWS ? N - row0 : ROWS) * d;
-            for (int64_t i = threadIdx.x; i < n_here; i += blockDim.x) stage_buf[s][i] = x[row0 * d + i];
+            for (int64_t i = threadIdx.x; i < n_here; i += blockDim.x) stage_buf[s][(i / d) * ds + i % d] = x[row0 * d + i];
             __syncthreads();
         }
         const int64_t r = row0 + threadIdx.x;
-        if (r < N) out[r] = pol.eval(P, stage_buf[s] + (size_t)threadIdx.x * d);
+        if (r < N) out[r] = pol.eval(P, stage_buf[s] + (size_t)threadIdx.x * ds);
         __syncthreads();  // everyone is done with stage s before it is refilled two iterations later
     }
 }

@@ -147,6 +147,27 @@ def test_fast_logprob_tiles_ragged_unaligned_large(golden):
         assert rel_err(pdf2.log_prob(x.astype(F32)), pdf2.log_prob(x)) <= 2e-5
 
 
+@pytest.mark.parametrize("d", [8, 12, 16, 20, 32, 33, 48, 64, 100, 128])
+def test_fast_logprob_row_layouts(d):
+    """Every shared-memory row layout of the tiled float32 log_prob: d a multiple of 8 (padded rows, one bulk
+    copy per row), a multiple of 4 (contiguous tile, 16-byte loads) and odd sizes (scalar loads); aligned,
+    unaligned and ragged inputs; all four targets against the float64 literal kernels."""
+    gen = np.random.default_rng(d)
+    K = 3 if d <= 16 else 7
+    pdfs = [gs.MixtureModel([gs.VonMisesFisher(30.0 * m) for m in gs.sample_sphere(d - 1, K, seed=2)], np.arange(1.0, K + 1)),
+            gs.random_bingham(d, 40.0, 0, True, 3), gs.BinghamFisher(gs.random_bingham(d, 40.0, 0, True, 3).A, gen.standard_normal(d)),
+            gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(9, d, 0.5, seed=4)), 200.0)]
+    if d <= 64:
+        pdfs.append(gs.random_bingham(d, 40.0, 0, False, 5))  # dense (tensor-core kernel for 8 <= d <= 64)
+    x = gs.radial_projection(gen.standard_normal((128 * 5 + 77, d)))
+    xt = torch.as_tensor(x, dtype=torch.float32).cuda()
+    for pdf in pdfs:
+        want = pdf.log_prob(x)
+        assert rel_err(pdf.log_prob(xt).cpu().numpy(), want) <= 2e-5, type(pdf).__name__
+        assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 2e-5  # rows start 4 d bytes later: unaligned for odd d
+        assert rel_err(pdf.log_prob(xt[:128]).cpu().numpy(), want[:128]) <= 2e-5
+
+
 def test_dense_bingham_logprob_on_tensor_cores():
     """Dense Bingham(-Fisher) log_prob, 8 <= d <= 64: tcgen05 3xTF32 kernel vs the float64 literal kernel,
     ragged tile counts, unaligned input, and the SIMT fallback (GEOSSS_NO_TC) as a second opinion."""
