@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-transitions", type=int, default=2500, help="transitions per host core in the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--numa-bind", default="off", choices=["on", "off"],
+                    help="pin the process to the GPU's NUMA-local cores (measured on this pool: 3.6x slower end to end at "
+                         "1 GPU, +3 %% at 8 GPUs -- gpurun_out/r41_bench_*.json -- so it is off by default)")
     return ap.parse_args()
 
 
@@ -170,7 +173,9 @@ def main_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from geosss_b200 import distributed as gdist
-    numa_cpus = gdist.bind_host_to_gpu(local)  # pinned host buffers next to this GPU's PCIe root
+    numa_cpus = None
+    if a.numa_bind == "on":
+        numa_cpus = gdist.bind_host_to_gpu(local)  # pinned host buffers next to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
