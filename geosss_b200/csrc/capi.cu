@@ -39,6 +39,94 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(GEOSSS_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+
+// ------------------------------------------------------------------ device / pinned scratch kept between calls
+// cudaMalloc / cudaFree cost 0.3-1 ms each and cudaFree synchronises the device; a sampler object that lives
+// for one sample() call (the reference's usage: construct, sample, drop) would pay that on every call.  Freed
+// sampler buffers are therefore parked per device (exact-size reuse, at most POOL_SLOTS blocks / POOL_BYTES) and
+// handed to the next sampler of the same shape.  Callers synchronise the device before parking a block.
+namespace {
+struct DevPool {
+    static constexpr int POOL_SLOTS = 16;
+    static constexpr size_t POOL_BYTES = size_t(1) << 30;
+    struct Slot { void* p; size_t bytes; int dev; };
+    std::mutex mu;
+    std::vector<Slot> parked;
+    size_t parked_bytes = 0;
+    cudaError_t get(void** out, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            for (size_t i = 0; i < parked.size(); ++i)
+                if (parked[i].dev == dev && parked[i].bytes == bytes) {
+                    *out = parked[i].p;
+                    parked_bytes -= bytes;
+                    parked.erase(parked.begin() + (long)i);
+                    return cudaSuccess;
+                }
+        }
+        e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) {  // give parked memory back before giving up
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(out, bytes);
+        }
+        return e;
+    }
+    void put(void* p, size_t bytes) {
+        if (!p) return;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && bytes <= POOL_BYTES / 4) {
+            std::lock_guard<std::mutex> lock(mu);
+            if ((int)parked.size() < POOL_SLOTS && parked_bytes + bytes <= POOL_BYTES) {
+                parked.push_back(Slot{p, bytes, dev});
+                parked_bytes += bytes;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& s : parked) { cudaSetDevice(s.dev); cudaFree(s.p); }
+        cudaSetDevice(cur);
+        parked.clear();
+        parked_bytes = 0;
+    }
+};
+DevPool g_pool;
+
+// pinned staging for the small host<->device state transfers (initial states in, rejection counters out)
+struct PinnedScratch {
+    std::mutex mu;
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); p = nullptr; return nullptr; }
+            cap = bytes;
+        }
+        return p;
+    }
+};
+PinnedScratch g_pinned;
+}  // namespace
+
+extern "C" int geosss_release_cached_memory(void) {
+    cudaDeviceSynchronize();
+    g_pool.trim();
+    std::lock_guard<std::mutex> lock(g_pinned.mu);
+    if (g_pinned.p) cudaFreeHost(g_pinned.p);
+    g_pinned.p = nullptr; g_pinned.cap = 0;
+    return 0;
+}
+
 // ------------------------------------------------------------------ device arrays in both precisions
 struct Arr {
     float* f = nullptr;
@@ -117,6 +205,7 @@ struct geosss_sampler {
     int64_t adapt_total = 0;
     double alpha = 0.5;
     int n_leap = 10;
+    size_t state_bytes = 0, ws_bytes = 0;  // sizes of the pooled blocks (g_pool)
     bool is_mh() const { return kind >= GEOSSS_RWMH; }
     size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
 };
@@ -528,10 +617,14 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     if (!s) return fail(GEOSSS_E_NOMEM, "out of host memory");
     s->t = t; s->kind = kind; s->dtype = dtype; s->path = path; s->N = N; s->seed = seed; s->chain0 = chain_offset;
     const size_t es = s->esize();
-    cudaError_t e = cudaMalloc(&s->state, (size_t)N * t->d * es);
-    if (e == cudaSuccess) e = cudaMalloc(&s->n_reject, (size_t)N * sizeof(unsigned long long));
+    s->state_bytes = (size_t)N * t->d * es;
+    cudaError_t e = g_pool.get(&s->state, s->state_bytes);
+    if (e == cudaSuccess) e = g_pool.get(reinterpret_cast<void**>(&s->n_reject), (size_t)N * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(s->n_reject, 0, (size_t)N * sizeof(unsigned long long));
-    if (e == cudaSuccess && path == GEOSSS_PATH_LITERAL && t->kind != TGT_CPD) e = cudaMalloc(&s->ws, (size_t)(mh ? 5 : 3) * N * t->d * es);
+    if (e == cudaSuccess && path == GEOSSS_PATH_LITERAL && t->kind != TGT_CPD) {
+        s->ws_bytes = (size_t)(mh ? 5 : 3) * N * t->d * es;
+        e = g_pool.get(&s->ws, s->ws_bytes);
+    }
     if (e == cudaSuccess && mh) e = cudaMalloc(&s->stepsize, (size_t)N * sizeof(double));
     if (e == cudaSuccess && mh) e = cudaMalloc(&s->adapt_count, (size_t)N * sizeof(int64_t));
     if (e == cudaSuccess && mh) e = cudaMemset(s->adapt_count, 0, (size_t)N * sizeof(int64_t));
@@ -550,9 +643,10 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
 
 extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     if (!s) return 0;
-    if (s->state) cudaFree(s->state);
-    if (s->ws) cudaFree(s->ws);
-    if (s->n_reject) cudaFree(s->n_reject);
+    cudaDeviceSynchronize();  // what cudaFree would do: nothing of this sampler is in flight when its blocks are parked
+    g_pool.put(s->state, s->state_bytes);
+    g_pool.put(s->ws, s->ws_bytes);
+    g_pool.put(s->n_reject, (size_t)s->N * sizeof(unsigned long long));
     if (s->stepsize) cudaFree(s->stepsize);
     if (s->adapt_count) cudaFree(s->adapt_count);
     if (s->n_walk) cudaFree(s->n_walk);
@@ -678,9 +772,11 @@ extern "C" int geosss_sampler_set_state_host(geosss_sampler_t s, const double* x
     if (s->dtype == GEOSSS_F64) {
         CU(cudaMemcpy(s->state, x_host, n * 8, cudaMemcpyHostToDevice));
     } else {
-        std::vector<float> f(n);
+        std::lock_guard<std::mutex> lock(g_pinned.mu);
+        float* f = static_cast<float*>(g_pinned.ensure(n * 4));
+        if (!f) return fail(GEOSSS_E_NOMEM, "set_state_host: no pinned staging memory");
         for (size_t i = 0; i < n; ++i) f[i] = (float)x_host[i];
-        CU(cudaMemcpy(s->state, f.data(), n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->state, f, n * 4, cudaMemcpyHostToDevice));
     }
     return 0;
 }

@@ -67,7 +67,8 @@ class Sampler:
         if x0.ndim not in (1, 2):
             raise ValueError("initial_state must have shape (d,) or (N, d)")
         self._single = x0.ndim == 1
-        self._host_state = np.array(x0, dtype=float).reshape(-1, x0.shape[-1])
+        # as upstream, the array is stored, not copied (mcmc.py:43); it is only ever replaced, never written to
+        self._host_state = np.asarray(x0, dtype=float).reshape(-1, x0.shape[-1])
         self.N, self.d = self._host_state.shape
         if distribution.d is not None and self.d != distribution.d:
             raise ValueError(f"initial_state has dimension {self.d}, target has {distribution.d}")
@@ -219,7 +220,7 @@ class Sampler:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
             if keeps_current:
                 cur = self._host_state if self.rng.steps_done == 0 else self._positions()
-                buf[0] = torch.as_tensor(cur, dtype=self._tdtype)
+                np.copyto(buf[0].numpy(), cur, casting="same_kind")  # one pass, float64 -> sampler dtype
             dst = buf[1:] if keeps_current else buf
             with torch.cuda.device(self.device):
                 _lib.check(lib.geosss_sampler_run_host(h, n_skip, n_new, dst.data_ptr() if n_new else None))

@@ -135,7 +135,11 @@ int geosss_sampler_run_tape(geosss_sampler_t s, int64_t n_steps, const double* t
                             int32_t* status, void* stream);
 /* transitions done so far (the Philox step counter) */
 int64_t geosss_sampler_steps_done(geosss_sampler_t s);
+/* Parks the sampler's device blocks for the next sampler of the same shape on this device (the reference's
+ * usage constructs a sampler per sample() call: geosss/utils.py:198-232); synchronises the device first. */
 int geosss_sampler_destroy(geosss_sampler_t s);
+/* Returns every parked device block and the pinned staging buffer to the driver. */
+int geosss_release_cached_memory(void);
 
 /* ---- HOST-buffer entry points (synchronous; copies are part of the call) ------------------- */
 
