@@ -62,16 +62,16 @@ __device__ __forceinline__ void box_muller_fast(uint32_t wa, uint32_t wb, float&
 
 // Stores the first d of x[0..D) to o, vectorised when d allows (o is 8- resp. 16-byte aligned
 // whenever d is even resp. a multiple of 4, because rows are d floats apart).
-template <int D> __device__ __forceinline__ void store_row(float* __restrict__ o, const float (&x)[D], int d) {
-    if (d == D) {
+template <int DT> __device__ __forceinline__ void store_row(float* __restrict__ o, const float (&x)[DT]) {
+    if (DT % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < D; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-    } else if (d == D - 2) {
+        for (int j = 0; j + 3 < DT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    } else if (DT % 2 == 0) {
 #pragma unroll
-        for (int j = 0; j < D - 2; j += 2) *reinterpret_cast<float2*>(o + j) = make_float2(x[j], x[j + 1]);
+        for (int j = 0; j + 1 < DT; j += 2) *reinterpret_cast<float2*>(o + j) = make_float2(x[j], x[j + 1]);
     } else {
 #pragma unroll
-        for (int j = 0; j < D; ++j) if (j < d) o[j] = x[j];
+        for (int j = 0; j < DT; ++j) o[j] = x[j];
     }
 }
 
@@ -114,22 +114,27 @@ __device__ __forceinline__ float kept_log2p(bool moved, float level2, float S, f
 // of the earlier angles (mcmc.py:400), never on the density, so all four are known up front; their
 // densities are evaluated with four-way ILP and the first accepted one wins -- identical to
 // evaluating them one after the other.
-template <int K, int D, int KIND>
+//
+// The true dimension DT is a template parameter (the parameter block keeps rows of D = 4 ceil(DT/4) floats):
+// the unused Box-Muller pair of the last Philox block, the padded FMAs of the projections and of the 2K dot
+// products and the tail predicates all disappear at compile time (d = 10: 52 of the prologue's ~580 instructions).
+template <int K, int DT, int KIND>
 __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__ VmfFastParams P, RunArgs a) {
+    constexpr int D = (DT + 3) / 4 * 4;
+    constexpr int d = DT;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = c < a.N;  // lanes past the end still vote
-    const int d = P.d;
     constexpr float LN2 = 0.6931471805599453f;
-    const bool aux_in_last = philox_aux_in_last(d);
-    const int nbn = D / 4;                       // normal blocks (D = 4 ceil(d/4))
-    const int pb = aux_in_last ? nbn : nbn + 1;  // first proposal block
+    constexpr bool aux_in_last = (DT & 3) == 1 || (DT & 3) == 2;  // philox_aux_in_last
+    constexpr int nbn = D / 4;                       // normal blocks
+    constexpr int pb = aux_in_last ? nbn : nbn + 1;  // first proposal block
     const int quorum = a.quorum;
     const int n_steps = (int)a.n_steps;
 
-    float x[D], u[D];
+    float x[DT], u[DT];
     float* st = static_cast<float*>(a.state) + (live ? c : 0) * d;
 #pragma unroll
-    for (int j = 0; j < D; ++j) { x[j] = (live && j < d) ? st[j] : 0.0f; u[j] = 0.f; }
+    for (int j = 0; j < DT; ++j) { x[j] = live ? st[j] : 0.0f; u[j] = 0.f; }
 
     PhiloxDraws<float> dr;
     dr.init(a.seed, a.chain0 + (uint64_t)c, d);
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
 #pragma unroll
     for (int k = 0; k < K; ++k) { A[k] = 0.f; B[k] = 0.f; G[k] = 0.f; }
     float lo = 0.f, hi = 2.f, level2 = 0.f, lp2 = 0.f;
+    bool have_lp = false;  // lp2 = log2 p(x) is carried from the accepted proposal (level2 + log2 S) instead of re-evaluated
     float sn = 0.f, cs = 1.f, S = 0.f;  // the accepted proposal, applied at the next prologue
     int t = live ? 0 : n_steps;         // transitions started by this lane
     int r = 0, batch = 0, cap = 0;
@@ -161,15 +167,16 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
                 if (pending) {
                     if (moved) {
 #pragma unroll
-                        for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+                        for (int j = 0; j < DT; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+                        lp2 = kept_log2p<K>(true, level2, S, lp2, cs, sn, A, B, P.c);
                     }
                     rej_total += (unsigned)r;
                     rej_window += (unsigned)r;
                     if (++since_keep == (int)a.thin) {
                         const int64_t k = kept++;
                         since_keep = 0;
-                        if (samples) store_row<D>(samples + (k * a.ss_step + c * a.ss_chain), x, d);
-                        if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                        if (samples) store_row<DT>(samples + (k * a.ss_step + c * a.ss_chain), x);
+                        if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp2 * LN2;
                         if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
                         rej_window = 0;
                     }
@@ -181,45 +188,53 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
                 dr.s_hi = (uint32_t)(step >> 32) & 0xFFFFu;
                 float xx = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) xx = fmaf(x[j], x[j], xx);
+                for (int j = 0; j < DT; ++j) xx = fmaf(x[j], x[j], xx);
                 const float inx = rsqrtf(xx);
 #pragma unroll
-                for (int j = 0; j < D; ++j) x[j] *= inx;
+                for (int j = 0; j < DT; ++j) x[j] *= inx;
 
                 uint32_t aux0 = 0, aux1 = 0;
 #pragma unroll
-                for (int b = 0; b < D / 4; ++b) {
+                for (int b = 0; b < nbn; ++b) {
                     U4 w = dr.block(b);
-                    box_muller_fast(w.x, w.y, u[4 * b], u[4 * b + 1]);
-                    box_muller_fast(w.z, w.w, u[4 * b + 2], u[4 * b + 3]);
-                    if (b == D / 4 - 1) { aux0 = w.z; aux1 = w.w; }
+                    float z0, z1;
+                    box_muller_fast(w.x, w.y, z0, z1);
+                    u[4 * b] = z0;
+                    if (4 * b + 1 < DT) u[4 * b + 1] = z1;
+                    if (4 * b + 2 < DT) {
+                        box_muller_fast(w.z, w.w, z0, z1);
+                        u[4 * b + 2] = z0;
+                        if (4 * b + 3 < DT) u[4 * b + 3] = z1;
+                    }
+                    if (b == nbn - 1) { aux0 = w.z; aux1 = w.w; }
                 }
                 if (!aux_in_last) { U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
-#pragma unroll
-                for (int j = 0; j < D; ++j) if (j >= d) u[j] = 0.f;
                 float zx = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) zx = fmaf(u[j], x[j], zx);
+                for (int j = 0; j < DT; ++j) zx = fmaf(u[j], x[j], zx);
                 float pp = 0.f;
 #pragma unroll
-                for (int j = 0; j < D; ++j) { u[j] = fmaf(-zx, x[j], u[j]); pp = fmaf(u[j], u[j], pp); }
+                for (int j = 0; j < DT; ++j) { u[j] = fmaf(-zx, x[j], u[j]); pp = fmaf(u[j], u[j], pp); }
                 const float inp = rsqrtf(pp);
 #pragma unroll
-                for (int j = 0; j < D; ++j) u[j] *= inp;
+                for (int j = 0; j < DT; ++j) u[j] *= inp;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     float sa = 0.f, sb = 0.f;
 #pragma unroll
-                    for (int j = 0; j < D; ++j) { sa = fmaf(P.mu[k * D + j], x[j], sa); sb = fmaf(P.mu[k * D + j], u[j], sb); }
+                    for (int j = 0; j < DT; ++j) { sa = fmaf(P.mu[k * D + j], x[j], sa); sb = fmaf(P.mu[k * D + j], u[j], sb); }
                     A[k] = sa; B[k] = sb;
                 }
-                float mx = -INFINITY;
+                if (!have_lp) {  // first transition of the launch: evaluate the mixture at x
+                    float mx = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < K; ++k) mx = fmaxf(mx, A[k] + P.c[k]);
-                float s0 = 0.f;
+                    for (int k = 0; k < K; ++k) mx = fmaxf(mx, A[k] + P.c[k]);
+                    float s0 = 0.f;
 #pragma unroll
-                for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - mx);
-                lp2 = mx + fast_lg2(s0);
+                    for (int k = 0; k < K; ++k) s0 += fast_ex2(A[k] + P.c[k] - mx);
+                    lp2 = mx + fast_lg2(s0);
+                    have_lp = true;
+                }
                 level2 = lp2 + fast_lg2(u01(aux0, 0.f));
 #pragma unroll
                 for (int k = 0; k < K; ++k) G[k] = P.c[k] - level2;
@@ -344,19 +359,20 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
         if (pending) {
             if (moved) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+                for (int j = 0; j < DT; ++j) x[j] = fmaf(cs, x[j], sn * u[j]);
+                lp2 = kept_log2p<K>(true, level2, S, lp2, cs, sn, A, B, P.c);
             }
             rej_total += (unsigned)r;
             rej_window += (unsigned)r;
             if (++since_keep == (int)a.thin) {
                 const int64_t k = kept++;
-                if (samples) store_row<D>(samples + (k * a.ss_step + c * a.ss_chain), x, d);
-                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = kept_log2p<K>(moved, level2, S, lp2, cs, sn, A, B, P.c) * LN2;
+                if (samples) store_row<DT>(samples + (k * a.ss_step + c * a.ss_chain), x);
+                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp2 * LN2;
                 if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
             }
         }
 #pragma unroll
-        for (int j = 0; j < D; ++j) if (j < d) st[j] = x[j];
+        for (int j = 0; j < DT; ++j) st[j] = x[j];
         a.n_reject[c] = rej_total;
     }
 }
@@ -365,7 +381,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
 inline int fast_supported(int target_kind, int d, int K, int single) {
     (void)single;
     if (target_kind != TGT_VMF_MIX) return -1;
-    if (d > FAST_MAX_D || K > FAST_MAX_K || K < 1) return -1;
+    if (d < 2 || d > FAST_MAX_D || K > FAST_MAX_K || K < 1) return -1;
     return 0;
 }
 
