@@ -31,6 +31,7 @@ SIGNATURES = {
     "geosss_target_create_cpd": (_i, [_i, _i, _pd, _pd, _pd, _pd, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_p)]),
     "geosss_target_create_cpd_projected": (_i, [_i, _i, _pd, _pd, _pd, _pd, _dbl, _dbl, _dbl, _i, _i, C.POINTER(_p)]),
     "geosss_target_cpd_set_translation": (_i, [_p, _pd]),
+    "geosss_target_cpd_grid_info": (_i, [_p, _pd, _pd, C.POINTER(_i), C.POINTER(_i)]),
     "geosss_target_dim": (_i, [_p]),
     "geosss_target_destroy": (_i, [_p]),
     "geosss_log_prob": (_i, [_p, _i, _i, _p, _p, _i64, _p]),

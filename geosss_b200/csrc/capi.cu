@@ -19,6 +19,7 @@
 #include "kernels_literal.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_mh.cuh"
+#include "kernels_cpd_cell.cuh"
 
 using namespace geosss;
 
@@ -173,6 +174,11 @@ struct geosss_target {
     double shift[3] = {0, 0, 0};
     int dim = 3;
     Arr tgt, wt, src, logws;
+    // cell lists of the float32 cutoff kernels (kernels_cpd_cell.cuh); has_grid = 0: dense pair sum
+    int has_grid = 0;
+    CpdCellGrid grid{};
+    double grid_rc = 0, grid_mean_candidates = 0;
+    void *d_cell = nullptr, *d_entry = nullptr, *d_tgt4 = nullptr;
 
     template <typename T> VmfMixP<T> vmf() const { return {mu.get<T>(), logw.get<T>(), logi0.get<T>(), K, d, single}; }
     template <typename T> BinghamP<T> bingham() const { return {A.get<T>(), has_b ? b.get<T>() : nullptr, d}; }
@@ -185,6 +191,8 @@ struct geosss_target {
     }
     void release() {
         for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (void** q : {&d_cell, &d_entry, &d_tgt4}) { if (*q) cudaFree(*q); *q = nullptr; }
+        has_grid = 0;
     }
 };
 
@@ -217,6 +225,19 @@ static int fill_stepsize(geosss_sampler* s, double value) {
 }
 
 // ------------------------------------------------------------------ fast-path dispatch
+// the cutoff kernels serve the dense sum (k <= 0 or k >= ns) when the lists exist; GEOSSS_CPD_DENSE=1 forces the pair sum
+static bool cpd_use_grid(const geosss_target* t) {
+    if (!t->has_grid) return false;
+    const char* e = std::getenv("GEOSSS_CPD_DENSE");
+    return !(e && e[0] == '1');
+}
+
+static CpdCellGrid cpd_grid_now(const geosss_target* t) {
+    CpdCellGrid g = t->grid;
+    for (int a = 0; a < 3; ++a) g.shift[a] = (float)t->shift[a];
+    return g;
+}
+
 // the normals stay in shared memory for d < 64 and for dense Bingham (kernels_gc.cuh, STORE); measured on
 // B200: regenerating them pays at d = 100 (+37 %, twice the resident warps) and costs 6 % at d = 50
 static bool gc_store_normals(const geosss_target* t) { return t->d < 64 || (t->kind == TGT_BINGHAM && !t->diag); }
@@ -290,6 +311,20 @@ static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a
     }
     if (t->kind == TGT_BINGHAM) return launch_gc<BinghamGc>(t, kind, a, st);
     if (t->kind == TGT_CURVED_VMF) return launch_gc<CurvedGc>(t, kind, a, st);
+    if (t->kind == TGT_CPD && !target_fast_supported(t) && cpd_use_grid(t)) {
+        const CpdCellGrid g = cpd_grid_now(t);
+        const size_t smem = g.smem_bytes();
+        const unsigned grid = (unsigned)((a.N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS);
+        if (kind == SHRINK) {
+            CU(cudaFuncSetAttribute(k_sampler_cpd_cell<SHRINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sampler_cpd_cell<SHRINK><<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, a);
+        } else {
+            CU(cudaFuncSetAttribute(k_sampler_cpd_cell<REJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_sampler_cpd_cell<REJECT><<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, a);
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (t->kind == TGT_CPD && !target_fast_supported(t)) {
         const size_t smem = (size_t)CPD_WARPS * 4 * t->ns * sizeof(float);
         const unsigned grid = (unsigned)((a.N + CPD_WARPS - 1) / CPD_WARPS);
@@ -389,6 +424,95 @@ extern "C" int geosss_target_create_curved_vmf(int d, int n_knots, const double*
     return 0;
 }
 
+
+// Cell lists for the cutoff kernels (kernels_cpd_cell.cuh).  Cutoff: a source point farther than rc from a
+// target row adds less than exp(CPD_CELL_LOG_EPS) / ns of the outlier floor to the row sum:
+//   log_const + log w_k - rc^2 / (2 sigma^2)  <=  log_outlier + CPD_CELL_LOG_EPS - log(ns)   for every k.
+// Returns 0 and leaves has_grid = 0 when the lists would not pay (few, large cells) or do not fit shared memory.
+static int build_cpd_grid(geosss_target* t, const double* target, const double* wt, const double* source, const double* lws) {
+    t->has_grid = 0;
+    if (t->dim != 3 || !t->outlier || !std::isfinite(t->log_outlier) || !std::isfinite(t->log_const)) return 0;
+    const int ns = t->ns, nt = t->nt;
+    const double ln_ratio = t->log_const + t->max_logw + std::log((double)ns) - t->log_outlier - CPD_CELL_LOG_EPS;
+    const double rc = std::sqrt(2.0 * t->sigma2 * (ln_ratio > 0.25 ? ln_ratio : 0.25));
+    const double h = rc * (1.0 + 1e-4);
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = hi[a] = source[a];
+        for (int k = 1; k < ns; ++k) { double v = source[(size_t)k * 3 + a]; lo[a] = v < lo[a] ? v : lo[a]; hi[a] = v > hi[a] ? v : hi[a]; }
+        if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return 0;
+    }
+    int n[3];
+    double cells = 1;
+    for (int a = 0; a < 3; ++a) { n[a] = (int)std::floor((hi[a] - lo[a]) / h) + 3; cells *= n[a]; }
+    if (cells > 32768) return 0;
+    const int n_cells = n[0] * n[1] * n[2];
+    auto cell_of = [&](const double* x, int c[3]) {
+        for (int a = 0; a < 3; ++a) {
+            c[a] = (int)std::floor((x[a] - (lo[a] - h)) / h);
+            c[a] = c[a] < 1 ? 1 : (c[a] > n[a] - 2 ? n[a] - 2 : c[a]);
+        }
+    };
+    std::vector<std::vector<int>> bucket(n_cells);
+    for (int k = 0; k < ns; ++k) {
+        int c[3];
+        cell_of(source + (size_t)k * 3, c);
+        bucket[(c[2] * n[1] + c[1]) * n[0] + c[0]].push_back(k);
+    }
+    const double m0 = t->log_outlier > t->log_const + t->max_logw ? t->log_outlier : t->log_const + t->max_logw;
+    const double L2E = 1.4426950408889634;
+    std::vector<uint32_t> cell(n_cells);
+    std::vector<float4> entry;
+    double weighted = 0;
+    for (int cz = 0; cz < n[2]; ++cz)
+        for (int cy = 0; cy < n[1]; ++cy)
+            for (int cx = 0; cx < n[0]; ++cx) {
+                const size_t first = entry.size();
+                for (int dz = -1; dz <= 1; ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int x = cx + dx, y = cy + dy, z = cz + dz;
+                            if (x < 0 || y < 0 || z < 0 || x >= n[0] || y >= n[1] || z >= n[2]) continue;
+                            for (int k : bucket[(z * n[1] + y) * n[0] + x])
+                                entry.push_back(make_float4((float)((source[(size_t)k * 3] - (lo[0] - h)) / h),
+                                                            (float)((source[(size_t)k * 3 + 1] - (lo[1] - h)) / h),
+                                                            (float)((source[(size_t)k * 3 + 2] - (lo[2] - h)) / h),
+                                                            (float)((lws[k] + t->log_const - m0) * L2E)));
+                        }
+                const size_t cnt = entry.size() - first;
+                if (cnt >= (1u << (32 - CPD_CELL_COUNT_SHIFT)) || first >= (1u << CPD_CELL_COUNT_SHIFT)) return 0;
+                cell[(cz * n[1] + cy) * n[0] + cx] = (uint32_t)first | ((uint32_t)cnt << CPD_CELL_COUNT_SHIFT);
+                weighted += (double)cnt * bucket[(cz * n[1] + cy) * n[0] + cx].size();
+            }
+    const double mean_cand = weighted / ns;  // candidates met by a row sitting on a source point
+    CpdCellGrid g{};
+    for (int a = 0; a < 3; ++a) { g.org[a] = (float)(lo[a] - h); g.n[a] = n[a]; g.shift[a] = 0.f; }
+    g.inv_h = (float)(1.0 / h);
+    g.n_cells = n_cells; g.n_entries = (int)entry.size(); g.nt = nt;
+    g.q2 = (float)(-0.5 * L2E * h * h / t->sigma2);  // distances are measured in cell units
+    g.base = (float)std::exp(t->log_outlier - m0);
+    g.m0 = (float)m0;
+    g.beta = (float)t->beta;
+    if (mean_cand > 0.5 * ns || g.smem_bytes() > 200 * 1024 || entry.empty()) return 0;
+    std::vector<float4> tgt4(nt);
+    for (int l = 0; l < nt; ++l)
+        tgt4[l] = make_float4((float)target[(size_t)l * 3], (float)target[(size_t)l * 3 + 1], (float)target[(size_t)l * 3 + 2], (float)wt[l]);
+    CU(cudaMalloc(&t->d_cell, cell.size() * sizeof(uint32_t)));
+    CU(cudaMalloc(&t->d_entry, entry.size() * sizeof(float4)));
+    CU(cudaMalloc(&t->d_tgt4, tgt4.size() * sizeof(float4)));
+    CU(cudaMemcpy(t->d_cell, cell.data(), cell.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t->d_entry, entry.data(), entry.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t->d_tgt4, tgt4.data(), tgt4.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    g.cell = static_cast<const uint32_t*>(t->d_cell);
+    g.entry = static_cast<const float4*>(t->d_entry);
+    g.tgt4 = static_cast<const float4*>(t->d_tgt4);
+    t->grid = g;
+    t->grid_rc = rc;
+    t->grid_mean_candidates = mean_cand;
+    t->has_grid = 1;
+    return 0;
+}
+
 static int create_cpd(int dim, int n_t, int n_s, const double* target_in, const double* w_t, const double* source,
                       const double* w_s, double sigma, double omega, double beta, int k, int outlier, geosss_target_t* out) {
     if (!out || !target_in || !source || n_t < 1 || n_s < 1) return fail(GEOSSS_E_INVALID, "cpd: need target and source clouds");
@@ -431,6 +555,7 @@ static int create_cpd(int dim, int n_t, int n_s, const double* target_in, const 
     if (!rc) rc = t->src.upload(source, (size_t)n_s * 3);
     if (!rc) rc = t->wt.upload(wt.data(), n_t);
     if (!rc) rc = t->logws.upload(lws.data(), n_s);
+    if (!rc) rc = build_cpd_grid(t, target, wt.data(), source, lws.data());
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
     return 0;
@@ -452,6 +577,15 @@ extern "C" int geosss_target_cpd_set_translation(geosss_target_t t, const double
     if (!t || t->kind != TGT_CPD) return fail(GEOSSS_E_INVALID, "cpd_set_translation: not a registration target");
     for (int a = 0; a < 3; ++a) t->shift[a] = (translation && a < t->dim) ? translation[a] : 0.0;
     return 0;
+}
+
+extern "C" int geosss_target_cpd_grid_info(geosss_target_t t, double* cutoff, double* mean_candidates, int* n_cells, int* n_entries) {
+    if (!t || t->kind != TGT_CPD) return fail(GEOSSS_E_INVALID, "cpd_grid_info: not a registration target");
+    if (cutoff) *cutoff = t->has_grid ? t->grid_rc : 0.0;
+    if (mean_candidates) *mean_candidates = t->has_grid ? t->grid_mean_candidates : 0.0;
+    if (n_cells) *n_cells = t->has_grid ? t->grid.n_cells : 0;
+    if (n_entries) *n_entries = t->has_grid ? t->grid.n_entries : 0;
+    return t->has_grid;
 }
 
 extern "C" int geosss_target_dim(geosss_target_t t) { return t ? t->d : GEOSSS_E_INVALID; }
@@ -579,6 +713,19 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
         case TGT_CPD: {
             if (target_fast_supported(t)) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast CPD kernel needs the dense sum with an outlier term");
+            if (cpd_use_grid(t)) {
+                const CpdCellGrid g = cpd_grid_now(t);
+                const size_t gsmem = g.smem_bytes();
+                int dev = 0, sms = 148;
+                CU(cudaGetDevice(&dev));
+                CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                const int64_t want = (N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS;
+                const int64_t cap = (int64_t)sms * (gsmem <= 110 * 1024 ? 2 : 1);
+                CU(cudaFuncSetAttribute(k_logp_cpd_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+                k_logp_cpd_cell<<<(unsigned)(want < cap ? want : cap), CPD_CELL_WARPS * 32, gsmem, st>>>(g, xi, o, N);
+                CU(cudaGetLastError());
+                return 0;
+            }
             const size_t smem = (size_t)CPD_WARPS * 4 * t->ns * sizeof(float);
             CU(cudaFuncSetAttribute(k_logp_cpd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_logp_cpd_fast<<<(unsigned)((N + CPD_WARPS - 1) / CPD_WARPS), CPD_WARPS * 32, smem, st>>>(t->cpd<float>(), (float)t->max_logw, xi, o, N);

@@ -15,8 +15,11 @@ namespace geosss {
 
 // x, u, y: views of length d (u receives the direction, y is proposal scratch).
 // Returns the number of rejected proposals; *lp_new receives log p(new state).
+// lp_x_io (optional, throughput kernels only): log p(x) carried from the previous transition -- NaN means
+// "not known yet"; it is updated when a proposal is accepted and left alone when the chain stays.  log p is a
+// pure function and the accepted y IS the next x, so the carried value equals the re-evaluated one bit for bit.
 template <typename T, int KIND, class Draws, class Vec, class LogP>
-GEOSSS_HD int transition_literal(int d, Vec x, Vec u, Vec y, Draws& dr, const LogP& logp, T* lp_new) {
+GEOSSS_HD int transition_literal(int d, Vec x, Vec u, Vec y, Draws& dr, const LogP& logp, T* lp_new, T* lp_x_io = nullptr) {
     // direction: u = unit(z - (z.n) n),  n = x / (|x| + tiny)
     dr.fill_normals(u, d);
     T xx = 0;
@@ -33,7 +36,13 @@ GEOSSS_HD int transition_literal(int d, Vec x, Vec u, Vec y, Draws& dr, const Lo
     const T np_ = m_sqrt(pp) + Const<T>::tiny();
     for (int j = 0; j < d; ++j) u[j] = u[j] / np_;
 
-    const T level = logp(x) + m_log(dr.level_uniform());
+    T lp_x;
+    if (lp_x_io && *lp_x_io == *lp_x_io) lp_x = *lp_x_io;
+    else {
+        lp_x = logp(x);
+        if (lp_x_io) *lp_x_io = lp_x;
+    }
+    const T level = lp_x + m_log(dr.level_uniform());
 
     T lo, hi;
     if (KIND == SHRINK) {
@@ -52,6 +61,7 @@ GEOSSS_HD int transition_literal(int d, Vec x, Vec u, Vec y, Draws& dr, const Lo
         if (ly > level) {
             for (int j = 0; j < d; ++j) x[j] = y[j];
             *lp_new = ly;
+            if (lp_x_io) *lp_x_io = ly;
             return r;
         }
         if (KIND == SHRINK) {

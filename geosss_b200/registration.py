@@ -97,6 +97,20 @@ class GaussianMixtureModel(Registration):
         """d log_prob / d q for scalar-last quaternions (registration.py:55-59, pointcloud.py:135-203)."""
         return self._shifted(translation, rotation, True)
 
+    def cutoff_grid_info(self, device=None):
+        """Cell lists the float32 throughput kernels use in place of upstream's per-call KD-tree
+        (registration.py:101-109): dict(cutoff, mean_candidates, n_cells, n_entries), or None when the
+        target runs the dense pair sum (no outlier floor, 2-D target, k-nearest truncation requested)."""
+        from . import _device
+        h = self._handle(_device.resolve_device(device))
+        rc, mc, nc, ne = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+        has = _lib.lib().geosss_target_cpd_grid_info(h, C.byref(rc), C.byref(mc), C.byref(nc), C.byref(ne))
+        if has < 0:
+            _lib.check(has)
+        if not has or not (self.dense or self.k >= len(self.source.positions)):
+            return None
+        return {"cutoff": rc.value, "mean_candidates": mc.value, "n_cells": nc.value, "n_entries": ne.value}
+
 
 class CoherentPointDrift(GaussianMixtureModel):
     """GMM plus a uniform outlier component of weight omega (registration.py:166-259)."""

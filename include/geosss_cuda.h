@@ -100,6 +100,12 @@ int geosss_target_create_cpd_projected(int n_t, int n_s, const double* target_xy
  * (3) or (2) host doubles, NULL = none (the `translation` argument of Registration.log_prob / gradient,
  * registration.py:47-59; pointcloud.py:260-264). */
 int geosss_target_cpd_set_translation(geosss_target_t t, const double* translation);
+/* Cell lists of the float32 cutoff kernels (dense sum with an outlier floor, 3-D clouds): returns 1 and fills
+ * the cutoff radius, the mean number of candidate source points a target row meets (instead of n_s), and
+ * the list sizes; 0 when the target uses the dense pair sum (no floor, 2-D target, lists would not pay or do
+ * not fit shared memory).  Replaces the per-call KD-tree of geosss/registration.py:101-109.
+ * GEOSSS_CPD_DENSE=1 in the environment forces the dense pair sum. */
+int geosss_target_cpd_grid_info(geosss_target_t t, double* cutoff, double* mean_candidates, int* n_cells, int* n_entries);
 int geosss_target_dim(geosss_target_t t); /* ambient dimension d of the state */
 int geosss_target_destroy(geosss_target_t t);
 

@@ -116,6 +116,42 @@ def test_cpd_fast_path(golden):
         assert clean >= 0.8 * 6 * steps, (clean, 6 * steps)
 
 
+def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
+    """Cell-list kernels (target rows rotated into the source frame, candidates from the 27-cell neighbourhood)
+    against the dense 214 x 214 pair sum of the same float32 path and against the float64 literal kernel:
+    random rotations, rotations near the optimum, a translation that moves rows out of the grid, a NaN."""
+    g = golden("logprob_cpd")
+    n = len(g["c5_source"])
+    mk = lambda **kw: gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n),
+                                            sigma=1.0, k=20, omega=0.4, **kw)
+    fast, exact = mk(dense=True), mk()
+    info = fast.cutoff_grid_info()
+    assert info is not None and 6.0 < info["cutoff"] < 8.0 and info["mean_candidates"] < 0.25 * n, info
+    assert exact.cutoff_grid_info() is None
+    gen = np.random.default_rng(5)
+    q = gs.sample_sphere(3, 777, seed=3)
+    best = g["c5_q"][int(np.argmax(g["c5_logp"]))]
+    near = best + 0.05 * gen.standard_normal((200, 4))
+    q = np.vstack([q, near / np.linalg.norm(near, axis=1, keepdims=True), best[None]])
+    for shift in (None, np.array([3.0, -2.0, 1.5]), np.array([500.0, 0.0, 0.0])):
+        want = exact.log_prob(q, shift)
+        cells = fast.log_prob(q.astype(F32), shift)
+        monkeypatch.setenv("GEOSSS_CPD_DENSE", "1")
+        dense = fast.log_prob(q.astype(F32), shift)
+        monkeypatch.delenv("GEOSSS_CPD_DENSE")
+        assert np.max(np.abs(cells - want)) <= 1e-3, np.max(np.abs(cells - want))
+        assert np.max(np.abs(cells - dense)) <= 5e-4, np.max(np.abs(cells - dense))
+    assert np.isnan(fast.log_prob(np.array([[np.nan, 0, 0, 1]], dtype=F32)))[0]
+    # sampler: same chains from both kernels until the first accept/reject flip (float32 rounding of the row sums)
+    x0 = gs.sample_sphere(3, 64, seed=9)
+    a = gs.ShrinkageSphericalSliceSampler(fast, x0, 77, dtype="float32", path="fast").sample(6)
+    monkeypatch.setenv("GEOSSS_CPD_DENSE", "1")
+    b = gs.ShrinkageSphericalSliceSampler(mk(dense=True), x0, 77, dtype="float32", path="fast").sample(6)
+    monkeypatch.delenv("GEOSSS_CPD_DENSE")
+    same = np.max(np.abs(a - b), axis=(1, 2)) < 1e-4
+    assert same.mean() >= 0.8, same.mean()
+
+
 def test_logprob_empty_and_ragged(golden):
     g = golden("logprob_vmf")
     pdf = mixture(g["c1_mus"])
