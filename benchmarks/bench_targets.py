@@ -30,11 +30,11 @@ def timed(fn, reps):
     return s.elapsed_time(e) * 1e-3 / reps
 
 
-def c5_target():
+def c5_target(dense=True):
     g = np.load(os.path.join(ROOT, "tests", "golden", "logprob_cpd.npz"))
     n = len(g["c5_source"])
     return gs.CoherentPointDrift(gs.PointCloud(g["c5_target"], np.ones(len(g["c5_target"]))),
-                                 gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=20, omega=0.4, dense=True)
+                                 gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=20, omega=0.4, dense=dense)
 
 
 def cases(quick):
@@ -45,6 +45,7 @@ def cases(quick):
     yield "C4 bingham d=50 diag", gs.random_bingham(50, 300, 0, True, 6982), (1 << 16 if quick else 1 << 20), 20, 1 << 20
     yield "C4 bingham d=50 dense", gs.random_bingham(50, 300, 0, False, 6982), (1 << 16 if quick else 1 << 20), 20, 1 << 20
     yield "C5 cpd 214x214 dense", c5_target(), (1 << 12 if quick else 1 << 15), 5, 1 << 14
+    yield "C5 cpd 214x214 k=20 (scripts/protein_reg3d3d.py as written)", c5_target(False), (1 << 12 if quick else 1 << 15), 5, 1 << 14
 
 
 def main():

@@ -276,8 +276,9 @@ static int target_fast_supported(const geosss_target* t) {
         return gc_smem_bytes(t, gc_params(t)) <= 200 * 1024 ? 0 : -1;
     }
     if (t->kind == TGT_CPD) {
-        // dense sum with a finite outlier floor; the k-nearest truncation stays on the literal path
-        const bool dense = t->k <= 0 || t->k >= t->ns;
+        // a finite outlier floor, and either the dense sum or the cutoff kernels (which also serve the k-nearest
+        // truncation: kernels_cpd_cell.cuh); without the lists the truncation stays on the literal path
+        const bool dense = t->k <= 0 || t->k >= t->ns || cpd_use_grid(t);
         return (dense && t->outlier && std::isfinite(t->log_outlier) && std::isfinite(t->log_const) &&
                 (size_t)CPD_WARPS * 4 * t->ns * sizeof(float) <= 200 * 1024) ? 0 : -1;
     }
@@ -315,13 +316,10 @@ static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a
         const CpdCellGrid g = cpd_grid_now(t);
         const size_t smem = g.smem_bytes();
         const unsigned grid = (unsigned)((a.N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS);
-        if (kind == SHRINK) {
-            CU(cudaFuncSetAttribute(k_sampler_cpd_cell<SHRINK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sampler_cpd_cell<SHRINK><<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, a);
-        } else {
-            CU(cudaFuncSetAttribute(k_sampler_cpd_cell<REJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_sampler_cpd_cell<REJECT><<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, a);
-        }
+        auto kern = kind == SHRINK ? (g.k > 0 ? k_sampler_cpd_cell<SHRINK, true> : k_sampler_cpd_cell<SHRINK, false>)
+                                   : (g.k > 0 ? k_sampler_cpd_cell<REJECT, true> : k_sampler_cpd_cell<REJECT, false>);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, a);
         CU(cudaGetLastError());
         return 0;
     }
@@ -493,6 +491,8 @@ static int build_cpd_grid(geosss_target* t, const double* target, const double* 
     g.base = (float)std::exp(t->log_outlier - m0);
     g.m0 = (float)m0;
     g.beta = (float)t->beta;
+    g.rc2 = (float)((rc / h) * (rc / h));
+    g.k = (t->k <= 0 || t->k >= ns) ? 0 : t->k;
     if (mean_cand > 0.5 * ns || g.smem_bytes() > 200 * 1024 || entry.empty()) return 0;
     std::vector<float4> tgt4(nt);
     for (int l = 0; l < nt; ++l)
@@ -721,8 +721,9 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
                 CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
                 const int64_t want = (N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS;
                 const int64_t cap = (int64_t)sms * (gsmem <= 110 * 1024 ? 2 : 1);
-                CU(cudaFuncSetAttribute(k_logp_cpd_cell, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-                k_logp_cpd_cell<<<(unsigned)(want < cap ? want : cap), CPD_CELL_WARPS * 32, gsmem, st>>>(g, xi, o, N);
+                auto kern = g.k > 0 ? k_logp_cpd_cell<true> : k_logp_cpd_cell<false>;
+                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+                kern<<<(unsigned)(want < cap ? want : cap), CPD_CELL_WARPS * 32, gsmem, st>>>(g, xi, o, N);
                 CU(cudaGetLastError());
                 return 0;
             }

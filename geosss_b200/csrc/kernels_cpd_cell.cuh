@@ -44,6 +44,8 @@ struct CpdCellGrid {
     const float4* tgt4;    // (nt) device: target row and its weight
     float q2, base, m0, beta;  // -0.5 log2(e) h^2 / sigma^2, exp(log_outlier - M0), M0, beta
     float shift[3];
+    float rc2;  // (cutoff / h)^2: squared cutoff radius in cell units
+    int k;      // k-nearest truncation of the reference (registration.py:107-108); <= 0: every source point
     size_t smem_bytes() const { return ((size_t)n_entries + nt) * sizeof(float4) + (size_t)n_cells * sizeof(uint32_t); }
 };
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ CpdCellShared cpd_cell_stage(const CpdCellGrid& g, un
 // f = (R^T / h)(y - t) - org / h, so floor(f) is the cell and |f - e|^2 h^2 the squared distance (h^2 is folded
 // into q2).  A row outside the padded grid is clamped onto a border cell: the candidates it then meets are all
 // farther than h -- legitimate, negligible terms of the dense sum.
-struct CpdWarpLogPCell {
+template <bool KNN> struct CpdWarpLogPCell {
     CpdCellGrid g;
     CpdCellShared s;
 
@@ -103,14 +105,46 @@ struct CpdWarpLogPCell {
             const int cnt = (int)(cw >> CPD_CELL_COUNT_SHIFT);
             const float4* e = s.entry + (cw & ((1u << CPD_CELL_COUNT_SHIFT) - 1u));
             float sum = 0.f;
+            int inside = 0;  // candidates within the cutoff radius (KNN only)
 #pragma unroll 2
             for (int k = sub; k < cnt; k += 4) {
                 const float4 m = e[k];
                 const float e0 = fx - m.x, e1 = fy - m.y, e2 = fz - m.z;
-                sum += fast_ex2(fmaf(fmaf(e0, e0, fmaf(e1, e1, e2 * e2)), g.q2, m.w));
+                const float d2 = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+                if (KNN) inside += d2 < g.rc2 ? 1 : 0;
+                sum += fast_ex2(fmaf(d2, g.q2, m.w));
             }
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            if (KNN) {
+                // The reference sums the k nearest source points only.  With at most k points inside the cutoff
+                // the other members of that set are beyond it (negligible, like the candidates summed here), so
+                // the two sums agree.  With more than k inside, the k nearest are all candidates: keep exactly
+                // those (rank by distance, ties by list position).  Rare: never at the shipped sigma = 1, k = 20.
+                inside += __shfl_xor_sync(0xffffffffu, inside, 1);
+                inside += __shfl_xor_sync(0xffffffffu, inside, 2);
+                const bool crowded = inside > g.k;
+                if (__any_sync(0xffffffffu, crowded)) {
+                    const int n = crowded ? cnt : 0;
+                    float exact = 0.f;
+                    for (int i = sub; i < n; i += 4) {
+                        const float4 mi = e[i];
+                        const float a0 = fx - mi.x, a1 = fy - mi.y, a2 = fz - mi.z;
+                        const float di = fmaf(a0, a0, fmaf(a1, a1, a2 * a2));
+                        int rank = 0;
+                        for (int j = 0; j < n; ++j) {
+                            const float4 mj = e[j];
+                            const float b0 = fx - mj.x, b1 = fy - mj.y, b2 = fz - mj.z;
+                            const float dj = fmaf(b0, b0, fmaf(b1, b1, b2 * b2));
+                            rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+                        }
+                        if (rank < g.k) exact += fast_ex2(fmaf(di, g.q2, mi.w));
+                    }
+                    exact += __shfl_xor_sync(0xffffffffu, exact, 1);
+                    exact += __shfl_xor_sync(0xffffffffu, exact, 2);
+                    if (crowded) sum = exact;
+                }
+            }
             const float row = (g.m0 + 0.6931471805599453f * fast_lg2(g.base + sum)) * y.w;
             if (sub == 0 && l < g.nt) acc += (double)row;
         }
@@ -121,11 +155,11 @@ struct CpdWarpLogPCell {
     }
 };
 
-template <int KIND>
+template <int KIND, bool KNN>
 __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_sampler_cpd_cell(CpdCellGrid g, RunArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    CpdWarpLogPCell f;
+    CpdWarpLogPCell<KNN> f;
     f.g = g;
     f.s = cpd_cell_stage(g, smem_raw);
     const int64_t c = (int64_t)blockIdx.x * CPD_CELL_WARPS + warp;
@@ -168,11 +202,12 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_sampler_cpd_cell(Cpd
 }
 
 // persistent over points: the lists are staged once per block, then each warp walks its share of the points
-static __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_logp_cpd_cell(CpdCellGrid g, const float* __restrict__ q,
+template <bool KNN>
+__global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_logp_cpd_cell(CpdCellGrid g, const float* __restrict__ q,
                                                                        float* __restrict__ out, int64_t N) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
-    CpdWarpLogPCell f;
+    CpdWarpLogPCell<KNN> f;
     f.g = g;
     f.s = cpd_cell_stage(g, smem_raw);
     for (int64_t i = (int64_t)blockIdx.x * CPD_CELL_WARPS + warp; i < N; i += (int64_t)gridDim.x * CPD_CELL_WARPS) {

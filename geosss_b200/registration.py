@@ -4,8 +4,10 @@ Rigid 3D-3D and 3D-2D registration likelihoods on S^3 (geosss/registration.py:19
 ``log_prob`` takes a unit quaternion (x, y, z, w) -- or rows of them, or a 3x3 rotation
 matrix -- and evaluates the coherent-point-drift log-likelihood on the GPU: the source cloud
 is rotated, every target point sees a Gaussian mixture over its k nearest rotated source
-points plus (CPD) a uniform outlier term.  The reference rebuilds a KDTree per call; the
-kernels evaluate all pairs and select the k nearest per row exactly (csrc/targets.cuh).
+points plus (CPD) a uniform outlier term.  The reference rebuilds a KDTree per call.  The float64 /
+literal kernels evaluate all pairs and select the k nearest per row exactly (csrc/targets.cuh); the
+float32 throughput kernels of CPD targets (csrc/kernels_cpd_cell.cuh) rotate the target rows into the
+source frame and read candidate lists from a grid built once, keeping the k-nearest semantics.
 A 2-D target with a ``RotationProjection`` source scores the rotated source projected onto its
 first two coordinates (pointcloud.py:273-293).  ``translation`` is a fixed shift added after the
 rotation, per call as upstream or persistently through the ``translation`` attribute (which the
@@ -66,8 +68,8 @@ class GaussianMixtureModel(Registration):
 
     def __init__(self, target: PointCloud, source: PointCloud, sigma: float = 1.0, k: int = 20, *, beta: float = 1.0,
                  dense: bool = False):
-        """``dense=True`` sums every source point instead of the k nearest (an extension: it is what the
-        float32 throughput kernels evaluate; at the shipped sigma = 1 it equals k = 20 to 5e-12, tested)."""
+        """``dense=True`` sums every source point instead of the k nearest (an extension; at the shipped
+        sigma = 1 it equals k = 20 to 5e-12, tested)."""
         if source.dim != 3 or target.dim not in (2, 3):
             raise NotImplementedError("the device engine handles 3D-3D and 3D-2D registration")
         if (target.dim == 2) != isinstance(source, RotationProjection):
@@ -100,14 +102,14 @@ class GaussianMixtureModel(Registration):
     def cutoff_grid_info(self, device=None):
         """Cell lists the float32 throughput kernels use in place of upstream's per-call KD-tree
         (registration.py:101-109): dict(cutoff, mean_candidates, n_cells, n_entries), or None when the
-        target runs the dense pair sum (no outlier floor, 2-D target, k-nearest truncation requested)."""
+        target has no such lists (no outlier floor, 2-D target, lists too large to pay)."""
         from . import _device
         h = self._handle(_device.resolve_device(device))
         rc, mc, nc, ne = C.c_double(), C.c_double(), C.c_int(), C.c_int()
         has = _lib.lib().geosss_target_cpd_grid_info(h, C.byref(rc), C.byref(mc), C.byref(nc), C.byref(ne))
         if has < 0:
             _lib.check(has)
-        if not has or not (self.dense or self.k >= len(self.source.positions)):
+        if not has:
             return None
         return {"cutoff": rc.value, "mean_candidates": mc.value, "n_cells": nc.value, "n_entries": ne.value}
 

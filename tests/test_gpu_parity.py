@@ -127,7 +127,7 @@ def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
     fast, exact = mk(dense=True), mk()
     info = fast.cutoff_grid_info()
     assert info is not None and 6.0 < info["cutoff"] < 8.0 and info["mean_candidates"] < 0.25 * n, info
-    assert exact.cutoff_grid_info() is None
+    assert exact.cutoff_grid_info() is not None  # k = 20 keeps its meaning on the cutoff kernels (next test)
     gen = np.random.default_rng(5)
     q = gs.sample_sphere(3, 777, seed=3)
     best = g["c5_q"][int(np.argmax(g["c5_logp"]))]
@@ -150,6 +150,30 @@ def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
     monkeypatch.delenv("GEOSSS_CPD_DENSE")
     same = np.max(np.abs(a - b), axis=(1, 2)) < 1e-4
     assert same.mean() >= 0.8, same.mean()
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 20])
+def test_cpd_cutoff_cells_keep_k_nearest_truncation(golden, k):
+    """registration.py:107-108 sums the k nearest rotated source points.  The cutoff kernels reproduce that:
+    rows with more than k points inside the cutoff rank their candidates exactly (small k here forces that
+    branch; at k = 20 it never runs on these clouds).  Checked against the float64 literal kernel, which
+    selects the k nearest of all pairs, and -- for k = 20 -- against the reference's own values."""
+    g = golden("logprob_cpd")
+    n = len(g["c5_source"])
+    pdf = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n),
+                                sigma=1.0, k=k, omega=0.4)
+    gen = np.random.default_rng(k)
+    best = g["c5_q"][int(np.argmax(g["c5_logp"]))]
+    near = best + 0.03 * gen.standard_normal((150, 4))
+    q = np.vstack([gs.sample_sphere(3, 300, seed=k), near / np.linalg.norm(near, axis=1, keepdims=True), g["c5_q"]])
+    want = pdf.log_prob(q)               # float64: literal kernel, exact selection over all pairs
+    got = pdf.log_prob(q.astype(F32))    # float32: cutoff kernels
+    assert np.max(np.abs(got - want)) <= 1e-3, np.max(np.abs(got - want))
+    if k == 20:
+        assert np.max(np.abs(got[-len(g["c5_q"]):] - g["c5_logp"])) <= 1e-3
+    smp = gs.ShrinkageSphericalSliceSampler(pdf, gs.sample_sphere(3, 32, seed=1), 5, dtype="float32")
+    out = smp.sample(4)
+    assert smp.path == "fast" and np.all(np.isfinite(out))
 
 
 def test_logprob_empty_and_ragged(golden):
