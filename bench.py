@@ -235,7 +235,7 @@ def main_ours(a):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f)["k_vmf_fast<5,12,SHRINK>"]
+            tr = json.load(f)["k_vmf_fast<5,10,SHRINK>"]
         if a.sampler == "shrink" and tr["chains"] == N and tr["transitions_per_step"] == T and a.kappa == 100.0:
             traffic = tr["chain_major_quorum_22_default"]["dram_read"] + tr["chain_major_quorum_22_default"]["dram_write"]
     except Exception:
@@ -315,7 +315,7 @@ def main_ours(a):
             torch.cuda.synchronize()
             sec = e0.elapsed_time(e1) * 1e-3 / 10
             gbs = n_pts * (d + 1) * 4 / sec / 1e9
-            lp_roof = {"kernel": "k_logp_tiled<VmfLpConst<5,12>> (TMA bulk-staged tiles, parameters in the constant bank)", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+            lp_roof = {"kernel": "k_logp_tiled<VmfLpConst<K=5,D=12>> (TMA bulk-staged tiles, parameters in the constant bank)", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
                        "frac": gbs / peak, "points_per_s": n_pts / sec, "algorithmic_bytes_per_launch": n_pts * (d + 1) * 4,
                        "avg_launch_ms": sec * 1e3}
             del xs_lp, out_lp
@@ -338,7 +338,7 @@ def main_ours(a):
                         "host_cpus_bound_to_gpu_numa": None if numa_cpus is None else len(numa_cpus), "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
                 "gpu_launches": a.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,D=12,%s>" % a.sampler.upper(),
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "k_vmf_fast<K=5,d=10,%s>" % a.sampler.upper(),
                              "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": avg_launch_s * 1e3,
                              "note": "kernel is instruction-issue/MUFU bound; HBM fraction = retained-sample write traffic"},
                 "roofline_compute": roof_compute, "roofline_log_prob": lp_roof, "cpu_baseline": cpu, "clocks": clk, "mean_rejections_per_transition": rej, "ess": ess,

@@ -374,6 +374,47 @@ def test_fast_path_follows_reference_under_shared_draws(golden, cls, kind, cfg):
     assert clean >= 0.9 * N * n, (clean, N * n)
 
 
+@pytest.mark.parametrize("d", list(range(2, 17)))
+def test_fast_kernel_every_dimension_follows_reference(d):
+    """k_vmf_fast is instantiated per true dimension (2..16): each one against the float64 reference algorithm
+    fed the same Philox draws (the draw layout -- aux words in the last normal block or in their own -- depends
+    on d mod 4), both samplers, K = 3."""
+    mus = 25.0 * gs.sample_sphere(d - 1, 3, seed=100 + d)
+    x0 = gs.sample_sphere(d - 1, 6, seed=d)
+    for cls, kind, n in ((gs.ShrinkageSphericalSliceSampler, samplers.SHRINK, 16), (gs.RejectionSphericalSliceSampler, samplers.REJECT, 8)):
+        smp = cls(mixture(mus), x0, 977 + d, dtype="float32", path="fast")
+        got = smp.sample(n + 1)
+        assert smp.path == "fast"
+        clean = 0
+        for c in range(6):
+            want, _ = oracle_chain(targets.VMFMixture(mus), kind, x0[c], 977 + d, c, n, d, F32)
+            bad = np.nonzero(np.max(np.abs(got[c, 1:] - want), axis=1) > 1e-4)[0]
+            clean += bad[0] if len(bad) else n
+        assert clean >= 0.85 * 6 * n, (d, kind, clean, 6 * n)
+
+
+def test_parked_device_blocks_are_reused_cleanly():
+    """Short-lived samplers (the reference constructs one per sample() call) reuse parked device blocks: a
+    second sampler of the same shape must start from its own state and zeroed counters, results must not
+    depend on what the previous owner left behind, and the cache can be released at any time."""
+    from geosss_b200 import _lib
+    pdf = mixture(30.0 * gs.sample_sphere(4, 3, seed=2))
+    x0 = gs.sample_sphere(4, 257, seed=3)
+    first = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5)
+    a = first.sample(20)
+    rej_a = first.n_reject
+    del first
+    other = gs.ShrinkageSphericalSliceSampler(pdf, gs.sample_sphere(4, 257, seed=4), 6)  # same shape: takes the parked blocks
+    other.sample(7)
+    del other
+    again = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5)
+    b = again.sample(20)
+    assert np.array_equal(a, b) and again.n_reject == rej_a
+    assert _lib.lib().geosss_release_cached_memory() == 0
+    c = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5).sample(20)
+    assert np.array_equal(a, c)
+
+
 def gc_case(golden, cfg):
     """(device pdf, oracle pdf, d) for the great-circle fast kernels."""
     if cfg in ("c4diag", "c4dense", "d10"):
