@@ -275,16 +275,18 @@ def main_ours(a):
         s.sample(T + 1, 0, out=out_host)  # H2D of the initial states, T transitions, D2H of every state
         return s
     e2e_step(1)
-    # raw pinned device->host bandwidth of this box, for context (the e2e number is PCIe-bound)
-    probe = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
-    host_probe = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+    # raw pinned device->host bandwidth into the SAME pinned buffer, all ranks copying at once (the ranks of one host
+    # share its PCIe switches and memory controllers): the ceiling of the e2e number, measured in this run
+    probe = torch.empty(out_host.numel() * 4, dtype=torch.uint8, device=dev)
+    host_probe = out_host.view(-1).view(torch.uint8)
     host_probe.copy_(probe)
-    torch.cuda.synchronize()
+    barrier()
     tp = time.perf_counter()
-    for _ in range(4):
+    for _ in range(2):
         host_probe.copy_(probe, non_blocking=True)
     torch.cuda.synchronize()
-    d2h_gbs = 4 * (64 << 20) / (time.perf_counter() - tp) / 1e9
+    d2h_gbs = 2 * probe.numel() / max_over_ranks(time.perf_counter() - tp) / 1e9
+    del probe
     barrier()
     t0 = time.perf_counter()
     for i in range(a.e2e_steps):
@@ -334,7 +336,7 @@ def main_ours(a):
                 "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(a, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs,
+                        "steps": a.e2e_steps, "pinned_d2h_gbs_this_box": d2h_gbs, "pinned_d2h_probe": "per rank, all ranks at once, same buffer and size as the e2e step",
                         "host_cpus_bound_to_gpu_numa": None if numa_cpus is None else len(numa_cpus), "api": "ShrinkageSphericalSliceSampler(pdf, x0_numpy, seed).sample(T+1, out=pinned)"},
                 "gpu_launches": a.steps,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

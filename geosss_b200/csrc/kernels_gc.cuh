@@ -394,8 +394,7 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
                     zz = fmaf(n, n, zz);
                     if (on_the_fly) pol.accumulate(co, j, xj, n);
                 };
-                for (int b = 0; b < nbn; ++b) {
-                    const U4 w = dr.block(b);
+                auto take_block = [&](int b, const U4& w) {
                     float n0, n1, n2, n3;
                     box_muller_fast(w.x, w.y, n0, n1);
                     box_muller_fast(w.z, w.w, n2, n3);
@@ -405,7 +404,19 @@ __global__ void __launch_bounds__(GC_BLOCK) k_gc_fast(GcParams P, RunArgs a) {
                     if (j + 2 < d) take(j + 2, n2);
                     if (j + 3 < d) take(j + 3, n3);
                     if (b == nbn - 1) { aux0 = w.z; aux1 = w.w; }
+                };
+                // Stored normals (d < 64, dense Bingham): two Philox blocks in flight per iteration -- one block is a
+                // chain of 10 dependent rounds and a scheduler holds ~3 warps (measured: Bingham d=50 diagonal +4 %,
+                // dense +9 %).  With the scores accumulated on the fly (curved vMF d=100) the same change costs 16 %.
+                int b = 0;
+                if (STORE) {
+                    for (; b + 1 < nbn; b += 2) {
+                        const U4 w0 = dr.block(b), w1 = dr.block(b + 1);
+                        take_block(b, w0);
+                        take_block(b + 1, w1);
+                    }
                 }
+                for (; b < nbn; ++b) take_block(b, dr.block(b));
                 if (!aux_in_last) { const U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
                 float pp;
                 if (STORE) {  // |z - zx x|^2 from the stored vector: no cancellation for small d
