@@ -42,7 +42,7 @@ def probe(nbytes, tag):
         host.copy_(d, non_blocking=True)
     torch.cuda.synchronize()
     gbs = 3 * nbytes / (time.perf_counter() - t0) / 1e9
-    rows = gather({"rank": rank, "gbs": round(gbs, 1), "page_node": page_node(host), "cpu": os.sched_getcpu()})
+    rows = gather({"rank": rank, "gbs": round(gbs, 1), "page_node": page_node(host)})
     if rank == 0:
         print(json.dumps({"variant": tag, "per_rank": rows, "total_gbs": round(sum(r["gbs"] for r in rows), 1)}), flush=True)
     del host, d
