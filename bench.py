@@ -317,7 +317,7 @@ def main_ours(a):
             torch.cuda.synchronize()
             sec = e0.elapsed_time(e1) * 1e-3 / 10
             gbs = n_pts * (d + 1) * 4 / sec / 1e9
-            lp_roof = {"kernel": "k_logp_tiled<VmfLpConst<K=5,D=12>> (TMA bulk-staged tiles, parameters in the constant bank)", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+            lp_roof = {"kernel": "k_logp_tiled<VmfLpConst<K=5,d=10>> (TMA bulk-staged tiles, 8-byte row loads, parameters in the constant bank)", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
                        "frac": gbs / peak, "points_per_s": n_pts / sec, "algorithmic_bytes_per_launch": n_pts * (d + 1) * 4,
                        "avg_launch_ms": sec * 1e3}
             del xs_lp, out_lp

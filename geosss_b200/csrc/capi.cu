@@ -214,6 +214,7 @@ struct geosss_sampler {
     double alpha = 0.5;
     int n_leap = 10;
     size_t state_bytes = 0, ws_bytes = 0;  // sizes of the pooled blocks (g_pool)
+    int device = 0;                        // device the blocks live on (current device at creation)
     bool is_mh() const { return kind >= GEOSSS_RWMH; }
     size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
 };
@@ -646,29 +647,18 @@ template <class Policy> static int launch_logp_tiled(const typename Policy::Para
     return Policy::dim(p) > 48 ? launch_logp_tiled_rows<Policy, 64>(p, x, out, N, st) : launch_logp_tiled_rows<Policy, LP_ROWS>(p, x, out, N, st);
 }
 
-template <int K> static int logp_vmf_const_k(int Dp, const VmfFastParams& P, const float* x, float* o, int64_t N, cudaStream_t st) {
-    switch (Dp) {
-        case 4: return launch_logp_tiled<VmfLpConst<K, 4>>(P, x, o, N, st);
-        case 8: return launch_logp_tiled<VmfLpConst<K, 8>>(P, x, o, N, st);
-        case 12: return launch_logp_tiled<VmfLpConst<K, 12>>(P, x, o, N, st);
-        default: return launch_logp_tiled<VmfLpConst<K, 16>>(P, x, o, N, st);
-    }
-}
-
-// small mixtures (d <= 16, K <= 8): parameters in the constant bank
+// small mixtures (d <= 16, K <= 8): parameters in the constant bank (instantiations in logp_vmf_const.cu)
 static int logp_vmf_const(geosss_target* t, const float* x, float* o, int64_t N, cudaStream_t st) {
     const VmfFastParams P = make_vmf_fast_params(t->d, t->K, t->h_mu.data(), t->h_const.data());
-    const int Dp = (t->d + 3) / 4 * 4;
-    switch (t->K) {
-        case 1: return logp_vmf_const_k<1>(Dp, P, x, o, N, st);
-        case 2: return logp_vmf_const_k<2>(Dp, P, x, o, N, st);
-        case 3: return logp_vmf_const_k<3>(Dp, P, x, o, N, st);
-        case 4: return logp_vmf_const_k<4>(Dp, P, x, o, N, st);
-        case 5: return logp_vmf_const_k<5>(Dp, P, x, o, N, st);
-        case 6: return logp_vmf_const_k<6>(Dp, P, x, o, N, st);
-        case 7: return logp_vmf_const_k<7>(Dp, P, x, o, N, st);
-        default: return logp_vmf_const_k<8>(Dp, P, x, o, N, st);
+    if (!g_sm_count) {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
+    const int rc = launch_logp_vmf_const(t->d, t->K, P, x, o, N, g_sm_count, st);
+    if (rc > 0) return fail(GEOSSS_E_CUDA, "log_prob: %s", cudaGetErrorString((cudaError_t)rc));
+    if (rc < 0) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: no constant-bank kernel for this shape");
+    return 0;
 }
 
 static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
@@ -764,6 +754,7 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     auto* s = new (std::nothrow) geosss_sampler();
     if (!s) return fail(GEOSSS_E_NOMEM, "out of host memory");
     s->t = t; s->kind = kind; s->dtype = dtype; s->path = path; s->N = N; s->seed = seed; s->chain0 = chain_offset;
+    if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return fail(GEOSSS_E_CUDA, "sampler_create: no current CUDA device"); }
     const size_t es = s->esize();
     s->state_bytes = (size_t)N * t->d * es;
     cudaError_t e = g_pool.get(&s->state, s->state_bytes);
@@ -791,6 +782,9 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
 
 extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     if (!s) return 0;
+    int cur = s->device;
+    cudaGetDevice(&cur);
+    if (cur != s->device) cudaSetDevice(s->device);  // blocks are parked under (and freed on) the device they live on
     cudaDeviceSynchronize();  // what cudaFree would do: nothing of this sampler is in flight when its blocks are parked
     g_pool.put(s->state, s->state_bytes);
     g_pool.put(s->ws, s->ws_bytes);
@@ -799,6 +793,7 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     if (s->adapt_count) cudaFree(s->adapt_count);
     if (s->n_walk) cudaFree(s->n_walk);
     if (s->momentum) cudaFree(s->momentum);
+    if (cur != s->device) cudaSetDevice(cur);
     delete s;
     return 0;
 }

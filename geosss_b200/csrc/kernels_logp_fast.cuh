@@ -57,24 +57,43 @@ struct LpParams {
 };
 
 // ---- policies: stage parameters, evaluate one row held in shared memory -------------------------
-// vMF mixture with compile-time K and padded D: means and constants sit in the kernel-parameter constant
-// bank (same block as the sampler kernel), so the K*d FMAs per point take them as immediate operands and
-// the only shared-memory traffic is the point itself.
-template <int K, int D> struct VmfLpConst {
+// vMF mixture with compile-time K and dimension DT (the parameter block keeps rows of D = 4 ceil(DT/4) floats):
+// means and constants sit in the kernel-parameter constant bank (same block as the sampler kernel), so the
+// K*d FMAs per point take them as immediate operands and the only shared-memory traffic is the point itself,
+// read with the widest loads the row alignment allows (16 bytes for d % 4 == 0, 8 bytes for even d: with a row
+// stride of d floats and lane-per-row access, 8-byte loads of even-d rows are conflict-free per half-warp where
+// scalar loads were 2-way conflicted).
+template <int K, int DT> struct VmfLpConst {
     using Params = VmfFastParams;
+    static constexpr int D = (DT + 3) / 4 * 4;
     static __host__ __device__ size_t smem_floats(const Params&) { return 0; }
-    static __host__ __device__ int dim(const Params& p) { return p.d; }
+    static __host__ __device__ int dim(const Params&) { return DT; }
     __device__ void stage(const Params&, float*) {}
     __device__ __forceinline__ float eval(const Params& P, const float* row) const {
-        const int d = P.d;
+        float x[DT];
+        if (DT % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j + 3 < DT; j += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(row + j);
+                x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+            }
+        } else if (DT % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j + 1 < DT; j += 2) {
+                const float2 v = *reinterpret_cast<const float2*>(row + j);
+                x[j] = v.x; x[j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < DT; ++j) x[j] = row[j];
+        }
         float s[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) s[k] = P.c[k];
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const float xj = j < d ? row[j] : 0.f;
+        for (int j = 0; j < DT; ++j) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) s[k] = fmaf(P.mu[k * D + j], xj, s[k]);
+            for (int k = 0; k < K; ++k) s[k] = fmaf(P.mu[k * D + j], x[j], s[k]);
         }
         float m = s[0];
 #pragma unroll
@@ -86,6 +105,10 @@ template <int K, int D> struct VmfLpConst {
         return (m + fast_lg2(acc)) * 0.6931471805599453f;
     }
 };
+
+// K = 1..8 x d = 2..16 instantiations of k_logp_tiled<VmfLpConst> live in their own translation unit
+// (logp_vmf_const.cu).  Returns 0, a negative GEOSSS_E_* code, or a positive cudaError_t.
+int launch_logp_vmf_const(int d, int K, const VmfFastParams& P, const float* x, float* out, int64_t N, int sm_count, cudaStream_t st);
 
 // Rows are read with 16-byte shared loads whenever d is a multiple of 4.  With lane-per-row access the row
 // stride decides the bank conflicts: a stride of 4 * odd floats is conflict-free for 16-byte loads, so rows
