@@ -7,12 +7,20 @@ namespace geosss {
 template <int K, int DT> static int launch_kd(const VmfFastParams& P, const float* x, float* out, int64_t N, int sm_count, cudaStream_t st) {
     using Policy = VmfLpConst<K, DT>;
     const size_t smem = (size_t)LP_STAGES * LP_ROWS * lp_row_stride(DT) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(k_logp_tiled<Policy, LP_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the shared-memory opt-in and the occupancy query cost tens of microseconds: once per kernel and device
+    static int per_sm_dev[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logp_tiled<Policy, LP_ROWS>, LP_ROWS, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
+    int per_sm = (dev >= 0 && dev < 64) ? per_sm_dev[dev] : 0;
+    if (per_sm == 0) {
+        e = cudaFuncSetAttribute(k_logp_tiled<Policy, LP_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logp_tiled<Policy, LP_ROWS>, LP_ROWS, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) per_sm = 1;
+        if (dev >= 0 && dev < 64) per_sm_dev[dev] = per_sm;
+    }
     const int64_t n_tiles = (N + LP_ROWS - 1) / LP_ROWS;
     int64_t grid = (int64_t)sm_count * per_sm;  // persistent: a multiple of the SM count
     if (grid > n_tiles) grid = n_tiles;
