@@ -148,6 +148,20 @@ def test_public_surface_is_a_superset_of_the_reference(golden):
     assert all(hasattr(hmc, a) for a in ref["attributes"]["SphericalHMC"]) and hmc.state.shape == (6,)
 
 
+def test_initial_state_is_kept_not_copied_and_never_written():
+    """mcmc.py:43 stores the caller's array; the device engine keeps that (no per-call host copy of N x d
+    states) and only ever replaces its reference, so the caller's array is never modified."""
+    pdf = gs.MixtureModel([gs.VonMisesFisher(10.0 * m) for m in gs.sample_sphere(3, 2, seed=1)])
+    x0 = gs.sample_sphere(3, 5, seed=2)
+    keep = x0.copy()
+    smp = gs.ShrinkageSphericalSliceSampler(pdf, x0, 3)
+    assert np.shares_memory(smp.state, x0)
+    smp.state = np.roll(x0, 1, axis=0)
+    assert np.array_equal(x0, keep) and not np.shares_memory(smp.state, x0)
+    one = gs.ShrinkageSphericalSliceSampler(pdf, x0[0].astype(np.float32), 3)  # other dtypes are converted (a copy)
+    assert one.state.dtype == np.float64 and one.state.shape == (4,)
+
+
 def test_numa_binding_helper_is_harmless_without_a_gpu():
     from geosss_b200 import distributed
     before = os.sched_getaffinity(0)
