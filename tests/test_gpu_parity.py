@@ -583,6 +583,30 @@ def test_marginals_match_exact_vmf_mixture(cls, path):
         assert ks_2samp_p(got @ m, ref @ m) > 1e-3
 
 
+def test_cpd_cutoff_sampler_has_the_law_of_the_literal_float64_sampler(golden):
+    """Own-RNG check of the registration sampler: the float32 cutoff kernel and the float64 literal kernel (exact
+    k-nearest over all pairs) are the same Markov kernel, so after the same number of transitions from the same
+    initial states their chains have the same law -- compared through log p and the rotation angle of the final
+    states (two-sample KS, alpha = 1e-3), with independent seeds."""
+    g = golden("logprob_cpd")
+    n = len(g["c5_source"])
+    pdf = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n),
+                                sigma=1.0, k=20, omega=0.4)
+    N, steps = 1024, 25
+    x0 = gs.sample_sphere(3, N, seed=31)
+    fast = gs.ShrinkageSphericalSliceSampler(pdf, x0, 101, dtype="float32")
+    a = fast.sample(1, steps)[:, 0].astype(float)
+    lit = gs.ShrinkageSphericalSliceSampler(pdf, x0, 202, dtype="float64")
+    b = lit.sample(1, steps)[:, 0]
+    assert fast.path == "fast" and lit.path == "literal"
+    la, lb = pdf.log_prob(a), pdf.log_prob(b)
+    assert ks_2samp_p(la, lb) > 1e-3, (np.mean(la), np.mean(lb))
+    assert ks_2samp_p(np.abs(a[:, 3]), np.abs(b[:, 3])) > 1e-3
+    # both climbed: the initial states sit near log p = -2475
+    assert np.mean(la) > np.mean(pdf.log_prob(x0)) + 20 and np.mean(lb) > np.mean(pdf.log_prob(x0)) + 20
+    assert abs(fast.n_reject - lit.n_reject) < 0.1 * lit.n_reject
+
+
 # ------------------------------------------------------------------ diagnostics
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_device_ess_matches_oracle(dtype):
