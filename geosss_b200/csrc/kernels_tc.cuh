@@ -29,7 +29,7 @@
 namespace geosss {
 
 constexpr int TC_ROWS = 128;     // UMMA M
-constexpr int TC_THREADS = 256;  // two threads per row: each splits half of the K steps and reduces half of the columns
+constexpr int TC_THREADS = 256;  // two threads per row: thread (row, half) splits K steps [4 half, 4 half + 4) and reduces the same 32 columns
 constexpr int TC_N = 64;      // UMMA N: d padded to 64 columns of A
 constexpr int TC_MAX_D = 64;
 
@@ -128,25 +128,39 @@ static __global__ void __launch_bounds__(TC_THREADS, 2) k_logp_bingham_tc(TcPara
             for (int64_t i = tid; i < (int64_t)tile_floats; i += TC_THREADS) raw[i] = i < n_here ? x[row0 * d + i] : 0.f;
             __syncthreads();
         }
-        // split this thread's row into the operand layout: one 16-byte store per (k step, half)
+        // split this thread's half of its row into the operand layout: one 16-byte store per (k step, chunk).  Thread
+        // (row, half) takes k steps [4 half, 4 half + 4) = columns [32 half, 32 half + 32) -- the columns of Y it reduces
+        // in the epilogue -- and keeps the values in registers (xv) for that dot product; even d reads the row with
+        // 8-byte loads (row stride d floats: conflict-free per half-warp, scalar loads were 2-way conflicted).
+        float xv[32];
         {
             const float* row = raw + (size_t)row_t * d;
             const size_t rbase = (size_t)(row_t >> 3) * 32 + (size_t)(row_t & 7) * 4;  // floats
-            const int k_mid = (ksteps + 1) >> 1;
-            for (int kk = half ? k_mid : 0; kk < (half ? ksteps : k_mid); ++kk) {
+            const bool even = (d & 1) == 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int kk = 4 * half + i;
 #pragma unroll
                 for (int chunk = 0; chunk < 2; ++chunk) {
-                    float v[4], h[4], l[4];
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int k0 = kk * 8 + chunk * 4;
+                    if (kk < ksteps) {
+                        if (even) {
+                            if (k0 < d) { const float2 a = *reinterpret_cast<const float2*>(row + k0); v[0] = a.x; v[1] = a.y; }
+                            if (k0 + 2 < d) { const float2 b2 = *reinterpret_cast<const float2*>(row + k0 + 2); v[2] = b2.x; v[3] = b2.y; }
+                        } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = kk * 8 + chunk * 4 + q;
-                        v[q] = k < d ? row[k] : 0.f;
-                        h[q] = to_tf32(v[q]);
-                        l[q] = to_tf32(v[q] - h[q]);
+                            for (int q = 0; q < 4; ++q) if (k0 + q < d) v[q] = row[k0 + q];
+                        }
+                        float h[4], l[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { h[q] = to_tf32(v[q]); l[q] = to_tf32(v[q] - h[q]); }
+                        const size_t off = kk * umma_kstep_floats(TC_ROWS) + (size_t)chunk * (TC_ROWS * 4) + rbase;
+                        *reinterpret_cast<float4*>(Xh + off) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(Xl + off) = make_float4(l[0], l[1], l[2], l[3]);
                     }
-                    const size_t off = kk * umma_kstep_floats(TC_ROWS) + (size_t)chunk * (TC_ROWS * 4) + rbase;
-                    *reinterpret_cast<float4*>(Xh + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4*>(Xl + off) = make_float4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) xv[i * 8 + chunk * 4 + q] = v[q];
                 }
             }
         }
@@ -179,9 +193,8 @@ static __global__ void __launch_bounds__(TC_THREADS, 2) k_logp_bingham_tc(TcPara
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        // epilogue: thread <-> row <-> TMEM lane; 64 accumulator columns in four 16-column loads; the row itself
-        // is read back as hi + lo from the operand buffers (16-byte loads), `raw` already belongs to the next tile
-        const size_t rbase = (size_t)(row_t >> 3) * 32 + (size_t)(row_t & 7) * 4;
+        // epilogue: thread <-> row <-> TMEM lane; its 32 accumulator columns in two 16-column loads, dotted with the row
+        // values kept in registers since the split (`raw` already belongs to the next tile)
         float q = 0.f;
 #pragma unroll
         for (int cc = 0; cc < TC_N / 2; cc += 16) {
@@ -198,15 +211,13 @@ static __global__ void __launch_bounds__(TC_THREADS, 2) k_logp_bingham_tc(TcPara
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const int n0 = c0 + j4;  // four columns = one (k step, half) of the operand layout
+                    const int n0 = c0 + j4;  // four columns = one (k step, chunk) of the operand layout
                     if (n0 < 8 * ksteps) {
-                        const size_t off = (size_t)(n0 >> 3) * umma_kstep_floats(TC_ROWS) + (size_t)((n0 >> 2) & 1) * (TC_ROWS * 4) + rbase;
-                        const float4 h = *reinterpret_cast<const float4*>(Xh + off), l = *reinterpret_cast<const float4*>(Xl + off);
                         const float4 bv = *reinterpret_cast<const float4*>(bs + n0);
-                        q = fmaf(__uint_as_float(r[j4]) + bv.x, h.x + l.x, q);
-                        q = fmaf(__uint_as_float(r[j4 + 1]) + bv.y, h.y + l.y, q);
-                        q = fmaf(__uint_as_float(r[j4 + 2]) + bv.z, h.z + l.z, q);
-                        q = fmaf(__uint_as_float(r[j4 + 3]) + bv.w, h.w + l.w, q);
+                        q = fmaf(__uint_as_float(r[j4]) + bv.x, xv[cc + j4], q);
+                        q = fmaf(__uint_as_float(r[j4 + 1]) + bv.y, xv[cc + j4 + 1], q);
+                        q = fmaf(__uint_as_float(r[j4 + 2]) + bv.z, xv[cc + j4 + 2], q);
+                        q = fmaf(__uint_as_float(r[j4 + 3]) + bv.w, xv[cc + j4 + 3], q);
                     }
                 }
             }
