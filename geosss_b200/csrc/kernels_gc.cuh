@@ -146,7 +146,17 @@ struct CurvedGc {
             c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]); c.gu[4 * q + 3] = fmaf(k.w, uj, c.gu[4 * q + 3]);
         }
     }
-    // knots . x only (standalone log_prob: no direction)
+    // knots . x only (standalone log_prob: no direction), knot quads as a compile-time count: the caller selects the
+    // instantiation once per row (warp-uniform), so the padded quads cost nothing (predicated-off FMAs still issue)
+    template <int NQ> __device__ __forceinline__ void accumulate_x_n(Coef& c, int j, float xj) const {
+        const float4* col = reinterpret_cast<const float4*>(knotsT + j * (NQ << 2));
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float4 k = col[q];
+            c.gx[4 * q] = fmaf(k.x, xj, c.gx[4 * q]);         c.gx[4 * q + 1] = fmaf(k.y, xj, c.gx[4 * q + 1]);
+            c.gx[4 * q + 2] = fmaf(k.z, xj, c.gx[4 * q + 2]); c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]);
+        }
+    }
     __device__ __forceinline__ void accumulate_x(Coef& c, int j, float xj) const {
         const int nq = (M + 3) >> 2;
         const float4* col = reinterpret_cast<const float4*>(knotsT + j * (nq << 2));

@@ -228,16 +228,25 @@ struct CurvedLp {
         q.a0 = p.a0; q.a1 = p.a1; q.a2 = p.a2; q.d = p.d; q.M = p.M; q.kappa = p.kappa;
         g.stage(q, sm);
     }
-    __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
-        CurvedGc::Coef co;
-        g.begin(co);
+    template <int NQ> __device__ __forceinline__ void scores(CurvedGc::Coef& co, const float* row) const {
         if ((g.d & 3) == 0) {
             for (int j = 0; j < g.d; j += 4) {
                 const float4 xv = *reinterpret_cast<const float4*>(row + j);
-                g.accumulate_x(co, j, xv.x); g.accumulate_x(co, j + 1, xv.y); g.accumulate_x(co, j + 2, xv.z); g.accumulate_x(co, j + 3, xv.w);
+                g.accumulate_x_n<NQ>(co, j, xv.x); g.accumulate_x_n<NQ>(co, j + 1, xv.y);
+                g.accumulate_x_n<NQ>(co, j + 2, xv.z); g.accumulate_x_n<NQ>(co, j + 3, xv.w);
             }
         } else {
-            for (int j = 0; j < g.d; ++j) g.accumulate_x(co, j, row[j]);
+            for (int j = 0; j < g.d; ++j) g.accumulate_x_n<NQ>(co, j, row[j]);
+        }
+    }
+    __device__ __forceinline__ float eval(const LpParams&, const float* row) const {
+        CurvedGc::Coef co;
+        g.begin(co);
+        switch ((g.M + 3) >> 2) {  // warp-uniform: knot quads
+            case 1: scores<1>(co, row); break;
+            case 2: scores<2>(co, row); break;
+            case 3: scores<3>(co, row); break;
+            default: scores<4>(co, row); break;
         }
         return g.kappa * g.best_dot(co, 1.f, 0.f);
     }
