@@ -304,7 +304,14 @@ template <class Policy> static int launch_gc(const geosss_target* t, int kind, c
 }
 
 static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a, cudaStream_t st) {
-    if (t->kind == TGT_VMF_MIX && fast_supported(t->kind, t->d, t->K, t->single)) return launch_gc<VmfGc>(t, kind, a, st);
+    if (t->kind == TGT_VMF_MIX && fast_supported(t->kind, t->d, t->K, t->single)) {
+        switch ((t->K + 3) / 4) {  // one instantiation per component-quad count
+            case 1: return launch_gc<VmfGcT<1, true>>(t, kind, a, st);
+            case 2: return launch_gc<VmfGcT<2, true>>(t, kind, a, st);
+            case 3: return launch_gc<VmfGcT<3, true>>(t, kind, a, st);
+            default: return launch_gc<VmfGcT<4, true>>(t, kind, a, st);
+        }
+    }
     if (t->kind == TGT_VMF_MIX) {
         int rc = launch_fast(t->kind, kind, t->d, t->K, t->h_mu.data(), t->h_const.data(), a, st);
         if (rc > 0) return fail(GEOSSS_E_CUDA, "run: %s", cudaGetErrorString((cudaError_t)rc));
@@ -312,7 +319,14 @@ static int target_launch_fast(const geosss_target* t, int kind, const RunArgs& a
         return 0;
     }
     if (t->kind == TGT_BINGHAM) return launch_gc<BinghamGc>(t, kind, a, st);
-    if (t->kind == TGT_CURVED_VMF) return launch_gc<CurvedGc>(t, kind, a, st);
+    if (t->kind == TGT_CURVED_VMF) {
+        switch ((t->M + 3) / 4) {  // one instantiation per knot-quad count
+            case 1: return launch_gc<CurvedGcT<1, true>>(t, kind, a, st);
+            case 2: return launch_gc<CurvedGcT<2, true>>(t, kind, a, st);
+            case 3: return launch_gc<CurvedGcT<3, true>>(t, kind, a, st);
+            default: return launch_gc<CurvedGcT<4, true>>(t, kind, a, st);
+        }
+    }
     if (t->kind == TGT_CPD && !target_fast_supported(t) && cpd_use_grid(t)) {
         const CpdCellGrid g = cpd_grid_now(t);
         const size_t smem = g.smem_bytes();

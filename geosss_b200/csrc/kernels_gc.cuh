@@ -106,8 +106,12 @@ struct BinghamGc {
     __device__ __forceinline__ float logp_x(const Coef& c) const { return c.qxx + c.bx; }
 };
 
-struct CurvedGc {
-    struct Coef { float gx[GC_MAX_KNOTS], gu[GC_MAX_KNOTS], best0; };
+// QUADS = knot quads held per chain (scores in registers: 8 QUADS floats).  EXACT: the target has exactly QUADS quads, so the
+// quad loops carry no run-time guards (the sampler kernels are instantiated per quad count: less code, no dead quad);
+// CurvedGc = <4, false> serves any M <= 16 with guards (standalone log_prob).
+template <int QUADS, bool EXACT> struct CurvedGcT {
+    static constexpr int MAXK = 4 * QUADS;
+    struct Coef { float gx[MAXK], gu[MAXK], best0; };
     __device__ __forceinline__ bool needs_vector() const { return false; }
     const float* knotsT;  // shared (d, MP): knotsT[j * MP + m], MP = 4 ceil(M/4), zero for m >= M (float4 loads)
     const float* ca;      // shared (M-1)
@@ -132,13 +136,13 @@ struct CurvedGc {
     }
     __device__ __forceinline__ void begin(Coef& c) const {
 #pragma unroll
-        for (int m = 0; m < GC_MAX_KNOTS; ++m) { c.gx[m] = 0.f; c.gu[m] = 0.f; }
+        for (int m = 0; m < MAXK; ++m) { c.gx[m] = 0.f; c.gu[m] = 0.f; }
     }
     __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
-        const int nq = (M + 3) >> 2;  // warp-uniform
+        const int nq = EXACT ? QUADS : (M + 3) >> 2;  // warp-uniform
         const float4* col = reinterpret_cast<const float4*>(knotsT + j * (nq << 2));
 #pragma unroll
-        for (int q = 0; q < GC_MAX_KNOTS / 4; ++q) if (q < nq) {
+        for (int q = 0; q < QUADS; ++q) if (EXACT || q < nq) {
             const float4 k = col[q];
             c.gx[4 * q] = fmaf(k.x, xj, c.gx[4 * q]);         c.gu[4 * q] = fmaf(k.x, uj, c.gu[4 * q]);
             c.gx[4 * q + 1] = fmaf(k.y, xj, c.gx[4 * q + 1]); c.gu[4 * q + 1] = fmaf(k.y, uj, c.gu[4 * q + 1]);
@@ -158,10 +162,10 @@ struct CurvedGc {
         }
     }
     __device__ __forceinline__ void accumulate_x(Coef& c, int j, float xj) const {
-        const int nq = (M + 3) >> 2;
+        const int nq = EXACT ? QUADS : (M + 3) >> 2;
         const float4* col = reinterpret_cast<const float4*>(knotsT + j * (nq << 2));
 #pragma unroll
-        for (int q = 0; q < GC_MAX_KNOTS / 4; ++q) if (q < nq) {
+        for (int q = 0; q < QUADS; ++q) if (EXACT || q < nq) {
             const float4 k = col[q];
             c.gx[4 * q] = fmaf(k.x, xj, c.gx[4 * q]);         c.gx[4 * q + 1] = fmaf(k.y, xj, c.gx[4 * q + 1]);
             c.gx[4 * q + 2] = fmaf(k.z, xj, c.gx[4 * q + 2]); c.gx[4 * q + 3] = fmaf(k.w, xj, c.gx[4 * q + 3]);
@@ -170,15 +174,15 @@ struct CurvedGc {
     // coefficients were accumulated against the raw normals z; the direction is u = inp (z - zx x)
     __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
 #pragma unroll
-        for (int m = 0; m < GC_MAX_KNOTS; ++m) c.gu[m] = inp * fmaf(-zx, c.gx[m], c.gu[m]);
+        for (int m = 0; m < MAXK; ++m) c.gu[m] = inp * fmaf(-zx, c.gx[m], c.gu[m]);
     }
     // another lane's coefficients (cooperative reject batches)
     __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
         Coef o;
-        const int nq = (M + 3) >> 2;
+        const int nq = EXACT ? QUADS : (M + 3) >> 2;
 #pragma unroll
-        for (int m = 0; m < GC_MAX_KNOTS; ++m) {
-            if ((m >> 2) < nq) { o.gx[m] = __shfl_sync(0xffffffffu, c.gx[m], src); o.gu[m] = __shfl_sync(0xffffffffu, c.gu[m], src); }
+        for (int m = 0; m < MAXK; ++m) {
+            if (EXACT || (m >> 2) < nq) { o.gx[m] = __shfl_sync(0xffffffffu, c.gx[m], src); o.gu[m] = __shfl_sync(0xffffffffu, c.gu[m], src); }
             else { o.gx[m] = 0.f; o.gu[m] = 0.f; }
         }
         o.best0 = __shfl_sync(0xffffffffu, c.best0, src);
@@ -189,7 +193,7 @@ struct CurvedGc {
         float ga = fmaf(cs, c.gx[0], sn * c.gu[0]);
         float best = 0.f, best_clipped = -INFINITY;
 #pragma unroll
-        for (int m = 1; m < GC_MAX_KNOTS; ++m) if (m < M) {
+        for (int m = 1; m < MAXK; ++m) if (m < M) {
             const float gb = fmaf(cs, c.gx[m], sn * c.gu[m]);
             const float p2 = (gb - ga * ca[m - 1]) * isa[m - 1];
             const bool inside = p2 >= 0.f && fmaf(ga, sa[m - 1], -p2 * ca[m - 1]) >= 0.f;
@@ -206,13 +210,18 @@ struct CurvedGc {
     __device__ __forceinline__ float delta(const Coef& c, float cs, float sn) const { return kappa * (best_dot(c, cs, sn) - c.best0); }
     __device__ __forceinline__ float logp_x(const Coef& c) const { return kappa * c.best0; }
 };
+using CurvedGc = CurvedGcT<GC_MAX_KNOTS / 4, false>;
+
 
 // vMF mixture of any dimension that fits shared memory and up to GC_MAX_K components (the register-
 // resident k_vmf_fast covers d <= 16, K <= 8): scores mu_k . y = c A_k + s B_k as in kernels_fast.cuh,
 // log p(y) - log p(x) through a max-shifted base-2 log-sum-exp.
 constexpr int GC_MAX_K = 16;
-struct VmfGc {
-    struct Coef { float A[GC_MAX_K], B[GC_MAX_K], lp2; };
+// QUADS / EXACT as for CurvedGcT: the sampler kernels are instantiated per component-quad count (2 QUADS x 4 scores in
+// registers instead of 32, no guarded quads).
+template <int QUADS, bool EXACT> struct VmfGcT {
+    static constexpr int MAXK = 4 * QUADS;
+    struct Coef { float A[MAXK], B[MAXK], lp2; };
     __device__ __forceinline__ bool needs_vector() const { return false; }
     const float* muT;  // shared (d, KP): muT[j * KP + k] * log2(e), KP = 4 ceil(K/4), zero padded
     const float* c2;   // shared (KP): constants * log2(e), -inf for the padding
@@ -233,13 +242,13 @@ struct VmfGc {
     }
     __device__ __forceinline__ void begin(Coef& c) const {
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) { c.A[k] = 0.f; c.B[k] = 0.f; }
+        for (int k = 0; k < MAXK; ++k) { c.A[k] = 0.f; c.B[k] = 0.f; }
     }
     __device__ __forceinline__ void accumulate(Coef& c, int j, float xj, float uj) const {
-        const int nq = (K + 3) >> 2;
+        const int nq = EXACT ? QUADS : (K + 3) >> 2;
         const float4* col = reinterpret_cast<const float4*>(muT + j * (nq << 2));
 #pragma unroll
-        for (int q = 0; q < GC_MAX_K / 4; ++q) if (q < nq) {
+        for (int q = 0; q < QUADS; ++q) if (EXACT || q < nq) {
             const float4 m = col[q];
             c.A[4 * q] = fmaf(m.x, xj, c.A[4 * q]);         c.B[4 * q] = fmaf(m.x, uj, c.B[4 * q]);
             c.A[4 * q + 1] = fmaf(m.y, xj, c.A[4 * q + 1]); c.B[4 * q + 1] = fmaf(m.y, uj, c.B[4 * q + 1]);
@@ -249,16 +258,16 @@ struct VmfGc {
     }
     __device__ __forceinline__ void fixup(Coef& c, float zx, float inp) const {
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) c.B[k] = inp * fmaf(-zx, c.A[k], c.B[k]);
+        for (int k = 0; k < MAXK; ++k) c.B[k] = inp * fmaf(-zx, c.A[k], c.B[k]);
     }
     __device__ __forceinline__ float lse2(const Coef& c, float cs, float sn) const {
         const int KP = (K + 3) & ~3;
-        float e[GC_MAX_K], m = -INFINITY;
+        float e[MAXK], m = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) if (k < KP) { e[k] = fmaf(cs, c.A[k], fmaf(sn, c.B[k], c2[k])); m = fmaxf(m, e[k]); }
+        for (int k = 0; k < MAXK; ++k) if (EXACT || k < KP) { e[k] = fmaf(cs, c.A[k], fmaf(sn, c.B[k], c2[k])); m = fmaxf(m, e[k]); }
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) if (k < KP) acc += fast_ex2(e[k] - m);
+        for (int k = 0; k < MAXK; ++k) if (EXACT || k < KP) acc += fast_ex2(e[k] - m);
         return m + fast_lg2(acc);
     }
     template <class V> __device__ __forceinline__ void finish(Coef& c, V, V) const { c.lp2 = lse2(c, 1.f, 0.f); }
@@ -266,16 +275,18 @@ struct VmfGc {
     __device__ __forceinline__ float logp_x(const Coef& c) const { return 0.6931471805599453f * c.lp2; }
     __device__ __forceinline__ Coef fetch(const Coef& c, int src) const {
         Coef o;
-        const int nq = (K + 3) >> 2;
+        const int nq = EXACT ? QUADS : (K + 3) >> 2;
 #pragma unroll
-        for (int k = 0; k < GC_MAX_K; ++k) {
-            if ((k >> 2) < nq) { o.A[k] = __shfl_sync(0xffffffffu, c.A[k], src); o.B[k] = __shfl_sync(0xffffffffu, c.B[k], src); }
+        for (int k = 0; k < MAXK; ++k) {
+            if (EXACT || (k >> 2) < nq) { o.A[k] = __shfl_sync(0xffffffffu, c.A[k], src); o.B[k] = __shfl_sync(0xffffffffu, c.B[k], src); }
             else { o.A[k] = 0.f; o.B[k] = 0.f; }
         }
         o.lp2 = __shfl_sync(0xffffffffu, c.lp2, src);
         return o;
     }
 };
+using VmfGc = VmfGcT<GC_MAX_K / 4, false>;
+
 
 // column view of one lane's vector in shared memory
 struct SCol {
