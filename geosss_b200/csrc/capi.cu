@@ -246,7 +246,7 @@ static bool gc_store_normals(const geosss_target* t) { return t->d < 64 || (t->k
 static size_t gc_smem_bytes(const geosss_target* t, const GcParams& p) {
     const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p)
                        : t->kind == TGT_VMF_MIX ? VmfGc::smem_floats(p) : CurvedGc::smem_floats(p);
-    return ((gc_store_normals(t) ? 2 : 1) * (size_t)t->d * GC_BLOCK + pol) * sizeof(float);
+    return ((gc_store_normals(t) ? 2 : 1) * (size_t)t->d * gc_block(gc_store_normals(t)) + pol) * sizeof(float);
 }
 
 static GcParams gc_params(const geosss_target* t) {
@@ -287,9 +287,10 @@ static int target_fast_supported(const geosss_target* t) {
 }
 
 template <class Policy, int KIND, bool STORE> static int launch_gc_one(const GcParams& p, size_t smem, const RunArgs& a, cudaStream_t st) {
-    const unsigned grid = (unsigned)((a.N + GC_BLOCK - 1) / GC_BLOCK);
+    constexpr int BLOCK = gc_block(STORE);
+    const unsigned grid = (unsigned)((a.N + BLOCK - 1) / BLOCK);
     CU(cudaFuncSetAttribute(k_gc_fast<Policy, KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gc_fast<Policy, KIND, STORE><<<grid, GC_BLOCK, smem, st>>>(p, a);
+    k_gc_fast<Policy, KIND, STORE><<<grid, BLOCK, smem, st>>>(p, a);
     CU(cudaGetLastError());
     return 0;
 }
