@@ -443,12 +443,16 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
                 for (; b < nbn; ++b) take_block(b, dr.block(b));
                 if (!aux_in_last) { const U4 w = dr.block(nbn); aux0 = w.x; aux1 = w.y; }
                 float pp;
-                if (STORE) {  // |z - zx x|^2 from the stored vector: no cancellation for small d
-                    pp = 0.f;
-                    for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); pp = fmaf(p, p, pp); }
+                if (STORE) {
+                    if (d < 32) {  // |z - zx x|^2 from the stored vector: no cancellation for small d
+                        pp = 0.f;
+                        for (int j = 0; j < d; ++j) { const float p = fmaf(-zx, xs[j], us[j]); pp = fmaf(p, p, pp); }
+                    } else {
+                        pp = fmaf(-zx, zx, zz);  // x is unit and zx^2 ~ 1 << |z|^2 ~ d: one pass over x and z less (d = 50: -7 % instructions)
+                    }
                     if (!on_the_fly) for (int j = 0; j < d; ++j) pol.accumulate(co, j, xs[j], us[j]);
                 } else {
-                    pp = fmaf(-zx, zx, zz);  // x is unit; used for d >= 64 only, where zx^2 << |z|^2
+                    pp = fmaf(-zx, zx, zz);  // x is unit; d >= 64, where zx^2 << |z|^2
                 }
                 u_scale = rsqrtf(pp);
                 zx_keep = zx;
