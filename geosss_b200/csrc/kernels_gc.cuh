@@ -342,7 +342,12 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
     bool inloop = false, pending = false, moved = false;
 
     auto finish_transition = [&]() {
-        // apply the accepted move, renormalise (|x| would otherwise drift in fp32), store
+        // apply the accepted move and store.  x' = c x + s u is a unit vector up to fp32 rounding (x, u orthonormal), so the
+        // renormalisation only has to stop the drift: it runs on every 16th transition of the chain, by the GLOBAL step index
+        // (split-invariant, and warp-uniform in lock-step) -- one pass over x less on the other fifteen.
+        // Only in the kernels with on-the-fly scores (d >= 64: C3 +7 %): in the stored-normals instantiation the same edit made the
+        // dense-Bingham path 17 % slower (same work, different code generation; A/B on one box), so those keep renormalising always.
+        const bool renorm = STORE || ((a.step0 + (uint64_t)(t - 1)) & 15u) == 0u;
         float xx = 0.f;
         if (moved) {
             const float beta = sn * u_scale, alpha = fmaf(-beta, zx_keep, cs);  // x' = alpha x + beta z
@@ -361,11 +366,13 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
                     if (j + 3 < d) { v = fmaf(alpha, xs[j + 3], beta * n3); xs[j + 3] = v; xx = fmaf(v, v, xx); }
                 }
             }
-        } else {
+        } else if (renorm) {
             for (int j = 0; j < d; ++j) xx = fmaf(xs[j], xs[j], xx);
         }
-        const float inx = rsqrtf(xx);
-        for (int j = 0; j < d; ++j) xs[j] *= inx;
+        if (renorm) {
+            const float inx = rsqrtf(xx);
+            for (int j = 0; j < d; ++j) xs[j] *= inx;
+        }
         rej_total += (unsigned)r;
         rej_window += (unsigned)r;
         if (++since_keep == (int)a.thin) {
