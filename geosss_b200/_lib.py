@@ -42,6 +42,7 @@ SIGNATURES = {
     "geosss_sampler_run_layout": (_i, [_p, _i64, _i64, _i, _i64, _i64, _p, _p, _p, _p]),
     "geosss_sampler_run_tape": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     "geosss_sampler_steps_done": (_i64, [_p]),
+    "geosss_sampler_trace_out": (_i, [_p, _pd, _p]),
     "geosss_sampler_destroy": (_i, [_p]),
     "geosss_release_cached_memory": (_i, []),
     "geosss_sampler_set_state_host": (_i, [_p, _pd]),

@@ -210,6 +210,8 @@ struct geosss_sampler {
     unsigned long long* n_walk = nullptr;
     void* momentum = nullptr;
     void* momenta_out = nullptr;
+    void* fdir = nullptr;   // (d) direction of the scalar test function, sampler dtype (device), see geosss_sampler_trace_out
+    void* fout = nullptr;   // where the next run calls write its trace
     int64_t adapt_total = 0;
     double alpha = 0.5;
     int n_leap = 10;
@@ -815,6 +817,7 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     if (s->adapt_count) cudaFree(s->adapt_count);
     if (s->n_walk) cudaFree(s->n_walk);
     if (s->momentum) cudaFree(s->momentum);
+    if (s->fdir) cudaFree(s->fdir);
     if (cur != s->device) cudaSetDevice(cur);
     delete s;
     return 0;
@@ -831,6 +834,27 @@ extern "C" int geosss_sampler_get_state(geosss_sampler_t s, void* x, uint64_t* n
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x) CU(cudaMemcpyAsync(x, s->state, (size_t)s->N * s->t->d * s->esize(), cudaMemcpyDeviceToDevice, st));
     if (n_reject) CU(cudaMemcpyAsync(n_reject, s->n_reject, (size_t)s->N * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// Scalar test function f(x) = x . direction, evaluated by the sampler kernels at every kept state (4 or 8 bytes per
+// kept transition instead of d): what the ESS diagnostics need from runs too large to retain (scripts/ess_curve_vMF.py:267,
+// scripts/bingham.py:50-52).  Sticky like geosss_sampler_mh_momenta_out: applies to the run calls that follow.
+extern "C" int geosss_sampler_trace_out(geosss_sampler_t s, const double* direction_host, void* trace_out) {
+    if (!s) return fail(GEOSSS_E_INVALID, "trace_out: bad arguments");
+    if (!trace_out) { s->fout = nullptr; return 0; }
+    if (!direction_host) return fail(GEOSSS_E_INVALID, "trace_out: a direction is needed with an output buffer");
+    if (s->t->kind == TGT_CPD) return fail(GEOSSS_E_UNSUPPORTED, "trace_out: registration chains report log_prob (logp_out) instead");
+    const size_t d = (size_t)s->t->d;
+    if (!s->fdir) CU(cudaMalloc(&s->fdir, d * sizeof(double)));
+    if (s->dtype == GEOSSS_F64) {
+        CU(cudaMemcpy(s->fdir, direction_host, d * 8, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float> f(d);
+        for (size_t i = 0; i < d; ++i) f[i] = (float)direction_host[i];
+        CU(cudaMemcpy(s->fdir, f.data(), d * 4, cudaMemcpyHostToDevice));
+    }
+    s->fout = trace_out;
     return 0;
 }
 
@@ -883,7 +907,7 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     a.N = s->N; a.n_steps = n_steps; a.thin = thin; a.seed = s->seed; a.chain0 = s->chain0; a.step0 = s->step;
     a.state = s->state; a.ws = s->ws; a.n_reject = s->n_reject;
     a.stepsize = s->stepsize; a.adapt_count = s->adapt_count; a.n_walk = s->n_walk; a.momentum = s->momentum;
-    a.momenta_out = s->momenta_out; a.adapt_total = s->adapt_total; a.alpha = s->alpha; a.n_leap = s->n_leap;
+    a.momenta_out = s->momenta_out; a.fdir = s->fdir; a.fout = s->fout; a.adapt_total = s->adapt_total; a.alpha = s->alpha; a.n_leap = s->n_leap;
     // quorum of the persistent bracket loop (kernels_fast.cuh); tuned on B200, see DESIGN.md
     a.ss_step = s->N * (int64_t)s->t->d; a.ss_chain = s->t->d; a.sl_step = s->N; a.sl_chain = 1;  // step-major
     a.quorum = s->kind == GEOSSS_SHRINK ? 22 : 20;

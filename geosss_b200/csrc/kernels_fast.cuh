@@ -75,6 +75,15 @@ template <int DT> __device__ __forceinline__ void store_row(float* __restrict__ 
     }
 }
 
+// f(x) = x . v, the scalar test function whose trace the diagnostics use (first coordinate: scripts/ess_mixture_vMF.py:233;
+// x . mode: scripts/bingham.py:50-52); v is read through the uniform path (same address for every lane)
+template <int DT> __device__ __forceinline__ float test_function(const float (&x)[DT], const float* __restrict__ v) {
+    float f = 0.f;
+#pragma unroll
+    for (int j = 0; j < DT; ++j) f = fmaf(x[j], __ldg(v + j), f);
+    return f;
+}
+
 constexpr int FAST_BATCH = 4;  // proposals evaluated together = words of one Philox block
 
 // log2 p at the accepted point: level2 + log2(S) is exact for it; when S overflowed fp32 the
@@ -178,6 +187,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
                         if (samples) store_row<DT>(samples + (k * a.ss_step + c * a.ss_chain), x);
                         if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp2 * LN2;
                         if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
+                        if (a.fout) static_cast<float*>(a.fout)[k * a.sl_step + c * a.sl_chain] = test_function<DT>(x, static_cast<const float*>(a.fdir));
                         rej_window = 0;
                     }
                     pending = false;
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(FAST_BLOCK) k_vmf_fast(const __grid_constant__
                 if (samples) store_row<DT>(samples + (k * a.ss_step + c * a.ss_chain), x);
                 if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp2 * LN2;
                 if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
+                if (a.fout) static_cast<float*>(a.fout)[k * a.sl_step + c * a.sl_chain] = test_function<DT>(x, static_cast<const float*>(a.fdir));
             }
         }
 #pragma unroll

@@ -385,6 +385,12 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
             }
             if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp_x + (moved ? dl_acc : 0.f);
             if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
+            if (a.fout) {  // scalar test function x . v (see test_function, kernels_fast.cuh)
+                const float* v = static_cast<const float*>(a.fdir);
+                float f = 0.f;
+                for (int j = 0; j < d; ++j) f = fmaf(xs[j], __ldg(v + j), f);
+                static_cast<float*>(a.fout)[k * a.sl_step + c * a.sl_chain] = f;
+            }
             rej_window = 0;
         }
         pending = false;

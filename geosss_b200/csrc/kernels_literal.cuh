@@ -70,6 +70,8 @@ struct RunArgs {
     void* samples;        // (n_keep, N, d) or null
     void* logp;           // (n_keep, N) or null
     uint32_t* nrej;       // (n_keep, N) rejections of each kept transition (thin == 1) or null
+    const void* fdir;     // (d) direction v of the scalar test function f(x) = x . v, sampler dtype, or null
+    void* fout;           // (n_keep, N) trace of f at the kept states (scalar layout like logp) or null
     unsigned long long* n_reject;  // (N) running totals
     int* status;          // (N) tape mode: 0 ok, 1 tape exhausted; may be null
     int quorum;           // fast path: lanes that must wait before a warp runs the prologue (32 = lock-step)
@@ -139,6 +141,12 @@ __global__ void __launch_bounds__(LANE_BLOCK) k_sampler_lane(P p, RunArgs a) {
             }
             if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
             if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = rej_window;
+            if (a.fout) {
+                const T* v = static_cast<const T*>(a.fdir);
+                T f_ = 0;
+                for (int j = 0; j < d; ++j) f_ += x[j] * v[j];
+                static_cast<T*>(a.fout)[k * a.sl_step + c * a.sl_chain] = f_;
+            }
             rej_window = 0;
         }
     }

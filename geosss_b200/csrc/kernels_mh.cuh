@@ -78,6 +78,12 @@ __global__ void __launch_bounds__(LANE_BLOCK) k_mh_lane(P p, int kind, RunArgs a
             }
             if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
             if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = acc_window;
+            if (a.fout) {
+                const T* dir = static_cast<const T*>(a.fdir);
+                T f_ = 0;
+                for (int j = 0; j < d; ++j) f_ += x[j] * dir[j];
+                static_cast<T*>(a.fout)[k * a.sl_step + c * a.sl_chain] = f_;
+            }
             acc_window = 0;
         }
     }

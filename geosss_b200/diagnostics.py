@@ -86,6 +86,100 @@ def ess(samples, direction=None, max_lag=None, group=None, chain_major=True):
     return ess_from_partials(part.cpu().numpy(), n, int(total.item()))
 
 
+def _tau_bulk(acov_sum, mean_sum, mean_sq_sum, n_draws, n_chains):
+    """Integrated autocorrelation time from all-reduced partial sums with the truncation rules of
+    ``arviz.ess`` (Geyer's initial positive sequence on the pair sums rho(2k) + rho(2k+1), then the initial
+    monotone sequence; Vehtari et al. 2021, section 3.2).  Returns (tau, exhausted): ``exhausted`` when the
+    lags supplied ended before a pair sum turned non-positive (the caller then asks the device for more)."""
+    n, m = float(n_draws), float(n_chains)
+    acov = np.asarray(acov_sum, dtype=float) / m
+    L = len(acov)
+    mean_var = acov[0] * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n
+    if n_chains > 1:
+        var_plus += (mean_sq_sum - mean_sum * mean_sum / m) / (m - 1.0)
+    rho = 1.0 - (mean_var - acov) / var_plus
+    rho[0] = 1.0
+    # pair k >= 1 is formed while its predecessor is positive and 2k - 1 < n - 3; the last pair formed (index J)
+    # contributes only its even lag
+    J, last_pair, exhausted = 0, rho[0] + rho[1], False
+    while 2 * (J + 1) - 1 < n_draws - 3 and last_pair > 0.0:
+        if 2 * (J + 1) + 1 >= L:
+            exhausted = True
+            break
+        J += 1
+        last_pair = rho[2 * J] + rho[2 * J + 1]
+    if J == 0:
+        tau = 0.0
+    else:
+        full = np.minimum.accumulate(rho[0:2 * J:2] + rho[1:2 * J:2])  # monotone: running minimum of the pair sums
+        even = rho[2 * J]
+        tau = -1.0 + 2.0 * float(full.sum()) + (even if last_pair >= 0.0 else max(even, 0.0))
+    return max(tau, 1.0 / math.log10(m * n)), exhausted
+
+
+def bulk_ess(trace, group=None, relative=False):
+    """Rank-normalised split bulk-ESS of a scalar trace, the estimator the upstream scripts obtain from
+    ``arviz.ess`` (default method "bulk"; scripts/bingham.py:28-70, scripts/ess_curve_vMF.py:97-130,
+    scripts/vMF_diagnostics.py:451-492), after Vehtari et al. (2021): every chain is split in two halves, the
+    draws are replaced by the normal scores of their ranks over ALL draws of all chains, the autocovariances
+    of the half chains are accumulated on the GPU (``csrc/diag.cuh``) and the initial-monotone-sequence
+    estimator finishes on the host.
+
+    ``trace``: CUDA tensor ``(n_chains, n_draws)`` -- e.g. ``sampler.sample_trace(...)`` or
+    ``samples[..., 0]``.  With ``torch.distributed`` initialised the ranks are taken over the chains of all
+    processes (all_gather of the scalar traces) and the partial sums are all-reduced, so every process
+    returns the ESS of all chains.  Returns ESS, or ESS / (chains x draws) with ``relative``."""
+    import torch.distributed as dist
+    if not (isinstance(trace, torch.Tensor) and trace.is_cuda and trace.dim() == 2):
+        raise ValueError("bulk_ess needs a CUDA tensor (n_chains, n_draws); there is no CPU fallback")
+    N, n = trace.shape
+    half = n // 2
+    if half < 4:
+        raise ValueError("bulk_ess needs at least 8 draws per chain")
+    local = torch.cat([trace[:, :half], trace[:, n - half:]], dim=0).to(torch.float32).contiguous()  # (2N, half)
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        counts = torch.zeros(world, dtype=torch.int64, device=trace.device)
+        counts[rank] = local.shape[0]
+        dist.all_reduce(counts, group=group)
+        biggest = int(counts.max())
+        pad = local if local.shape[0] == biggest else torch.cat([local, local.new_zeros(biggest - local.shape[0], half)])
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        everything = torch.cat([p[:int(c)] for p, c in zip(parts, counts)])
+        first = int(counts[:rank].sum())
+    else:
+        everything, first = local, 0
+    # fractional ranks over all draws (ties share the mean of their ranks), then normal scores
+    flat = everything.reshape(-1)
+    S = flat.numel()
+    srt, order = torch.sort(flat)
+    new_run = torch.ones(S, dtype=torch.bool, device=flat.device)
+    new_run[1:] = srt[1:] != srt[:-1]
+    run_first = torch.nonzero(new_run).squeeze(1)
+    run_last = torch.cat([run_first[1:], run_first.new_tensor([S])]) - 1
+    run_id = torch.cumsum(new_run, 0) - 1
+    mean_rank = 0.5 * (run_first + run_last).to(torch.float64)[run_id] + 1.0
+    ranks = torch.empty(S, dtype=torch.float64, device=flat.device)
+    ranks[order] = mean_rank
+    z = torch.special.ndtri((ranks - 0.375) / (S + 0.25)).to(torch.float32).reshape(everything.shape)
+    mine = z[first:first + local.shape[0]].contiguous().unsqueeze(-1)  # (2N, half, 1): this process's half chains
+    m_total = everything.shape[0]
+    lags = min(half, 128)
+    while True:
+        part = ess_partials(mine, np.ones(1), lags, chain_major=True)
+        if distributed:
+            dist.all_reduce(part, group=group)
+        p = part.cpu().numpy()
+        tau, exhausted = _tau_bulk(p[:lags], p[lags], p[lags + 1], half, m_total)
+        if not exhausted or lags >= half:
+            break
+        lags = min(half, 2 * lags)
+    return 1.0 / tau if relative else m_total * half / tau
+
+
 def path_stats(samples, modes=None, sign_labels=False, group=None, chain_major=True):
     """One pass over retained draws on the GPU: label populations, hops and geodesic steps.
 

@@ -174,15 +174,51 @@ class Sampler:
         self._run_device(1, None)
         return self.state.copy()
 
-    def _run_device(self, n_steps, samples, thin=1, logp=None, nrej=None, chain_major=False, chain_stride=0):
+    def _run_device(self, n_steps, samples, thin=1, logp=None, nrej=None, chain_major=False, chain_stride=0,
+                    trace=None, direction=None):
         h = self._sampler()
+        lib = _lib.lib()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().geosss_sampler_run_layout(
-                h, n_steps, thin, _lib.CHAIN_MAJOR if chain_major else _lib.STEP_MAJOR, chain_stride, 0,
-                None if samples is None else samples.data_ptr(),
-                None if logp is None else logp.data_ptr(), None if nrej is None else nrej.data_ptr(),
-                _device.stream_ptr(self.device)))
+            if trace is not None:
+                v = np.ascontiguousarray(direction, dtype=float)
+                assert v.shape == (self.d,)
+                _lib.check(lib.geosss_sampler_trace_out(h, _lib.dptr(v), trace.data_ptr()))
+            try:
+                _lib.check(lib.geosss_sampler_run_layout(
+                    h, n_steps, thin, _lib.CHAIN_MAJOR if chain_major else _lib.STEP_MAJOR, chain_stride, 0,
+                    None if samples is None else samples.data_ptr(),
+                    None if logp is None else logp.data_ptr(), None if nrej is None else nrej.data_ptr(),
+                    _device.stream_ptr(self.device)))
+            finally:
+                if trace is not None:
+                    _lib.check(lib.geosss_sampler_trace_out(h, None, None))
         self.rng.steps_done += n_steps
+
+    def sample_trace(self, n_samples, direction=None, burnin=0, thin=1, *, out=None):
+        """Trace of the scalar test function ``f(x) = x . direction`` (default: the first coordinate) at
+        ``n_samples`` successive kept states of every chain, WITHOUT retaining the states: ``(N, n_samples)`` CUDA
+        tensor of the sampler's dtype (``(n_samples,)`` for one chain).  This is what the upstream ESS scripts slice out
+        of fully retained chains (scripts/ess_mixture_vMF.py:233, scripts/ess_curve_vMF.py:267; ``x . mode`` in
+        scripts/bingham.py:50-52); written by the sampler kernels, 4 bytes per kept transition instead of 4 d.
+        ``burnin`` transitions run first (a float is a fraction of ``n_samples``), then ``thin`` transitions per kept state."""
+        assert n_samples > 0 and thin >= 1
+        burnin = determine_burnin(n_samples, burnin)
+        self._sampler()
+        v = np.zeros(self.d)
+        if direction is None:
+            v[0] = 1.0
+        else:
+            v[:] = np.asarray(direction, dtype=float)
+        shape = (self.N, n_samples)
+        if out is None:
+            out = torch.empty(shape, dtype=self._tdtype, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != self._tdtype or not out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CUDA {self._tdtype} tensor of shape {shape}")
+        if burnin:
+            self._run_device(burnin, None)
+        self._run_device(n_samples * thin, None, thin=thin, chain_major=True, trace=out, direction=v)
+        self._sync_counters()
+        return out[0] if self._single else out
 
     def sample(self, n_samples, burnin=0, return_all_samples=False, *, out=None):
         """Markov chain(s) of the requested length (mcmc.py:55-77).

@@ -133,6 +133,12 @@ int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* 
 int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, int64_t thin, int layout,
                               int64_t chain_stride, int64_t scalar_chain_stride, void* samples_out,
                               void* logp_out, uint32_t* nrej_out, void* stream);
+/* Scalar test function f(x) = x . direction (direction: d float64 on the host), written for every kept state of the
+ * run calls that follow into trace_out (device, sampler dtype, same scalar layout as logp_out: (n_keep, N), or
+ * (N, n_keep) with CHAIN_MAJOR).  trace_out == NULL switches it off.  Replaces retaining (n, N, d) samples for the
+ * ESS of a coordinate / of x . mode (reference: scripts/ess_mixture_vMF.py:233, scripts/ess_curve_vMF.py:267,
+ * scripts/bingham.py:50-52, where the full chains are kept and sliced afterwards). */
+int geosss_sampler_trace_out(geosss_sampler_t s, const double* direction_host, void* trace_out);
 /* Parity mode: draws come from a flat float64 tape per chain, in the order the reference consumes
  * them (d normals, level uniform, [bracket uniform,] one uniform per proposal; next transition).
  * tape_offsets: (N + 1) int64.  status: (N) 0 ok / 1 tape exhausted early, or NULL. */

@@ -1,6 +1,10 @@
 """
-CPU baseline worker: the float64 oracle port of the reference samplers, one independent chain
-per process (oracle; used only by bench.py's cpu_baseline / --impl reference legs).
+CPU baseline worker, one independent chain per process (used only by bench.py's cpu_baseline /
+--impl reference legs).  When ``oracle/_ref`` holds the upstream package (``oracle/build_ref.py``, run by
+``__graft_entry__.build()`` in the build container) the chains are run by the REFERENCE ITSELF, unmodified:
+``geosss.ShrinkageSphericalSliceSampler(pdf, x0, seed).sample(n)`` (geosss/mcmc.py:335-401) on targets built by
+the reference's own constructors -- ``kind`` "reference".  Otherwise the float64 oracle port of the same
+samplers runs -- ``kind`` "port".
 
 Follows BASELINE.md section 3: chains seeded from SeedSequence(48385).spawn, initial states
 from sample_sphere, BLAS/OpenMP threads pinned to 1, wall-clock with perf_counter.
@@ -25,8 +29,63 @@ def build_target(workload):
     raise ValueError(name)
 
 
+def reference_dir():
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = os.path.join(here, "_ref")
+    return ref if os.path.isdir(os.path.join(ref, "geosss")) and not os.environ.get("GEOSSS_CPU_PORT") else None
+
+
+def kind_name():
+    return "reference" if reference_dir() else "port"
+
+
+def build_reference_target(gs, workload):
+    """The same targets through the upstream constructors (scripts/mixture_vMF.py:406-411, scripts/bingham.py:123-131,
+    scripts/curve_vMF.py:577-582, scripts/protein_reg3d3d.py:561-595)."""
+    name = workload["name"]
+    if name == "vmf_mixture":
+        modes = gs.sample_sphere(workload["d"] - 1, workload["K"], seed=1234)
+        return gs.MixtureModel([gs.VonMisesFisher(workload["kappa"] * m) for m in modes])
+    if name == "bingham":
+        return gs.random_bingham(workload["d"], workload["vmax"], 0, workload.get("eigensystem", True), 6982)
+    if name == "curved_vmf":
+        from geosss.spherical_curve import SlerpCurve, brownian_curve
+        from geosss.distributions import CurvedVonMisesFisher
+        return CurvedVonMisesFisher(SlerpCurve(brownian_curve(10, workload["d"], 0.5, seed=4562)), workload["kappa"])
+    if name == "cpd":
+        from geosss.pointcloud import PointCloud
+        from geosss.registration import CoherentPointDrift
+        data = np.load(os.path.join(reference_dir(), "data", "protein_registration.npz"))
+        target = PointCloud(data["target"], weights=None)
+        source = PointCloud(data["source"], weights=np.ones(len(data["source"])) / len(data["source"]))
+        return CoherentPointDrift(target, source, float(data["sigma"]), 20, omega=float(data["prob_outlier"]))
+    raise ValueError(name)
+
+
+def run_chain_reference(args):
+    """One chain run by the upstream package.  Returns (transitions, rejections, seconds, trace of x0)."""
+    workload, kind, proc_index, n_transitions = args
+    import sys
+    ref = reference_dir()
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import geosss as gs
+    pdf = build_reference_target(gs, workload)
+    child = np.random.SeedSequence(48385).spawn(proc_index + 1)[proc_index]
+    init_seed = np.random.SeedSequence(48485).spawn(proc_index + 1)[proc_index]
+    d = workload["d"] if workload["name"] != "cpd" else 4
+    x0 = gs.sample_sphere(d - 1, seed=init_seed)
+    cls = gs.ShrinkageSphericalSliceSampler if kind == 1 else gs.RejectionSphericalSliceSampler
+    smp = cls(pdf, x0, seed=child)
+    t0 = time.perf_counter()
+    out = smp.sample(n_transitions + 1)
+    return n_transitions, smp.n_reject, time.perf_counter() - t0, np.asarray(out)[1:, 0].copy()
+
+
 def run_chain(args):
     """One chain of ``n_transitions`` steps. Returns (transitions, rejections, seconds)."""
+    if reference_dir():
+        return run_chain_reference(args)
     workload, kind, proc_index, n_transitions = args
     from . import samplers, sphere
     pdf = build_target(workload)
@@ -53,11 +112,11 @@ def run_all_cores(workload, kind, n_transitions, n_procs=None):
         wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     out = {"value": total / wall, "cores": n_procs, "wall_s": wall, "transitions": total,
-           "mean_rejections": sum(r[1] for r in res) / total}
-    try:  # ESS of the first coordinate over the CPU chains, same estimator as the GPU arm
+           "mean_rejections": sum(r[1] for r in res) / total, "kind": kind_name()}
+    try:  # bulk ESS of the first coordinate over the CPU chains, same estimator as the GPU arm
         from . import ess
         trace = np.stack([r[3] for r in res])
-        rel = ess.ess_multichain(trace, min(trace.shape[1] // 2, 400)) / trace.size
+        rel = ess.bulk_ess(trace, relative=True)
         out["relative_ess_x0"] = float(rel)
         out["ess_per_sec"] = float(rel * out["value"])
     except Exception as exc:
@@ -66,5 +125,11 @@ def run_all_cores(workload, kind, n_transitions, n_procs=None):
 
 
 def _warm(_):
+    if reference_dir():
+        import sys
+        if reference_dir() not in sys.path:
+            sys.path.insert(0, reference_dir())
+        import geosss  # noqa: F401
+        return 0
     from . import samplers, sphere, targets  # noqa: F401
     return 0

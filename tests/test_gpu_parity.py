@@ -6,10 +6,15 @@ the float64 oracle fed the same draws.  Nothing here reads /root/reference.
 Stated tolerances:
   float64  log_prob <= 1e-12 * max(1, |logp|);  CPD <= 5e-12 abs;  tape trajectories <= 1e-12
            abs with identical per-step rejection counts
-  float32  log_prob <= 1e-5 * max(1, |logp|) (curved vMF 2e-5);  CPD <= 1e-3 abs;  trajectories
-           <= 1e-4 abs up to the first accept/reject flip
+  float32  log_prob <= 1e-5 * max(1, |logp|);  CPD <= 1e-3 abs;  trajectories <= 1e-4 abs STRICTLY
+           before the first accept/reject flip of a chain (a flip = the per-transition rejection count
+           differs from the float64 reference algorithm fed the same draws); the flip count per 1000
+           transitions is printed, appended to gpurun_out/flips.jsonl and bounded per test
   own-RNG marginals: Kolmogorov-Smirnov against exact draws at alpha = 1e-3
 """
+
+import json
+import os
 
 import numpy as np
 import pytest
@@ -30,6 +35,66 @@ def rel_err(got, want):
 
 def mixture(mus, weights=None):
     return gs.MixtureModel([gs.VonMisesFisher(m) for m in mus], weights)
+
+
+def oracle_of(pdf):
+    """The float64 numpy restatement (oracle/targets.py) of a device target."""
+    if isinstance(pdf, gs.MixtureModel):
+        return targets.VMFMixture(np.stack([p.mu for p in pdf.pdfs]), pdf.weights)
+    if isinstance(pdf, gs.VonMisesFisher):
+        return targets.SingleVMF(pdf.mu)
+    if isinstance(pdf, gs.BinghamFisher):
+        return targets.Bingham(pdf.A, pdf.b)
+    if isinstance(pdf, gs.Bingham):
+        return targets.Bingham(pdf.A)
+    if isinstance(pdf, gs.CurvedVonMisesFisher):
+        return targets.CurvedVMF(pdf.curve.knots, pdf.kappa)
+    raise TypeError(type(pdf))
+
+
+def run_with_rejections(smp, n):
+    """n transitions through the C ABI: states (N, n, d) and per-transition rejection counts (N, n)."""
+    smp._sampler()
+    buf = torch.empty((smp.N, n, smp.d), dtype=smp._tdtype, device=smp.device)
+    nrej = torch.zeros((smp.N, n), dtype=torch.int32, device=smp.device)
+    smp._run_device(n, buf, nrej=nrej, chain_major=True)
+    torch.cuda.synchronize()
+    return buf.cpu().numpy(), nrej.cpu().numpy()
+
+
+class FlipCount:
+    """Accept/reject flips of float32 chains against the float64 reference algorithm fed the same draws.
+    A chain is compared up to its first flip (first transition whose rejection count differs); before it the
+    states must agree to `tol`, strictly.  rate() = flipped chains per 1000 compared transitions."""
+
+    def __init__(self, name, tol=1e-4):
+        self.name, self.tol, self.flips, self.compared, self.max_err = name, tol, 0, 0, 0.0
+
+    def add(self, got, nrej, want, rej_want):
+        n = len(rej_want)
+        diff = np.nonzero(np.asarray(nrej[:n]) != np.asarray(rej_want))[0]
+        upto = int(diff[0]) if len(diff) else n
+        if upto:
+            err = float(np.max(np.abs(got[:upto] - want[:upto])))
+            self.max_err = max(self.max_err, err)
+            assert err <= self.tol, (self.name, "deviation before any flip", err, upto)
+        self.flips += 1 if len(diff) else 0
+        self.compared += upto + (1 if len(diff) else 0)
+
+    def rate(self):
+        return 1000.0 * self.flips / max(self.compared, 1)
+
+    def check(self, max_per_1000):
+        rec = {"test": self.name, "flips": self.flips, "transitions_compared": self.compared,
+               "flips_per_1000_transitions": round(self.rate(), 4), "max_abs_err_before_flip": self.max_err, "bound": max_per_1000}
+        print("FLIPS", json.dumps(rec))
+        try:
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open(os.path.join("gpurun_out", "flips.jsonl"), "a") as f:
+                f.write(json.dumps(rec) + "\n")
+        except OSError:
+            pass
+        assert self.rate() <= max_per_1000, rec
 
 
 def c5_target(golden, k=20):
@@ -71,7 +136,9 @@ def test_logprob_bingham_curved(golden, dtype, tol):
     g = golden("logprob_curved")
     for tag in ("c3", "d10", "d3"):
         pdf = gs.CurvedVonMisesFisher(gs.SlerpCurve(g[f"{tag}_knots"]), 500.0)
-        assert rel_err(pdf.log_prob(g[f"{tag}_x"].astype(dtype)), g[f"{tag}_logp"]) <= (tol if dtype == F64 else 2e-5)
+        err = rel_err(pdf.log_prob(g[f"{tag}_x"].astype(dtype)), g[f"{tag}_logp"])
+        print(f"curved log_prob {tag} {np.dtype(dtype).name}: max rel err {err:.3g}")
+        assert err <= tol, (tag, err)
 
 
 @pytest.mark.parametrize("dtype,tol", [(F64, 5e-12), (F32, 1e-3)])
@@ -103,17 +170,15 @@ def test_cpd_fast_path(golden):
     assert np.max(np.abs(got - g["c5_logp"])) <= 1e-3
     ora = targets.CPD(g["c5_target"], g["c5_source"], sigma=1.0, k=20, omega=0.4, source_weights=np.ones(n) / n)
     x0 = gs.sample_sphere(3, 6, seed=17)
+    fc = FlipCount("cpd_fast_dense_c5", tol=2e-4)
     for cls, kind, steps in ((gs.ShrinkageSphericalSliceSampler, samplers.SHRINK, 12), (gs.RejectionSphericalSliceSampler, samplers.REJECT, 4)):
         smp = cls(pdf, x0, 4242, dtype="float32", path="fast")
-        out = smp.sample(steps + 1)
+        got, nrej = run_with_rejections(smp, steps)
         assert smp.path == "fast"
-        clean = 0
         for c in range(6):
-            want, _ = oracle_chain(ora, kind, x0[c], 4242, c, steps, 4, F32)
-            err = np.max(np.abs(out[c, 1:] - want), axis=1)
-            bad = np.nonzero(err > 2e-4)[0]
-            clean += bad[0] if len(bad) else steps
-        assert clean >= 0.8 * 6 * steps, (clean, 6 * steps)
+            want, rej = oracle_chain(ora, kind, x0[c], 4242, c, steps, 4, F32)
+            fc.add(got[c], nrej[c], want, rej)
+    fc.check(25.0)  # row sums near -2400 in float32: a proposal within ~2e-4 of the level can flip
 
 
 def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
@@ -142,14 +207,16 @@ def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
         assert np.max(np.abs(cells - want)) <= 1e-3, np.max(np.abs(cells - want))
         assert np.max(np.abs(cells - dense)) <= 5e-4, np.max(np.abs(cells - dense))
     assert np.isnan(fast.log_prob(np.array([[np.nan, 0, 0, 1]], dtype=F32)))[0]
-    # sampler: same chains from both kernels until the first accept/reject flip (float32 rounding of the row sums)
-    x0 = gs.sample_sphere(3, 64, seed=9)
-    a = gs.ShrinkageSphericalSliceSampler(fast, x0, 77, dtype="float32", path="fast").sample(6)
-    monkeypatch.setenv("GEOSSS_CPD_DENSE", "1")
-    b = gs.ShrinkageSphericalSliceSampler(mk(dense=True), x0, 77, dtype="float32", path="fast").sample(6)
-    monkeypatch.delenv("GEOSSS_CPD_DENSE")
-    same = np.max(np.abs(a - b), axis=(1, 2)) < 1e-4
-    assert same.mean() >= 0.8, same.mean()
+    # sampler on the cutoff kernels against the float64 reference algorithm (KD-tree k = 20) fed the same draws
+    x0 = gs.sample_sphere(3, 16, seed=9)
+    ora = targets.CPD(g["c5_target"], g["c5_source"], sigma=1.0, k=20, omega=0.4, source_weights=np.ones(n) / n)
+    smp = gs.ShrinkageSphericalSliceSampler(fast, x0, 77, dtype="float32", path="fast")
+    got, nrej = run_with_rejections(smp, 6)
+    fc = FlipCount("cpd_cutoff_cells_c5_shrink", tol=2e-4)
+    for c in range(16):
+        want_c, rej_c = oracle_chain(ora, samplers.SHRINK, x0[c], 77, c, 6, 4, F32)
+        fc.add(got[c], nrej[c], want_c, rej_c)
+    fc.check(25.0)
 
 
 @pytest.mark.parametrize("k", [1, 3, 8, 20])
@@ -166,7 +233,9 @@ def test_cpd_cutoff_cells_keep_k_nearest_truncation(golden, k):
     best = g["c5_q"][int(np.argmax(g["c5_logp"]))]
     near = best + 0.03 * gen.standard_normal((150, 4))
     q = np.vstack([gs.sample_sphere(3, 300, seed=k), near / np.linalg.norm(near, axis=1, keepdims=True), g["c5_q"]])
-    want = pdf.log_prob(q)               # float64: literal kernel, exact selection over all pairs
+    ora = targets.CPD(g["c5_target"], g["c5_source"], sigma=1.0, k=k, omega=0.4, source_weights=np.ones(n) / n)
+    want = ora.log_prob(q)               # float64 numpy restatement: KD-tree query of the k nearest (registration.py:101-109)
+    assert np.max(np.abs(pdf.log_prob(q) - want)) <= 5e-12 * 1e3  # float64 literal kernel: exact selection over all pairs
     got = pdf.log_prob(q.astype(F32))    # float32: cutoff kernels
     assert np.max(np.abs(got - want)) <= 1e-3, np.max(np.abs(got - want))
     if k == 20:
@@ -195,7 +264,7 @@ def test_fast_logprob_tiles_ragged_unaligned_large(golden):
     gen = np.random.default_rng(0)
     for n in (127, 128, 129, 1000, 128 * 300 + 5):
         x = gs.radial_projection(gen.standard_normal((n + 1, 10)))
-        want = pdf.log_prob(x)  # float64 literal
+        want = oracle_of(pdf).log_prob(x)  # float64 numpy restatement
         xt = torch.as_tensor(x, dtype=torch.float32).cuda()
         got = pdf.log_prob(xt).cpu().numpy()
         assert rel_err(got, want) <= 1e-5
@@ -204,7 +273,9 @@ def test_fast_logprob_tiles_ragged_unaligned_large(golden):
     for pdf2, d in ((gs.random_bingham(50, 300, 0, True, 6982), 50), (gs.random_bingham(7, 30, 0, False, 1), 7),
                     (gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(10, 100, 0.5, seed=4562)), 500.0), 100)):
         x = gs.radial_projection(gen.standard_normal((128 * 9 + 17, d)))
-        assert rel_err(pdf2.log_prob(x.astype(F32)), pdf2.log_prob(x)) <= 2e-5
+        err = rel_err(pdf2.log_prob(x.astype(F32)), oracle_of(pdf2).log_prob(x))
+        print(f"tiled log_prob {type(pdf2).__name__} d={d}: max rel err {err:.3g}")
+        assert err <= 1e-5, (type(pdf2).__name__, d, err)
 
 
 @pytest.mark.parametrize("d", [8, 12, 16, 20, 32, 33, 48, 64, 100, 128])
@@ -222,10 +293,12 @@ def test_fast_logprob_row_layouts(d):
     x = gs.radial_projection(gen.standard_normal((128 * 5 + 77, d)))
     xt = torch.as_tensor(x, dtype=torch.float32).cuda()
     for pdf in pdfs:
-        want = pdf.log_prob(x)
-        assert rel_err(pdf.log_prob(xt).cpu().numpy(), want) <= 2e-5, type(pdf).__name__
-        assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 2e-5  # rows start 4 d bytes later: unaligned for odd d
-        assert rel_err(pdf.log_prob(xt[:128]).cpu().numpy(), want[:128]) <= 2e-5
+        want = oracle_of(pdf).log_prob(x)  # float64 numpy restatement
+        err = rel_err(pdf.log_prob(xt).cpu().numpy(), want)
+        print(f"row layout d={d} {type(pdf).__name__}: max rel err {err:.3g}")
+        assert err <= 1e-5, (type(pdf).__name__, err)
+        assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 1e-5  # rows start 4 d bytes later: unaligned for odd d
+        assert rel_err(pdf.log_prob(xt[:128]).cpu().numpy(), want[:128]) <= 1e-5
 
 
 def test_dense_bingham_logprob_on_tensor_cores():
@@ -237,20 +310,21 @@ def test_dense_bingham_logprob_on_tensor_cores():
         pdf = gs.random_bingham(d, 300.0, 0.0, False, 6982)
         for n in (1, 127, 128, 129, 128 * 37 + 5):
             x = gs.radial_projection(gen.standard_normal((n + 1, d)))
-            want = pdf.log_prob(x)
+            want = oracle_of(pdf).log_prob(x)  # float64 numpy restatement
             xt = torch.as_tensor(x, dtype=torch.float32).cuda()
-            assert rel_err(pdf.log_prob(xt).cpu().numpy(), want) <= 2e-5
-            assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 2e-5  # 4d-byte offset: plain-load path when not 16-byte aligned
+            assert rel_err(pdf.log_prob(xt).cpu().numpy(), want) <= 1e-5
+            assert rel_err(pdf.log_prob(xt[1:]).cpu().numpy(), want[1:]) <= 1e-5  # 4d-byte offset: plain-load path when not 16-byte aligned
     pf = gs.BinghamFisher(gs.random_bingham(20, 20.0, 0.0, False, 3).A, 4.0 * gs.sample_sphere(19, seed=4))
     x = gs.radial_projection(gen.standard_normal((1000, 20)))
     tc = pf.log_prob(x.astype(F32))
-    assert rel_err(tc, pf.log_prob(x)) <= 2e-5
+    want = oracle_of(pf).log_prob(x)
+    assert rel_err(tc, want) <= 1e-5
     os.environ["GEOSSS_NO_TC"] = "1"
     try:
         simt = pf.log_prob(x.astype(F32))
     finally:
         del os.environ["GEOSSS_NO_TC"]
-    assert rel_err(simt, pf.log_prob(x)) <= 2e-5 and not np.array_equal(simt, tc)
+    assert rel_err(simt, want) <= 1e-5 and not np.array_equal(simt, tc)
 
 
 # ------------------------------------------------------------------ trajectories under the reference's draws
@@ -292,16 +366,13 @@ def test_tape_trajectories_float64(golden):
 
 
 def test_tape_trajectories_float32(golden):
-    total = clean = 0
+    """Literal float32 kernels fed the reference's own recorded draws, C1-C5, both samplers (1100 + 8 x 1500 + ... transitions)."""
+    fc = FlipCount("tape_literal_float32_c1_to_c5")
     for pdf, cls, g, tag in tape_cases(golden):
         want, rej_want = g[f"{tag}_traj"], np.diff(g[f"{tag}_cumrej"])
         got, nrej, _ = cls(pdf, g[f"{tag}_x0"], 0, dtype="float32", path="literal").run_tape(g[f"{tag}_tape"], len(want) - 1)
-        flips = np.nonzero(nrej[0] != rej_want)[0]
-        upto = flips[0] if len(flips) else len(rej_want)
-        assert np.max(np.abs(got[0][:upto] - want[1:1 + upto])) <= 1e-4, tag
-        total += len(rej_want)
-        clean += upto
-    assert clean >= 0.8 * total, (clean, total)
+        fc.add(got[0], nrej[0], want[1:], rej_want)
+    fc.check(3.0)
 
 
 def test_tape_many_chains_ragged_block(golden):
@@ -348,30 +419,31 @@ def test_free_running_literal_float64_matches_oracle(golden, cls, kind):
     assert smp.n_reject == sum(oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, off + c, n, 10, F64)[1].sum() for c in range(6))
 
 
+# flips per 1000 transitions allowed (measured values: profiles/r2_flips.jsonl)
+FLIP_BOUND_VMF = {"c1": 3.0, "c2_k100": 3.0, "c2_k500": 6.0}
+
+
 @pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
                                       (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
 @pytest.mark.parametrize("cfg", ["c1", "c2_k100", "c2_k500"])
 def test_fast_path_follows_reference_under_shared_draws(golden, cls, kind, cfg):
-    """fp32 throughput kernel vs the float64 reference algorithm fed the same Philox draws:
-    <= 1e-4 until the first accept/reject flip; at most a small fraction of chains flip early."""
+    """fp32 throughput kernel vs the float64 reference algorithm fed the same Philox draws: <= 1e-4 strictly
+    before a chain's first accept/reject flip; flips per 1000 transitions reported and bounded."""
     if cfg == "c1":
         mus, d = golden("traj_c1")["mus"], 3
     else:
         mus, d = float(cfg.split("k")[1]) * golden("traj_c2")["modes"], 10
-    N, n = 24, (40 if kind == samplers.SHRINK else 15)
+    N, n = (8, 200) if kind == samplers.SHRINK else (8, 190)  # >= 1500 transitions per configuration (SURVEY 8d)
     x0 = gs.sample_sphere(d - 1, N, seed=11)
     seed = 20240607
     smp = cls(mixture(mus), x0, seed, dtype="float32", path="fast")
-    got = smp.sample(n + 1)
+    got, nrej = run_with_rejections(smp, n)
     assert smp.path == "fast" and got.dtype == F32
-    clean = 0
+    fc = FlipCount(f"k_vmf_fast_{cfg}_{'shrink' if kind == samplers.SHRINK else 'reject'}")
     for c in range(N):
         want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, c, n, d, F32)
-        err = np.max(np.abs(got[c, 1:] - want), axis=1)
-        bad = np.nonzero(err > 1e-4)[0]
-        upto = bad[0] if len(bad) else n
-        clean += upto
-    assert clean >= 0.9 * N * n, (clean, N * n)
+        fc.add(got[c], nrej[c], want, rej)
+    fc.check(FLIP_BOUND_VMF[cfg])
 
 
 @pytest.mark.parametrize("d", list(range(2, 17)))
@@ -381,16 +453,15 @@ def test_fast_kernel_every_dimension_follows_reference(d):
     on d mod 4), both samplers, K = 3."""
     mus = 25.0 * gs.sample_sphere(d - 1, 3, seed=100 + d)
     x0 = gs.sample_sphere(d - 1, 6, seed=d)
+    fc = FlipCount(f"k_vmf_fast_d{d}")
     for cls, kind, n in ((gs.ShrinkageSphericalSliceSampler, samplers.SHRINK, 16), (gs.RejectionSphericalSliceSampler, samplers.REJECT, 8)):
         smp = cls(mixture(mus), x0, 977 + d, dtype="float32", path="fast")
-        got = smp.sample(n + 1)
+        got, nrej = run_with_rejections(smp, n)
         assert smp.path == "fast"
-        clean = 0
         for c in range(6):
-            want, _ = oracle_chain(targets.VMFMixture(mus), kind, x0[c], 977 + d, c, n, d, F32)
-            bad = np.nonzero(np.max(np.abs(got[c, 1:] - want), axis=1) > 1e-4)[0]
-            clean += bad[0] if len(bad) else n
-        assert clean >= 0.85 * 6 * n, (d, kind, clean, 6 * n)
+            want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], 977 + d, c, n, d, F32)
+            fc.add(got[c], nrej[c], want, rej)
+    fc.check(15.0)  # 144 transitions per dimension: one flip is 7 per 1000
 
 
 def test_parked_device_blocks_are_reused_cleanly():
@@ -434,21 +505,21 @@ def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, c
     """Bingham(-Fisher) and curved-vMF throughput kernels vs the float64 reference algorithm fed the
     same Philox draws: <= 1e-4 until the first accept/reject flip."""
     pdf, ora, d = gc_case(golden, cfg)
-    N, n = 12, (25 if kind == samplers.SHRINK else 8)
+    N, n = 12, (60 if kind == samplers.SHRINK else 20)
+    if cfg in ("c3",):
+        N, n = 6, (40 if kind == samplers.SHRINK else 12)  # the float64 oracle of the d=100 curve costs ~3 ms per evaluation
     x0 = gs.sample_sphere(d - 1, N, seed=13)
     if cfg.startswith("c4") or cfg == "d10":
         x0[: N // 2] = gs.radial_projection(pdf.mode + 0.3 * x0[: N // 2])  # some chains start near the mode
     seed = 777
     smp = cls(pdf, x0, seed, dtype="float32", path="fast")
-    got = smp.sample(n + 1)
-    assert smp.path == "fast" and got.dtype == F32 and got.shape == (N, n + 1, d)
-    clean = 0
+    got, nrej = run_with_rejections(smp, n)
+    assert smp.path == "fast" and got.dtype == F32 and got.shape == (N, n, d)
+    fc = FlipCount(f"k_gc_fast_{cfg}_{'shrink' if kind == samplers.SHRINK else 'reject'}")
     for c in range(N):
-        want, _ = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32)
-        err = np.max(np.abs(got[c, 1:] - want), axis=1)
-        bad = np.nonzero(err > 1e-4)[0]
-        clean += bad[0] if len(bad) else n
-    assert clean >= 0.9 * N * n, (clean, N * n)
+        want, rej = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32)
+        fc.add(got[c], nrej[c], want, rej)
+    fc.check(8.0)
 
 
 @pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
@@ -463,18 +534,17 @@ def test_high_dimensional_vmf_mixture_fast_kernel(cls, kind, d, K, kappa):
     x0 = gs.sample_sphere(d - 1, N, seed=3)
     x0[: N // 2] = gs.radial_projection(mus[0] / kappa + 0.2 * x0[: N // 2])
     smp = cls(pdf, x0, 31337, dtype="float32", path="fast")
-    got = smp.sample(n + 1)
+    got, nrej = run_with_rejections(smp, n)
     assert smp.path == "fast"
-    clean = 0
+    fc = FlipCount(f"k_gc_fast_vmf_d{d}_K{K}_{'shrink' if kind == samplers.SHRINK else 'reject'}")
     for c in range(N):
-        want, _ = oracle_chain(ora, kind, x0[c], 31337, c, n, d, F32)
-        bad = np.nonzero(np.max(np.abs(got[c, 1:] - want), axis=1) > 1e-4)[0]
-        clean += bad[0] if len(bad) else n
-    assert clean >= 0.9 * N * n, (clean, N * n)
+        want, rej = oracle_chain(ora, kind, x0[c], 31337, c, n, d, F32)
+        fc.add(got[c], nrej[c], want, rej)
+    fc.check(10.0)
     # literal fp32 agrees in distribution of rejections (same algorithm): compare mean rejections loosely
     lit = cls(pdf, x0, 31337, dtype="float32", path="literal")
     lit.sample(n + 1)
-    assert abs(lit.n_reject - smp.n_reject) <= 0.2 * max(lit.n_reject, 10)
+    assert abs(lit.n_reject - int(nrej.sum())) <= 0.2 * max(lit.n_reject, 10)
 
 
 def test_shard_invariance_and_continuation(golden):
@@ -631,20 +701,77 @@ def test_device_ess_matches_oracle(dtype):
     assert abs(diagnostics.ess(xt, None, 200, chain_major=False)[1] - 0.25 / 1.75) < 0.03
 
 
+def test_device_bulk_ess_matches_independent_restatement():
+    """Rank-normalised split bulk ESS (what the upstream scripts get from arviz.ess): device implementation
+    (ranks by a device sort, autocovariance partial sums in csrc/diag.cuh, truncation rules on the host) against
+    the independently written numpy restatement oracle/ess.py:bulk_ess; known answers for AR(1) traces."""
+    from geosss_b200 import diagnostics
+    from oracle import ess as E
+    gen = np.random.default_rng(4)
+    for phi, N, n in ((0.0, 16, 400), (0.75, 24, 1001), (0.97, 8, 3000), (-0.5, 5, 64)):
+        e = gen.standard_normal((N, n))
+        x = np.zeros_like(e)
+        for t in range(1, n):
+            x[:, t] = phi * x[:, t - 1] + e[:, t]
+        x = x.astype(np.float32)  # the device ranks float32 values: give both sides the same ties
+        x[:, ::7] = np.round(x[:, ::7], 1)  # ... and some exact ties
+        got = diagnostics.bulk_ess(torch.as_tensor(x).cuda())
+        want = E.bulk_ess(x.astype(float))
+        assert abs(got - want) <= 2e-4 * want, (phi, got, want)
+        rel = diagnostics.bulk_ess(torch.as_tensor(x).cuda(), relative=True)
+        assert abs(rel - want / (N * (2 * (n // 2)))) <= 2e-4 * rel
+    # AR(1): ESS / S -> (1 - phi) / (1 + phi)
+    e = gen.standard_normal((64, 4000))
+    x = np.zeros_like(e)
+    for t in range(1, 4000):
+        x[:, t] = 0.75 * x[:, t - 1] + e[:, t]
+    assert abs(diagnostics.bulk_ess(torch.as_tensor(x, dtype=torch.float32).cuda(), relative=True) - 0.25 / 1.75) < 0.01
+
+
+def test_sample_trace_equals_projection_of_retained_samples(golden):
+    """The scalar test-function trace written by the sampler kernels (4 bytes per kept transition) equals
+    x . direction of the fully retained chain, for the register-resident, the shared-memory and the literal kernels."""
+    g = golden("traj_c2")
+    cases = [(mixture(100.0 * g["modes"]), "float32", 2e-6), (gs.random_bingham(50, 300, 0, True, 6982), "float32", 2e-6),
+             (gs.random_bingham(12, 30, 0, False, 3), "float32", 2e-6),
+             (gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(10, 100, 0.5, seed=4562)), 500.0), "float32", 2e-6),
+             (mixture(100.0 * g["modes"]), "float64", 1e-14)]
+    for pdf, dtype, tol in cases:
+        d = pdf.d
+        x0 = gs.sample_sphere(d - 1, 70, seed=d)
+        v = gs.sample_sphere(d - 1, seed=1)
+        for thin in (1, 3):
+            a = gs.ShrinkageSphericalSliceSampler(pdf, torch.as_tensor(x0).cuda(), 5, dtype=dtype)
+            full = a.sample(41 * thin + 10, 10, return_all_samples=True)  # (N, 41 thin + 20, d): initial state first
+            b = gs.ShrinkageSphericalSliceSampler(pdf, torch.as_tensor(x0).cuda(), 5, dtype=dtype)
+            tr = b.sample_trace(41, v, burnin=19, thin=thin)
+            assert tuple(tr.shape) == (70, 41) and tr.is_cuda
+            kept = full[:, 19 + thin::thin][:, :41]
+            want = kept.double().cpu().numpy() @ v
+            assert np.max(np.abs(tr.double().cpu().numpy() - want)) <= tol * 10, (type(pdf).__name__, dtype, thin)
+            assert a.n_reject >= b.n_reject > 0
+    # default direction: the first coordinate (scripts/ess_mixture_vMF.py:233)
+    one = gs.ShrinkageSphericalSliceSampler(cases[0][0], x0[0], 9).sample_trace(30)
+    ref = gs.ShrinkageSphericalSliceSampler(cases[0][0], torch.as_tensor(x0[0]).cuda(), 9).sample(31)
+    assert tuple(one.shape) == (30,) and torch.equal(one, ref[1:, 0])
+
+
 def test_launcher_and_bingham_relative_ess(golden):
-    """Published sampler quality (scripts/Bingham.ipynb:254): on the d=10 Bingham target
-    GeoSSS-reject has ~100 % relative ESS of x . mode and GeoSSS-shrink far less (~15 %)."""
+    """Published sampler quality (scripts/Bingham.ipynb:254, arviz bulk ESS of x . mode over 10 runs of
+    1e5 draws started at the mode, scripts/bingham.py:28-70,113-134): GeoSSS-reject 99.73 %, GeoSSS-shrink 15.2 %
+    on the d=10 Bingham target.  Here: 64 chains x 20,000 draws after 2,000 of burn-in, the same estimator."""
     from geosss_b200 import diagnostics
     pdf = gs.random_bingham(10, 30, 0, True, 6982)
-    x0 = np.tile(pdf.mode, (256, 1))
+    la = gs.SamplerLauncher(pdf, torch.as_tensor(np.tile(pdf.mode, (16, 1))).cuda(), 300, burnin=0.2, seed=3)
+    assert tuple(la.run("sss-shrink").shape) == (16, 300, 10)
+    x0 = np.tile(pdf.mode, (64, 1))
     out = {}
-    for method in ("sss-reject", "sss-shrink"):
-        la = gs.SamplerLauncher(pdf, torch.as_tensor(x0).cuda(), 2000, burnin=0.2, seed=3)
-        s = la.run(method)  # (N, n, d) CUDA tensor
-        assert tuple(s.shape) == (256, 2000, 10)
-        out[method] = diagnostics.ess(s, pdf.mode, 500)[1]
-    assert out["sss-reject"] > 0.6
-    assert 0.05 < out["sss-shrink"] < 0.5 and out["sss-shrink"] < out["sss-reject"]
+    for name, cls in (("sss-reject", gs.RejectionSphericalSliceSampler), ("sss-shrink", gs.ShrinkageSphericalSliceSampler)):
+        tr = cls(pdf, torch.as_tensor(x0).cuda(), 3).sample_trace(20000, pdf.mode, burnin=2000)
+        out[name] = diagnostics.bulk_ess(tr, relative=True)
+    print("relative bulk ESS of x . mode, Bingham d=10:", out)
+    assert out["sss-reject"] >= 0.9
+    assert abs(out["sss-shrink"] - 0.152) <= 0.04
 
 
 @pytest.mark.parametrize("d,vmax,want", [(10, 30.0, {"sss-reject": 1.58, "sss-shrink": 0.54}),

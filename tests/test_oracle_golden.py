@@ -241,3 +241,40 @@ def test_exact_samplers_oracle_matches_reference_moments(golden):
         x, eff = exact.kent_bingham(g[f"bing_{tag}_A"], 100000, seed=2, return_efficiency=True)
         assert np.max(np.abs(x.T @ x / len(x) - g[f"bing_{tag}_second"])) < 5 * np.sqrt(1.5e-5)
         assert abs(eff - g[f"bing_{tag}_eff"]) < 0.06
+
+
+def test_bulk_ess_restatement_known_answers():
+    """oracle/ess.py:bulk_ess (arviz-style rank-normalised split ESS, restated from Vehtari et al. 2021): i.i.d. draws
+    give ESS ~ S, AR(1) chains ESS / S ~ (1 - phi) / (1 + phi), average ranks equal scipy's, and the truncation rules
+    written for the device path (geosss_b200/diagnostics.py:_tau_bulk, from all-reduced partial sums) agree with the
+    literal arviz-order loop of the oracle on random traces, including runs that stop for lack of lags."""
+    from scipy.stats import rankdata
+    from geosss_b200.diagnostics import _tau_bulk
+    gen = np.random.default_rng(0)
+    assert abs(ess.bulk_ess(gen.standard_normal((8, 4000)), relative=True) - 1.0) < 0.05
+    for phi in (0.5, 0.9):
+        e = gen.standard_normal((16, 20000))
+        y = np.zeros_like(e)
+        for t in range(1, e.shape[1]):
+            y[:, t] = phi * y[:, t - 1] + e[:, t]
+        assert abs(ess.bulk_ess(y, relative=True) / ((1 - phi) / (1 + phi)) - 1.0) < 0.08
+    v = gen.integers(0, 50, 1000).astype(float)
+    assert np.array_equal(ess.average_ranks(v), rankdata(v))
+    assert ess.split_chains(np.arange(14.0).reshape(2, 7)).tolist() == [[0, 1, 2], [7, 8, 9], [4, 5, 6], [11, 12, 13]]
+    for trial in range(200):
+        m, n, phi = int(gen.integers(1, 6)), int(gen.integers(8, 200)), gen.uniform(-0.9, 0.99)
+        e = gen.standard_normal((m, n))
+        y = np.zeros_like(e)
+        for t in range(1, n):
+            y[:, t] = phi * y[:, t - 1] + e[:, t]
+        acov = ess.autocov_fft_chains(y)
+        assert np.allclose(acov[:, :min(n, 30)], ess.autocov_multichain(y, min(n, 30)), atol=1e-12)
+        mean_var = acov[:, 0].mean() * n / (n - 1.0)
+        var_plus = mean_var * (n - 1.0) / n + (y.mean(1).var(ddof=1) if m > 1 else 0.0)
+        tau_o, _ = ess.geyer_tau(acov.mean(0), mean_var, var_plus, n, m * n)
+        cm = y.mean(1)
+        tau_d, exhausted = _tau_bulk(acov.sum(0), cm.sum(), (cm * cm).sum(), n, m)
+        assert not exhausted and abs(tau_o - tau_d) <= 1e-12 * tau_o
+        L = max(4, n // 3)
+        tau_l, exhausted = _tau_bulk(acov.sum(0)[:L], cm.sum(), (cm * cm).sum(), n, m)
+        assert exhausted or abs(tau_l - tau_o) <= 1e-9 * tau_o
