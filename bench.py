@@ -224,7 +224,10 @@ def run_extras(a, gs, dev, rank, world, barrier, max_over_ranks, hbm_peak, fp32_
             else:
                 off, n_loc = gdist.shard_range(chains, rank, world)
                 total = chains
-            x0 = gs.sample_sphere(d - 1, total, seed=977)[off:off + n_loc]
+            if testfn == "mode":  # scripts/bingham.py:134 starts every chain at the mode
+                x0 = np.tile(np.asarray(pdf.mode, dtype=float), (n_loc, 1))
+            else:  # uniform initial states (scripts/curve_vMF.py:86, scripts/mixture_vMF.py:150, scripts/protein_reg3d3d.py:231)
+                x0 = gs.sample_sphere(d - 1, total, seed=977)[off:off + n_loc]
             smp = cls(pdf, torch.as_tensor(x0).to(dev), 48385, chain_offset=off)
             direction = None
             if testfn == "mode":
@@ -240,7 +243,7 @@ def run_extras(a, gs, dev, rank, world, barrier, max_over_ranks, hbm_peak, fp32_
                 samples = torch.empty((n_loc, T, d), dtype=torch.float32, device=dev)
                 logp = torch.empty((n_loc, T), dtype=torch.float32, device=dev)
             launch = lambda: smp._run_device(T, samples, logp=logp, chain_major=True, trace=trace, direction=direction)
-            smp._run_device(5 if testfn == "logp" else 50, None)  # burn-in
+            smp._run_device(10 if testfn == "logp" else 200, None)  # burn-in
             launch()
             rej0 = int(smp.n_reject_per_chain.sum())
             clocks = ClockSampler(local)
@@ -269,7 +272,9 @@ def run_extras(a, gs, dev, rank, world, barrier, max_over_ranks, hbm_peak, fp32_
             gbs = bytes_kept * n_loc * T / launch_s / 1e9
             roof_c = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak,
                       "frac_of_nominal_74.5": tf / 74.5, "peak_source": fp32_src, "kernel": kernel,
-                      "algorithmic_flops_per_transition": flops}
+                      "algorithmic_flops_per_transition": flops,
+                      "note": "flops of the REFERENCE algorithm (SURVEY.md 8d: 9d + (1 + rejections)(3d + 4 + F_logp)); the kernels evaluate "
+                              "proposals through the great-circle algebra, so a fraction near or above 1 means work avoided, not a faster pipe"}
             roof_h = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "kernel": kernel,
                       "algorithmic_bytes_per_transition": bytes_kept}
             rec.update({"chains": total, "chains_per_gpu": n_loc, "value": value, "unit": UNIT, "ms_per_launch": launch_s * 1e3,

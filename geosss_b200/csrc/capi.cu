@@ -16,6 +16,7 @@
 #include "kernels_gc.cuh"
 #include "kernels_logp_fast.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_logp_tc.cuh"
 #include "kernels_literal.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_mh.cuh"
@@ -685,6 +686,30 @@ static int logp_vmf_const(geosss_target* t, const float* x, float* o, int64_t N,
     return 0;
 }
 
+// Tensor-core log_prob (kernels_logp_tc.cuh): whole 128-row tiles of a 16-byte aligned input; the ragged tail (and an
+// unaligned input) goes to the SIMT tiled kernel passed as `simt`.  GEOSSS_NO_TC=1 keeps everything on the SIMT kernels.
+template <class Epi, class Simt>
+static int logp_tc(const TcpParams& tp, const float* x, float* out, int64_t N, cudaStream_t st, Simt simt) {
+    const int64_t full = N / TCP_ROWS;
+    if (full == 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return simt(x, out, N);
+    if (!g_sm_count) {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int R = tcp_stages<Epi>(tp.d);
+    if (const char* e = std::getenv("GEOSSS_TC_STAGES")) { const int v = std::atoi(e); if (v >= 2 && v <= R) R = v; }
+    const size_t smem = tcp_smem_bytes<Epi>(tp.d, R);
+    CU(cudaFuncSetAttribute(k_logp_tc<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = full < g_sm_count ? full : g_sm_count;  // persistent: one block per SM (all 512 TMEM columns)
+    k_logp_tc<Epi><<<(unsigned)grid, TCP_THREADS, smem, st>>>(tp, x, out, full, R);
+    CU(cudaGetLastError());
+    const int64_t done = full * TCP_ROWS;
+    return done < N ? simt(x + done * tp.d, out + done, N - done) : 0;
+}
+
+static bool tc_enabled() { return !std::getenv("GEOSSS_NO_TC"); }
+
 static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
     LpParams p{};
     p.d = t->d;
@@ -695,10 +720,21 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
             if (!fast_supported(t->kind, t->d, t->K, t->single)) return logp_vmf_const(t, xi, o, N, st);
             p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
+            // chains x components contraction on the tensor cores for wide rows (K padded to 16 accumulator columns)
+            if (tc_enabled() && t->d >= 24 && t->K <= TcVmfEpi::NP && tcp_fits<TcVmfEpi>(t->d)) {
+                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K};
+                return logp_tc<TcVmfEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<VmfLp>(p, xs, os, n, st); });
+            }
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
         case TGT_BINGHAM:
             // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
-            if (!t->diag && t->d >= 8 && t->d <= TC_MAX_D && !std::getenv("GEOSSS_NO_TC")) {
+            if (!t->diag && t->d >= 8 && t->d <= TC_MAX_D && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
+                p.diag = 0; p.a0 = t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
+                const TcpParams tp{t->A.f, t->has_b ? t->b.f : nullptr, nullptr, 0.f, t->d, t->d};
+                return logp_tc<TcBinghamEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<BinghamLp>(p, xs, os, n, st); });
+            }
+            // round-1 kernel (one block-wide phase at a time), kept selectable for A/B runs: GEOSSS_TC_V1=1
+            if (!t->diag && t->d >= 8 && t->d <= TC_MAX_D && tc_enabled()) {
                 if (!g_sm_count) {
                     int dev = 0;
                     CU(cudaGetDevice(&dev));
@@ -724,6 +760,10 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
         case TGT_CURVED_VMF:
             if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
             p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
+            if (tc_enabled() && t->d >= 24 && t->M <= TcCurvedEpi::NP && tcp_fits<TcCurvedEpi>(t->d)) {  // G = X knots^T on the tensor cores
+                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M};
+                return logp_tc<TcCurvedEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<CurvedLp>(p, xs, os, n, st); });
+            }
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
         case TGT_CPD: {
             if (target_fast_supported(t)) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast CPD kernel needs the dense sum with an outlier term");

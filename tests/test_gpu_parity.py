@@ -94,7 +94,8 @@ class FlipCount:
                 f.write(json.dumps(rec) + "\n")
         except OSError:
             pass
-        assert self.rate() <= max_per_1000, rec
+        # the bound is a rate; a run shorter than 1000 / bound transitions may still hold one flip
+        assert self.flips <= max(1, int(max_per_1000 * self.compared / 1000.0)), rec
 
 
 def c5_target(golden, k=20):
@@ -178,7 +179,7 @@ def test_cpd_fast_path(golden):
         for c in range(6):
             want, rej = oracle_chain(ora, kind, x0[c], 4242, c, steps, 4, F32)
             fc.add(got[c], nrej[c], want, rej)
-    fc.check(25.0)  # row sums near -2400 in float32: a proposal within ~2e-4 of the level can flip
+    fc.check(1.0)  # measured: 0 flips in 96 transitions (profiles/r2_flips.jsonl)
 
 
 def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
@@ -216,7 +217,7 @@ def test_cpd_cutoff_cells_equal_dense_sum(golden, monkeypatch):
     for c in range(16):
         want_c, rej_c = oracle_chain(ora, samplers.SHRINK, x0[c], 77, c, 6, 4, F32)
         fc.add(got[c], nrej[c], want_c, rej_c)
-    fc.check(25.0)
+    fc.check(1.0)
 
 
 @pytest.mark.parametrize("k", [1, 3, 8, 20])
@@ -372,7 +373,7 @@ def test_tape_trajectories_float32(golden):
         want, rej_want = g[f"{tag}_traj"], np.diff(g[f"{tag}_cumrej"])
         got, nrej, _ = cls(pdf, g[f"{tag}_x0"], 0, dtype="float32", path="literal").run_tape(g[f"{tag}_tape"], len(want) - 1)
         fc.add(got[0], nrej[0], want[1:], rej_want)
-    fc.check(3.0)
+    fc.check(1.0)  # measured on B200: 1 flip in 8994 transitions (profiles/r2_flips.jsonl)
 
 
 def test_tape_many_chains_ragged_block(golden):
@@ -419,10 +420,6 @@ def test_free_running_literal_float64_matches_oracle(golden, cls, kind):
     assert smp.n_reject == sum(oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, off + c, n, 10, F64)[1].sum() for c in range(6))
 
 
-# flips per 1000 transitions allowed (measured values: profiles/r2_flips.jsonl)
-FLIP_BOUND_VMF = {"c1": 3.0, "c2_k100": 3.0, "c2_k500": 6.0}
-
-
 @pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
                                       (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
 @pytest.mark.parametrize("cfg", ["c1", "c2_k100", "c2_k500"])
@@ -443,7 +440,7 @@ def test_fast_path_follows_reference_under_shared_draws(golden, cls, kind, cfg):
     for c in range(N):
         want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], seed, c, n, d, F32)
         fc.add(got[c], nrej[c], want, rej)
-    fc.check(FLIP_BOUND_VMF[cfg])
+    fc.check(1.0)
 
 
 @pytest.mark.parametrize("d", list(range(2, 17)))
@@ -461,7 +458,7 @@ def test_fast_kernel_every_dimension_follows_reference(d):
         for c in range(6):
             want, rej = oracle_chain(targets.VMFMixture(mus), kind, x0[c], 977 + d, c, n, d, F32)
             fc.add(got[c], nrej[c], want, rej)
-    fc.check(15.0)  # 144 transitions per dimension: one flip is 7 per 1000
+    fc.check(1.0)  # 144 transitions per dimension; measured: 0 flips in all 15 dimensions
 
 
 def test_parked_device_blocks_are_reused_cleanly():
@@ -519,7 +516,7 @@ def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, c
     for c in range(N):
         want, rej = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32)
         fc.add(got[c], nrej[c], want, rej)
-    fc.check(8.0)
+    fc.check(1.0)
 
 
 @pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
@@ -540,7 +537,7 @@ def test_high_dimensional_vmf_mixture_fast_kernel(cls, kind, d, K, kappa):
     for c in range(N):
         want, rej = oracle_chain(ora, kind, x0[c], 31337, c, n, d, F32)
         fc.add(got[c], nrej[c], want, rej)
-    fc.check(10.0)
+    fc.check(1.0)
     # literal fp32 agrees in distribution of rejections (same algorithm): compare mean rejections loosely
     lit = cls(pdf, x0, 31337, dtype="float32", path="literal")
     lit.sample(n + 1)
