@@ -12,6 +12,7 @@
 
 #include "../../include/geosss_cuda.h"
 #include "diag.cuh"
+#include "eigh_jacobi.h"
 #include "kernels_fast.cuh"
 #include "kernels_gc.cuh"
 #include "kernels_logp_fast.cuh"
@@ -164,7 +165,8 @@ struct geosss_target {
     Arr consts;                         // (K) log w - log 2pi - log i0, device
     // Bingham
     Arr A, b, Adiag;
-    int has_b = 0, diag = 0;
+    Arr eig_rows, eig_vals;  // dense A, d <= 64: eigenvectors as rows (+ b as row d when it fits), eigenvalues (kernels_logp_tc.cuh)
+    int has_b = 0, diag = 0, eig_n_out = 0;
     // curved vMF
     int M = 0;
     double kappa = 0;
@@ -191,7 +193,7 @@ struct geosss_target {
                 (T)log_outlier, (T)beta, nt, ns, k, outlier, {(T)shift[0], (T)shift[1], (T)shift[2]}, dim};
     }
     void release() {
-        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &eig_rows, &eig_vals, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
         for (void** q : {&d_cell, &d_entry, &d_tgt4}) { if (*q) cudaFree(*q); *q = nullptr; }
         has_grid = 0;
     }
@@ -419,6 +421,20 @@ extern "C" int geosss_target_create_bingham(int d, const double* A, const double
         std::vector<double> dg(d);
         for (int i = 0; i < d; ++i) dg[i] = A[(size_t)i * d + i];
         rc = t->Adiag.upload(dg.data(), d);
+    }
+    if (!rc && !diag && d <= TC_MAX_D && (!b || d < TcBinghamEpi::NP)) {
+        // x^T A x = sum_j w_j (v_j . x)^2: rows of W = eigenvectors (the reference holds the same decomposition, distributions.py:73-76)
+        std::vector<double> sym((size_t)d * d), w, V;
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) sym[(size_t)i * d + j] = 0.5 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
+        eigh_jacobi(d, sym, w, V);
+        t->eig_n_out = d + (b ? 1 : 0);
+        std::vector<double> rows((size_t)t->eig_n_out * d);
+        for (int j = 0; j < d; ++j)
+            for (int k = 0; k < d; ++k) rows[(size_t)j * d + k] = V[(size_t)k * d + j];
+        if (b) for (int k = 0; k < d; ++k) rows[(size_t)d * d + k] = b[k];
+        rc = t->eig_rows.upload(rows.data(), rows.size());
+        if (!rc) rc = t->eig_vals.upload(w.data(), d);
     }
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
@@ -728,9 +744,9 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
         case TGT_BINGHAM:
             // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
-            if (!t->diag && t->d >= 8 && t->d <= TC_MAX_D && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
+            if (!t->diag && t->d >= 8 && t->eig_n_out > 0 && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
                 p.diag = 0; p.a0 = t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
-                const TcpParams tp{t->A.f, t->has_b ? t->b.f : nullptr, nullptr, 0.f, t->d, t->d};
+                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out};
                 return logp_tc<TcBinghamEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<BinghamLp>(p, xs, os, n, st); });
             }
             // round-1 kernel (one block-wide phase at a time), kept selectable for A/B runs: GEOSSS_TC_V1=1

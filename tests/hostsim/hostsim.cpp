@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "eigh_jacobi.h"
 #include "philox.cuh"
 #include "targets.cuh"
 #include "transition.cuh"
@@ -244,6 +245,14 @@ int hs_run_mh(const Spec* s, int dtype, int kind, const double* tape, int64_t ta
                                              stepsizes, accepted, n_walk)
                         : run_mh_any<float>(*s, kind, tape, tape_len, seed, chain, x0, n_steps, step0, stepsize, mp, samples, momenta,
                                             stepsizes, accepted, n_walk);
+}
+
+// symmetric eigen-decomposition used for the dense Bingham tensor-core path (csrc/eigh_jacobi.h)
+void hs_eigh(int n, const double* a, double* w, double* V) {
+    std::vector<double> A(a, a + (size_t)n * n), ww, VV;
+    eigh_jacobi(n, A, ww, VV);
+    std::memcpy(w, ww.data(), sizeof(double) * n);
+    std::memcpy(V, VV.data(), sizeof(double) * n * n);
 }
 
 int hs_spec_size(void) { return (int)sizeof(Spec); }

@@ -34,7 +34,7 @@ class Spec(C.Structure):
 
 
 def _newest_source():
-    files = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    files = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     return max(os.path.getmtime(f) for f in files)
 
 
@@ -53,6 +53,7 @@ def load():
                               C.c_uint64, C.c_double, C.c_double, C.c_int, C.c_int64, _pd, _pd, _pd, C.POINTER(C.c_int32),
                               C.POINTER(C.c_int64)]
     lib.hs_run_mh.restype = C.c_int
+    lib.hs_eigh.argtypes = [C.c_int, _pd, _pd, _pd]
     return lib
 
 

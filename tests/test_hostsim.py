@@ -160,3 +160,26 @@ def test_philox_step_counter_crosses_32_bits(lib, golden):
     want = samplers.SliceSampler(samplers.SHRINK, pdf.log_prob, x0.copy(), rng).sample(9)
     rc, got, _ = hs.run(lib, hs.vmf_mixture(g["mus"]), samplers.SHRINK, x0, 8, F64, seed=7, chain=11, step0=first)
     assert rc == 0 and np.max(np.abs(got - want[1:])) <= 1e-11
+
+
+def test_jacobi_eigensystem_for_dense_bingham():
+    """csrc/eigh_jacobi.h (cyclic Jacobi, what the dense-Bingham tensor-core path evaluates x^T A x in) against numpy:
+    reconstruction, orthonormality and eigenvalues for random symmetric, diagonal, rank-deficient and C4-like matrices."""
+    import ctypes as C
+    lib = hs.load()
+    gen = np.random.default_rng(0)
+    mats = [np.diag(np.arange(5.0)), np.zeros((3, 3)), np.ones((4, 4))]
+    for n in (2, 7, 50, 64):
+        G = gen.standard_normal((n, n))
+        mats += [G + G.T, G.T @ G, (G[:, :3] @ G[:, :3].T)]
+    from oracle import targets
+    mats.append(targets.random_bingham_matrix(50, 300, 0, False, 6982))
+    for A in mats:
+        n = len(A)
+        A = np.ascontiguousarray(A, dtype=float)
+        w, V = np.empty(n), np.empty((n, n))
+        lib.hs_eigh(n, A.ctypes.data_as(hs._pd), w.ctypes.data_as(hs._pd), V.ctypes.data_as(hs._pd))
+        scale = max(1.0, np.abs(A).max())
+        assert np.max(np.abs((V * w) @ V.T - A)) <= 1e-12 * scale * n
+        assert np.max(np.abs(V.T @ V - np.eye(n))) <= 1e-13 * n
+        assert np.allclose(np.sort(w), np.linalg.eigvalsh(A), atol=1e-11 * scale * n)
