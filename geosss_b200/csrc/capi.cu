@@ -422,7 +422,7 @@ extern "C" int geosss_target_create_bingham(int d, const double* A, const double
         for (int i = 0; i < d; ++i) dg[i] = A[(size_t)i * d + i];
         rc = t->Adiag.upload(dg.data(), d);
     }
-    if (!rc && !diag && d <= TC_MAX_D && (!b || d < TcBinghamEpi::NP)) {
+    if (!rc && !diag && d <= TC_MAX_D && (!b || d < TcBinghamEpi::NP_MAX)) {
         // x^T A x = sum_j w_j (v_j . x)^2: rows of W = eigenvectors (the reference holds the same decomposition, distributions.py:73-76)
         std::vector<double> sym((size_t)d * d), w, V;
         for (int i = 0; i < d; ++i)
@@ -713,9 +713,9 @@ static int logp_tc(const TcpParams& tp, const float* x, float* out, int64_t N, c
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    int R = tcp_stages<Epi>(tp.d);
+    int R = tcp_stages(tp.d, tp.np, Epi::AUX);
     if (const char* e = std::getenv("GEOSSS_TC_STAGES")) { const int v = std::atoi(e); if (v >= 2 && v <= R) R = v; }
-    const size_t smem = tcp_smem_bytes<Epi>(tp.d, R);
+    const size_t smem = tcp_smem_bytes(tp.d, tp.np, Epi::AUX, R);
     CU(cudaFuncSetAttribute(k_logp_tc<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = full < g_sm_count ? full : g_sm_count;  // persistent: one block per SM (all 512 TMEM columns)
     k_logp_tc<Epi><<<(unsigned)grid, TCP_THREADS, smem, st>>>(tp, x, out, full, R);
@@ -737,16 +737,16 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             if (!fast_supported(t->kind, t->d, t->K, t->single)) return logp_vmf_const(t, xi, o, N, st);
             p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
             // chains x components contraction on the tensor cores for wide rows (K padded to 16 accumulator columns)
-            if (tc_enabled() && t->d >= 24 && t->K <= TcVmfEpi::NP && tcp_fits<TcVmfEpi>(t->d)) {
-                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K};
+            if (tc_enabled() && t->d >= 24 && tcp_fits<TcVmfEpi>(t->d, t->K)) {
+                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K, tcp_np(t->K)};
                 return logp_tc<TcVmfEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<VmfLp>(p, xs, os, n, st); });
             }
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
         case TGT_BINGHAM:
             // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
-            if (!t->diag && t->d >= 8 && t->eig_n_out > 0 && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
+            if (!t->diag && t->d >= 8 && t->eig_n_out > 0 && tcp_fits<TcBinghamEpi>(t->d, t->eig_n_out) && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
                 p.diag = 0; p.a0 = t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
-                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out};
+                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out, tcp_np(t->eig_n_out)};
                 return logp_tc<TcBinghamEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<BinghamLp>(p, xs, os, n, st); });
             }
             // round-1 kernel (one block-wide phase at a time), kept selectable for A/B runs: GEOSSS_TC_V1=1
@@ -776,8 +776,8 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
         case TGT_CURVED_VMF:
             if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
             p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
-            if (tc_enabled() && t->d >= 24 && t->M <= TcCurvedEpi::NP && tcp_fits<TcCurvedEpi>(t->d)) {  // G = X knots^T on the tensor cores
-                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M};
+            if (tc_enabled() && t->d >= 24 && tcp_fits<TcCurvedEpi>(t->d, t->M)) {  // G = X knots^T on the tensor cores
+                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M, tcp_np(t->M)};
                 return logp_tc<TcCurvedEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<CurvedLp>(p, xs, os, n, st); });
             }
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);

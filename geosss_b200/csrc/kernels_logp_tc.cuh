@@ -40,6 +40,7 @@ constexpr int TCP_ROWS = 128;                       // UMMA M = TMEM lanes
 constexpr int TCP_THREADS = (2 + 8 + 8) * 32;       // producer, MMA, 2 x 4 split warps, 2 x 4 epilogue warps
 constexpr int TCP_MAX_STAGES = 4;
 constexpr int TCP_TMEM_COLS = 512;
+constexpr int TCP_TMEM_STAGES = 4;                  // at most; as many (hi | lo | accumulator) column groups as fit the 512 columns
 
 struct TcpParams {
     const float* W;   // (n_out, d) row-major: eigenvectors of A as rows (+ b as row d) | mu | knots
@@ -47,6 +48,7 @@ struct TcpParams {
     const float* v1;  // curved: sin(ang) (M-1)
     float kappa;
     int d, n_out;
+    int np;           // accumulator columns per half: n_out rounded up to 16 (UMMA N is a multiple of 16 at M = 128)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -75,7 +77,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 // Every policy consumes the accumulator row in chunks of 16 columns (begin / consume / result), so that the
 // epilogue holds 32 accumulator registers at a time whatever NP is.
 struct TcBinghamEpi {
-    static constexpr int NP = 64;
+    static constexpr int NP_MAX = 64;
     static constexpr int AUX = 64;
     struct State { float q0, q1, q2, q3; };
     static __device__ void stage(const TcpParams& P, float* aux) {  // eigenvalues; the Fisher row (n_out == d + 1) and the padding weigh 0
@@ -100,7 +102,7 @@ struct TcBinghamEpi {
 };
 
 struct TcVmfEpi {
-    static constexpr int NP = 16;
+    static constexpr int NP_MAX = 16;
     static constexpr int AUX = 16;
     struct State { float v; };
     static __device__ void stage(const TcpParams& P, float* aux) {  // constants in log2 units, -inf for the padding
@@ -122,7 +124,7 @@ struct TcVmfEpi {
 };
 
 struct TcCurvedEpi {
-    static constexpr int NP = 16;
+    static constexpr int NP_MAX = 16;
     static constexpr int AUX = 48;  // cos(ang), 1 / (sin(ang) + 1e-10), sin(ang): 15 each
     struct State { float v; };
     static __device__ void stage(const TcpParams& P, float* aux) {
@@ -159,11 +161,17 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// split 8 row values into TF32 hi / lo and store them to this thread's TMEM lane, columns col .. col + 7 of the hi and lo blocks
+// Split 8 row values into TF32 hi / lo and store them to this thread's TMEM lane, columns col .. col + 7 of the hi and lo blocks.
+// hi = x rounded to 11 significant bits (bit pattern + half an ulp, low 13 bits cleared: round-to-nearest in magnitude, 2 integer
+// instructions instead of the ~6 of cvt.rna.tf32 with its inf / nan handling -- rows are finite); lo = x - hi is exact in fp32 and
+// goes to tensor memory as it is: the tensor core ignores its low 13 mantissa bits, an error of 2^-11 |lo| <= 2^-23 |x|.
 __device__ __forceinline__ void tcp_split_store(uint32_t xh, uint32_t xl, int col, const float (&v)[8]) {
     float h[8], l[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { h[c] = to_tf32(v[c]); l[c] = to_tf32(v[c] - h[c]); }
+    for (int c = 0; c < 8; ++c) {
+        h[c] = __uint_as_float((__float_as_uint(v[c]) + 0x1000u) & 0xFFFFE000u);
+        l[c] = v[c] - h[c];
+    }
     tmem_st8(xh + (uint32_t)col, h);
     tmem_st8(xl + (uint32_t)col, l);
 }
@@ -191,9 +199,10 @@ template <class Epi>
 __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const float* __restrict__ x, float* __restrict__ out,
                                                              int64_t n_tiles, int R) {
     extern __shared__ __align__(128) unsigned char tcp_smem[];
-    __shared__ __align__(8) uint64_t raw_full[TCP_MAX_STAGES], raw_empty[TCP_MAX_STAGES], op_full[2], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t raw_full[TCP_MAX_STAGES], raw_empty[TCP_MAX_STAGES], op_full[TCP_TMEM_STAGES], acc_full[TCP_TMEM_STAGES],
+        acc_empty[TCP_TMEM_STAGES];
     __shared__ uint32_t tmem_base_s;
-    constexpr int NP = Epi::NP, NS = 2 * NP;  // W is stacked: rows 0..NP-1 of a K block hold Wh, rows NP..2NP-1 hold Wl
+    const int NP = P.np, NS = 2 * NP;  // W is stacked: rows 0..NP-1 of a K block hold Wh, rows NP..2NP-1 hold Wl
     const int d = P.d, ksteps = (d + 7) >> 3, KP = ksteps << 3;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t stage_floats = ((size_t)TCP_ROWS * d + 31) & ~(size_t)31;
@@ -208,12 +217,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     }
     if (tid == 0) {
         for (int i = 0; i < TCP_MAX_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&op_full[i], 4); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < TCP_TMEM_STAGES; ++i) { mbar_init(&op_full[i], 4); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
         const float sc = Epi::scale();
-        constexpr int G = NS / 8;
+        const int G = NS / 8;
         for (int i = tid; i < ksteps * NS * 8; i += TCP_THREADS) {  // (kk, chunk, n / 8, n % 8, k % 4) <- W[n][8 kk + 4 chunk + k % 4]
             const int kq = i & 3, r8 = (i >> 2) & 7, g = (i >> 5) % G, chunk = (i / (32 * G)) & 1, kk = i / (64 * G);
             const int ns = g * 8 + r8, n = ns < NP ? ns : ns - NP, k = kk * 8 + chunk * 4 + kq;
@@ -229,6 +238,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     const int stage_cols = 2 * KP + NS;  // per TMEM stage: Xh | Xl | accumulator (Xh Wh + Xl Wh | Xh Wl)
+    // S TMEM stages; tile `it` uses stage it mod S.  The two warp groups take alternate tiles, so with S = 4 a group's next
+    // split does not have to wait for the MMAs of its previous tile.
+    const int S = min(TCP_TMEM_STAGES, TCP_TMEM_COLS / stage_cols) >= 4 ? 4 : 2;
     const int n_it = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const size_t tile_floats = (size_t)TCP_ROWS * d;
     const int quad = warp & 3;  // the TMEM lane quadrant this warp may access
@@ -257,9 +269,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         const uint32_t idesc_b = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TCP_ROWS >> 4) << 24);
         const bool elected = elect_one();
         const uint64_t wdesc = umma_smem_desc(Ws, NS * 16, 128);
-        constexpr uint32_t kdesc = (uint32_t)(NS * 8 * 4) >> 4;  // one K block further, in descriptor address units (16 bytes)
+        const uint32_t kdesc = (uint32_t)(NS * 8 * 4) >> 4;  // one K block further, in descriptor address units (16 bytes)
         for (int it = 0; it < n_it; ++it) {
-            const int s = it & 1, use = it >> 1;
+            const int s = it % S, use = it / S;
             mbar_wait(&op_full[s], (uint32_t)use & 1u);
             if (use > 0) mbar_wait(&acc_empty[s], (uint32_t)(use - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -286,17 +298,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     } else if (warp < 10) {
         // ===== split warps of stage g: tiles g, g + 2, ...
         const int g = (warp - 2) >> 2;
-        const uint32_t xh = lane_base + (uint32_t)(g * stage_cols), xl = xh + (uint32_t)KP;
         // Row stride d floats.  d % 16 == 0: the same 16-byte piece of neighbouring rows falls on the same banks (8-way conflict for
         // d % 32 == 0), so a thread reads the four pieces of a pair of K steps in the order (p + lane) mod 4 and rotates them back
         // in registers (two select stages): 2-way conflicts at worst.  Other d: at most 2-way as they are.
         const bool rot = (d & 15) == 0;
         const int rl = lane & 3;
         for (int it = g; it < n_it; it += 2) {
-            const int use = it >> 1, r = it % R;
+            const int s = it % S, use = it / S, r = it % R;
+            const uint32_t xh = lane_base + (uint32_t)(s * stage_cols), xl = xh + (uint32_t)KP;
             mbar_wait(&raw_full[r], (uint32_t)(it / R) & 1u);
             if (use > 0) {  // the MMAs of the tile that used these operand columns last have completed
-                mbar_wait(&acc_full[g], (uint32_t)(use - 1) & 1u);
+                mbar_wait(&acc_full[s], (uint32_t)(use - 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const float* rowp = raw + (size_t)r * stage_floats + (size_t)row * d;
@@ -325,20 +337,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&op_full[g]);
+            if (lane == 0) mbar_arrive(&op_full[s]);
         }
     } else {
         // ===== epilogue warps of stage e
         const int e = (warp - 10) >> 2;
-        const uint32_t acc = lane_base + (uint32_t)(e * stage_cols + 2 * KP);
         for (int it = e; it < n_it; it += 2) {
-            const int use = it >> 1;
+            const int s = it % S, use = it / S;
+            const uint32_t acc = lane_base + (uint32_t)(s * stage_cols + 2 * KP);
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TCP_ROWS;
-            mbar_wait(&acc_full[e], (uint32_t)use & 1u);
+            mbar_wait(&acc_full[s], (uint32_t)use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             typename Epi::State st;
             Epi::begin(st);
-#pragma unroll
             for (int c0 = 0; c0 < NP; c0 += 16) {
                 float a0[8], a1[8], b0[8], b1[8], sc[16];
                 tmem_ld8(acc + (uint32_t)c0, a0);
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                 if (c0 + 16 >= NP) {  // the accumulator row sits in registers now
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[e]);
+                    if (lane == 0) mbar_arrive(&acc_empty[s]);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { sc[q] = a0[q] + b0[q]; sc[8 + q] = a1[q] + b1[q]; }
@@ -368,17 +379,21 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
 }
 
 // shared memory of one block with R landing stages; R: as many as fit next to the operands (at most TCP_MAX_STAGES)
-template <class Epi> inline size_t tcp_smem_bytes(int d, int R) {
+inline int tcp_np(int n_out) { return (n_out + 15) / 16 * 16; }
+inline size_t tcp_smem_bytes(int d, int np, int aux, int R) {
     const int ksteps = (d + 7) / 8;
     const size_t stage = ((size_t)TCP_ROWS * d + 31) & ~(size_t)31;
-    return ((size_t)R * stage + 2 * (size_t)ksteps * Epi::NP * 8 + Epi::AUX) * sizeof(float) + 128;  // landing ring + stacked W + constants
+    return ((size_t)R * stage + 2 * (size_t)ksteps * np * 8 + aux) * sizeof(float) + 128;  // landing ring + stacked W + constants
 }
-template <class Epi> inline int tcp_stages(int d) {
+inline int tcp_stages(int d, int np, int aux) {
     int R = TCP_MAX_STAGES;
-    while (R > 2 && tcp_smem_bytes<Epi>(d, R) > 220 * 1024) --R;
-    return tcp_smem_bytes<Epi>(d, R) <= 220 * 1024 ? R : 0;
+    while (R > 2 && tcp_smem_bytes(d, np, aux, R) > 220 * 1024) --R;
+    return tcp_smem_bytes(d, np, aux, R) <= 220 * 1024 ? R : 0;
 }
-// the two TMEM stages (hi, lo operand columns + accumulator each) must fit the 512 columns
-template <class Epi> inline bool tcp_fits(int d) { return 2 * (2 * ((d + 7) / 8 * 8) + 2 * Epi::NP) <= TCP_TMEM_COLS && tcp_stages<Epi>(d) >= 2; }
+// two TMEM stages (hi, lo operand columns + the two accumulator halves each) must fit the 512 columns
+template <class Epi> inline bool tcp_fits(int d, int n_out) {
+    const int np = tcp_np(n_out);
+    return np <= Epi::NP_MAX && 2 * (2 * ((d + 7) / 8 * 8) + 2 * np) <= TCP_TMEM_COLS && tcp_stages(d, np, Epi::AUX) >= 2;
+}
 
 }  // namespace geosss
