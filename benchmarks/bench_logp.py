@@ -48,6 +48,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--points", type=int, default=1 << 22)
     ap.add_argument("--only", default="")
+    ap.add_argument("--sweep", action="store_true", help="tensor-core kernel tuning knobs (landing stages, TMEM rings, stacked W) instead of the standard variants")
     a = ap.parse_args()
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -66,6 +67,10 @@ def main():
          [("tcgen05 pipelined", {}), ("tcgen05, 2 landing stages", {"GEOSSS_TC_STAGES": "2"}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
         ("bingham diagonal d=50 (C4)", gs.random_bingham(50, 300, 0, True, 6982), [("fp32 SIMT", {})]),
     ]
+    if a.sweep:  # tuning knobs of the tensor-core kernel
+        knobs = [("default", {}), ("2 landing stages", {"GEOSSS_TC_STAGES": "2"}), ("3 landing stages", {"GEOSSS_TC_STAGES": "3"}),
+                 ("polling waits", {"GEOSSS_TC_SPIN": "1"})]
+        cases = [(n, p, knobs) for n, p, v in cases if "SIMT" not in v[0][0]]
     for name, pdf, variants in cases:
         if a.only and a.only not in name:
             continue

@@ -33,6 +33,7 @@ SIGNATURES = {
     "geosss_target_cpd_set_translation": (_i, [_p, _pd]),
     "geosss_target_cpd_grid_info": (_i, [_p, _pd, _pd, C.POINTER(_i), C.POINTER(_i)]),
     "geosss_target_dim": (_i, [_p]),
+    "geosss_target_bingham_eigenrows": (_i, [_p, _pd]),
     "geosss_target_destroy": (_i, [_p]),
     "geosss_log_prob": (_i, [_p, _i, _i, _p, _p, _i64, _p]),
     "geosss_sampler_create": (_i, [_p, _i, _i, _i, _i64, _u64, _u64, C.POINTER(_p)]),

@@ -166,6 +166,8 @@ struct geosss_target {
     // Bingham
     Arr A, b, Adiag;
     Arr eig_rows, eig_vals;  // dense A, d <= 64: eigenvectors as rows (+ b as row d when it fits), eigenvalues (kernels_logp_tc.cuh)
+    Arr eig_b;               // the Fisher vector in the eigenbasis (W b)
+    std::vector<double> h_eig_rows;  // host copy of the d eigenvector rows (direction of the test function, tests)
     int has_b = 0, diag = 0, eig_n_out = 0;
     // curved vMF
     int M = 0;
@@ -193,7 +195,7 @@ struct geosss_target {
                 (T)log_outlier, (T)beta, nt, ns, k, outlier, {(T)shift[0], (T)shift[1], (T)shift[2]}, dim};
     }
     void release() {
-        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &eig_rows, &eig_vals, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &eig_rows, &eig_vals, &eig_b, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
         for (void** q : {&d_cell, &d_entry, &d_tgt4}) { if (*q) cudaFree(*q); *q = nullptr; }
         has_grid = 0;
     }
@@ -218,11 +220,49 @@ struct geosss_sampler {
     int64_t adapt_total = 0;
     double alpha = 0.5;
     int n_leap = 10;
+    bool eig = false;                      // dense Bingham on the fast path: the chain lives in the eigenbasis of A
     size_t state_bytes = 0, ws_bytes = 0;  // sizes of the pooled blocks (g_pool)
     int device = 0;                        // device the blocks live on (current device at creation)
     bool is_mh() const { return kind >= GEOSSS_RWMH; }
     size_t esize() const { return dtype == GEOSSS_F64 ? 8 : 4; }
 };
+
+// Rows of a strided (n_outer, n_inner, d) float array rotated in place: y = W x (to_eig) or x = W^T y; W (d, d) row-major,
+// rows = eigenvectors, staged in shared memory; one thread per row, the row in registers (d <= 64).
+static __global__ void __launch_bounds__(128) k_rotate_rows(const float* __restrict__ W, int d, int to_eig, float* __restrict__ data,
+                                                            int64_t n_outer, int64_t n_inner, int64_t s_outer, int64_t s_inner) {
+    __shared__ float Ws[TC_MAX_D * TC_MAX_D];
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+        const int r = i / d, c = i - r * d;
+        Ws[to_eig ? c * d + r : i] = W[i];  // Ws[j * d + i] multiplies input j into output i
+    }
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_outer * n_inner) return;
+    float* row = data + (idx / n_inner) * s_outer + (idx % n_inner) * s_inner;
+    float v[TC_MAX_D];
+#pragma unroll
+    for (int j = 0; j < TC_MAX_D; ++j) v[j] = j < d ? row[j] : 0.f;
+    for (int i = 0; i < d; ++i) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < TC_MAX_D; j += 2) {
+            if (j < d) a0 = fmaf(Ws[j * d + i], v[j], a0);
+            if (j + 1 < d) a1 = fmaf(Ws[(j + 1) * d + i], v[j + 1], a1);
+        }
+        row[i] = a0 + a1;
+    }
+}
+
+static int rotate_rows(const geosss_sampler* s, bool to_eig, void* data, int64_t n_outer, int64_t n_inner, int64_t s_outer, int64_t s_inner,
+                       cudaStream_t st) {
+    const int64_t rows = n_outer * n_inner;
+    if (rows <= 0) return 0;
+    k_rotate_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(s->t->eig_rows.f, s->t->d, to_eig ? 1 : 0, static_cast<float*>(data), n_outer,
+                                                                    n_inner, s_outer, s_inner);
+    CU(cudaGetLastError());
+    return 0;
+}
 
 static int fill_stepsize(geosss_sampler* s, double value) {
     std::vector<double> h((size_t)s->N, value);
@@ -246,7 +286,15 @@ static CpdCellGrid cpd_grid_now(const geosss_target* t) {
 
 // the normals stay in shared memory for d < 64 and for dense Bingham (kernels_gc.cuh, STORE); measured on
 // B200: regenerating them pays at d = 100 (+37 %, twice the resident warps) and costs 6 % at d = 50
-static bool gc_store_normals(const geosss_target* t) { return t->d < 64 || (t->kind == TGT_BINGHAM && !t->diag); }
+// Dense Bingham chains run in the eigenbasis of A (the sampler is equivariant under rotations: great circles, the uniform
+// direction and the density are all carried along), i.e. on the DIAGONAL kernel with the eigenvalues; states and retained samples
+// are rotated at the boundary (k_rotate_rows).  The reference holds the same decomposition (distributions.py:67-76).
+// GEOSSS_NO_EIG=1 keeps the dense matrix-vector kernel.
+static bool bingham_eig(const geosss_target* t) {
+    return t->kind == TGT_BINGHAM && !t->diag && !t->h_eig_rows.empty() && !std::getenv("GEOSSS_NO_EIG");
+}
+static bool bingham_diag_like(const geosss_target* t) { return t->diag || bingham_eig(t); }
+static bool gc_store_normals(const geosss_target* t) { return t->d < 64 || (t->kind == TGT_BINGHAM && !bingham_diag_like(t)); }
 
 static size_t gc_smem_bytes(const geosss_target* t, const GcParams& p) {
     const size_t pol = t->kind == TGT_BINGHAM ? BinghamGc::smem_floats(p)
@@ -258,9 +306,9 @@ static GcParams gc_params(const geosss_target* t) {
     GcParams p{};
     p.d = t->d;
     if (t->kind == TGT_BINGHAM) {
-        p.diag = t->diag;
-        p.a0 = t->diag ? t->Adiag.f : t->A.f;
-        p.a1 = t->has_b ? t->b.f : nullptr;
+        p.diag = bingham_diag_like(t) ? 1 : 0;
+        p.a0 = t->diag ? t->Adiag.f : (bingham_eig(t) ? t->eig_vals.f : t->A.f);
+        p.a1 = t->has_b ? (bingham_eig(t) ? t->eig_b.f : t->b.f) : nullptr;
     } else if (t->kind == TGT_VMF_MIX) {
         p.M = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f;
     } else {
@@ -422,19 +470,26 @@ extern "C" int geosss_target_create_bingham(int d, const double* A, const double
         for (int i = 0; i < d; ++i) dg[i] = A[(size_t)i * d + i];
         rc = t->Adiag.upload(dg.data(), d);
     }
-    if (!rc && !diag && d <= TC_MAX_D && (!b || d < TcBinghamEpi::NP_MAX)) {
+    if (!rc && !diag && d <= TC_MAX_D) {
         // x^T A x = sum_j w_j (v_j . x)^2: rows of W = eigenvectors (the reference holds the same decomposition, distributions.py:73-76)
         std::vector<double> sym((size_t)d * d), w, V;
         for (int i = 0; i < d; ++i)
             for (int j = 0; j < d; ++j) sym[(size_t)i * d + j] = 0.5 * (A[(size_t)i * d + j] + A[(size_t)j * d + i]);
         eigh_jacobi(d, sym, w, V);
-        t->eig_n_out = d + (b ? 1 : 0);
-        std::vector<double> rows((size_t)t->eig_n_out * d);
+        t->eig_n_out = (!b || d < TcBinghamEpi::NP_MAX) ? d + (b ? 1 : 0) : 0;  // 0: the Fisher row does not fit the tensor-core log_prob
+        std::vector<double> rows((size_t)(d + (b ? 1 : 0)) * d);
         for (int j = 0; j < d; ++j)
             for (int k = 0; k < d; ++k) rows[(size_t)j * d + k] = V[(size_t)k * d + j];
         if (b) for (int k = 0; k < d; ++k) rows[(size_t)d * d + k] = b[k];
+        t->h_eig_rows.assign(rows.begin(), rows.begin() + (size_t)d * d);
         rc = t->eig_rows.upload(rows.data(), rows.size());
         if (!rc) rc = t->eig_vals.upload(w.data(), d);
+        if (!rc && b) {
+            std::vector<double> wb(d, 0.0);
+            for (int j = 0; j < d; ++j)
+                for (int k = 0; k < d; ++k) wb[j] += rows[(size_t)j * d + k] * b[k];
+            rc = t->eig_b.upload(wb.data(), d);
+        }
     }
     if (rc) { t->release(); delete t; return rc; }
     *out = t;
@@ -632,6 +687,15 @@ extern "C" int geosss_target_cpd_grid_info(geosss_target_t t, double* cutoff, do
 
 extern "C" int geosss_target_dim(geosss_target_t t) { return t ? t->d : GEOSSS_E_INVALID; }
 
+// The eigenvector rows W (d, d) the float32 dense-Bingham kernels work in (chain coordinates y = W x); returns 1 when such a
+// system is in use for this target, 0 otherwise (rows_out untouched).
+extern "C" int geosss_target_bingham_eigenrows(geosss_target_t t, double* rows_out) {
+    if (!t || t->kind != TGT_BINGHAM) return fail(GEOSSS_E_INVALID, "bingham_eigenrows: not a Bingham target");
+    if (!bingham_eig(t)) return 0;
+    if (rows_out) std::memcpy(rows_out, t->h_eig_rows.data(), t->h_eig_rows.size() * sizeof(double));
+    return 1;
+}
+
 extern "C" int geosss_target_destroy(geosss_target_t t) {
     if (!t) return 0;
     t->release();
@@ -725,6 +789,7 @@ static int logp_tc(const TcpParams& tp, const float* x, float* out, int64_t N, c
 }
 
 static bool tc_enabled() { return !std::getenv("GEOSSS_NO_TC"); }
+static int tc_spin() { const char* e = std::getenv("GEOSSS_TC_SPIN"); return e ? std::atoi(e) : 0; }
 
 static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
     LpParams p{};
@@ -732,21 +797,26 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
     const float* xi = static_cast<const float*>(x);
     float* o = static_cast<float*>(out);
     switch (t->kind) {
-        case TGT_VMF_MIX:
-            if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
+        case TGT_VMF_MIX: {
             if (!fast_supported(t->kind, t->d, t->K, t->single)) return logp_vmf_const(t, xi, o, N, st);
             p.K = t->K; p.a0 = t->mu.f; p.a1 = t->consts.f; p.single = t->single;
-            // chains x components contraction on the tensor cores for wide rows (K padded to 16 accumulator columns)
+            // chains x components contraction on the tensor cores for wide rows (K padded to 16 accumulator columns); the ragged
+            // tail of fewer than 128 rows runs on the SIMT kernel (K <= 8) or the literal one
+            auto simt = [&](const float* xs, float* os, int64_t n) {
+                return t->K <= LP_MAX_K ? launch_logp_tiled<VmfLp>(p, xs, os, n, st) : logp_literal<float>(t, xs, os, n, st);
+            };
             if (tc_enabled() && t->d >= 24 && tcp_fits<TcVmfEpi>(t->d, t->K)) {
-                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K, tcp_np(t->K)};
-                return logp_tc<TcVmfEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<VmfLp>(p, xs, os, n, st); });
+                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K, tcp_np(t->K), tc_spin()};
+                return logp_tc<TcVmfEpi>(tp, xi, o, N, st, simt);
             }
+            if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
             return launch_logp_tiled<VmfLp>(p, xi, o, N, st);
+        }
         case TGT_BINGHAM:
             // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
             if (!t->diag && t->d >= 8 && t->eig_n_out > 0 && tcp_fits<TcBinghamEpi>(t->d, t->eig_n_out) && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
                 p.diag = 0; p.a0 = t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
-                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out, tcp_np(t->eig_n_out)};
+                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out, tcp_np(t->eig_n_out), tc_spin()};
                 return logp_tc<TcBinghamEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<BinghamLp>(p, xs, os, n, st); });
             }
             // round-1 kernel (one block-wide phase at a time), kept selectable for A/B runs: GEOSSS_TC_V1=1
@@ -777,7 +847,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
             p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
             if (tc_enabled() && t->d >= 24 && tcp_fits<TcCurvedEpi>(t->d, t->M)) {  // G = X knots^T on the tensor cores
-                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M, tcp_np(t->M)};
+                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M, tcp_np(t->M), tc_spin()};
                 return logp_tc<TcCurvedEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<CurvedLp>(p, xs, os, n, st); });
             }
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
@@ -834,6 +904,7 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     auto* s = new (std::nothrow) geosss_sampler();
     if (!s) return fail(GEOSSS_E_NOMEM, "out of host memory");
     s->t = t; s->kind = kind; s->dtype = dtype; s->path = path; s->N = N; s->seed = seed; s->chain0 = chain_offset;
+    s->eig = path == GEOSSS_PATH_FAST && bingham_eig(t);
     if (cudaGetDevice(&s->device) != cudaSuccess) { delete s; return fail(GEOSSS_E_CUDA, "sampler_create: no current CUDA device"); }
     const size_t es = s->esize();
     s->state_bytes = (size_t)N * t->d * es;
@@ -882,6 +953,7 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
 extern "C" int geosss_sampler_set_state(geosss_sampler_t s, const void* x, void* stream) {
     if (!s || !x) return fail(GEOSSS_E_INVALID, "set_state: bad arguments");
     CU(cudaMemcpyAsync(s->state, x, (size_t)s->N * s->t->d * s->esize(), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    if (s->eig) return rotate_rows(s, true, s->state, s->N, 1, s->t->d, 0, static_cast<cudaStream_t>(stream));
     return 0;
 }
 
@@ -889,6 +961,7 @@ extern "C" int geosss_sampler_get_state(geosss_sampler_t s, void* x, uint64_t* n
     if (!s) return fail(GEOSSS_E_INVALID, "get_state: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x) CU(cudaMemcpyAsync(x, s->state, (size_t)s->N * s->t->d * s->esize(), cudaMemcpyDeviceToDevice, st));
+    if (x && s->eig) { int rc = rotate_rows(s, false, x, s->N, 1, s->t->d, 0, st); if (rc) return rc; }
     if (n_reject) CU(cudaMemcpyAsync(n_reject, s->n_reject, (size_t)s->N * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
     return 0;
 }
@@ -908,6 +981,14 @@ extern "C" int geosss_sampler_trace_out(geosss_sampler_t s, const double* direct
     } else {
         std::vector<float> f(d);
         for (size_t i = 0; i < d; ++i) f[i] = (float)direction_host[i];
+        if (s->eig) {  // x . v = y . (W v) for the chain's eigenbasis coordinates y = W x
+            const std::vector<double>& W = s->t->h_eig_rows;
+            for (size_t i = 0; i < d; ++i) {
+                double acc = 0;
+                for (size_t j = 0; j < d; ++j) acc += W[i * d + j] * direction_host[j];
+                f[i] = (float)acc;
+            }
+        }
         CU(cudaMemcpy(s->fdir, f.data(), d * 4, cudaMemcpyHostToDevice));
     }
     s->fout = trace_out;
@@ -993,6 +1074,10 @@ extern "C" int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, in
     a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
     int rc = s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
     if (rc) return rc;
+    if (s->eig && samples_out) {  // retained samples back into the caller's coordinates, in place
+        rc = rotate_rows(s, false, samples_out, n_steps / thin, s->N, a.ss_step, a.ss_chain, st);
+        if (rc) return rc;
+    }
     s->step += (uint64_t)n_steps;
     return 0;
 }
@@ -1023,6 +1108,11 @@ extern "C" int geosss_sampler_set_state_host(geosss_sampler_t s, const double* x
         for (size_t i = 0; i < n; ++i) f[i] = (float)x_host[i];
         CU(cudaMemcpy(s->state, f, n * 4, cudaMemcpyHostToDevice));
     }
+    if (s->eig) {
+        int rc = rotate_rows(s, true, s->state, s->N, 1, s->t->d, 0, nullptr);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(nullptr));
+    }
     return 0;
 }
 
@@ -1034,7 +1124,18 @@ extern "C" int geosss_sampler_get_state_host(geosss_sampler_t s, double* x_host,
             CU(cudaMemcpy(x_host, s->state, n * 8, cudaMemcpyDeviceToHost));
         } else {
             std::vector<float> f(n);
-            CU(cudaMemcpy(f.data(), s->state, n * 4, cudaMemcpyDeviceToHost));
+            if (s->eig) {  // back to the caller's coordinates through a scratch copy
+                void* tmp = nullptr;
+                CU(cudaMalloc(&tmp, n * 4));
+                cudaError_t e = cudaMemcpy(tmp, s->state, n * 4, cudaMemcpyDeviceToDevice);
+                int rc = e == cudaSuccess ? rotate_rows(s, false, tmp, s->N, 1, s->t->d, 0, nullptr) : 0;
+                if (e == cudaSuccess && !rc) e = cudaMemcpy(f.data(), tmp, n * 4, cudaMemcpyDeviceToHost);
+                cudaFree(tmp);
+                if (rc) return rc;
+                if (e != cudaSuccess) return fail(GEOSSS_E_CUDA, "get_state_host: %s", cudaGetErrorString(e));
+            } else {
+                CU(cudaMemcpy(f.data(), s->state, n * 4, cudaMemcpyDeviceToHost));
+            }
             for (size_t i = 0; i < n; ++i) x_host[i] = (double)f[i];
         }
     }

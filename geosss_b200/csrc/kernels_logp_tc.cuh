@@ -49,7 +49,25 @@ struct TcpParams {
     float kappa;
     int d, n_out;
     int np;           // accumulator columns per half: n_out rounded up to 16 (UMMA N is a multiple of 16 at M = 128)
+    int spin;         // 1: barrier waits poll with mbarrier.test_wait, 0 (default): mbarrier.try_wait
 };
+
+// Waits of the role warps: mbarrier.try_wait (may suspend the warp for a time slice) or, with GEOSSS_TC_SPIN=1, polling with
+// mbarrier.test_wait.  Measured on B200 (r2 sweep): polling is 2-7 % SLOWER on every shape, so try_wait is the default.
+__device__ __forceinline__ void tcp_wait(uint64_t* bar, uint32_t parity, int spin) {
+    if (!spin) { mbar_wait(bar, parity); return; }
+    uint32_t done = 0;
+    for (uint32_t n = 0; !done; ++n) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (n > (1u << 28)) __trap();  // a lost hand-off must not hang the GPU
+    }
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -251,7 +269,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         // ===== producer
         for (int it = 0; it < n_it; ++it) {
             const int r = it % R, use = it / R;
-            if (use > 0) mbar_wait(&raw_empty[r], (uint32_t)(use - 1) & 1u);
+            if (use > 0) tcp_wait(&raw_empty[r], (uint32_t)(use - 1) & 1u, P.spin);
             if (lane == 0) {
                 const float* src = x + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)tile_floats;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -272,8 +290,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         const uint32_t kdesc = (uint32_t)(NS * 8 * 4) >> 4;  // one K block further, in descriptor address units (16 bytes)
         for (int it = 0; it < n_it; ++it) {
             const int s = it % S, use = it / S;
-            mbar_wait(&op_full[s], (uint32_t)use & 1u);
-            if (use > 0) mbar_wait(&acc_empty[s], (uint32_t)(use - 1) & 1u);
+            tcp_wait(&op_full[s], (uint32_t)use & 1u, P.spin);
+            if (use > 0) tcp_wait(&acc_empty[s], (uint32_t)(use - 1) & 1u, P.spin);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t xh = tmem + (uint32_t)(s * stage_cols), xl = xh + (uint32_t)KP, acc = xl + (uint32_t)KP;
             if (elected) {
@@ -306,9 +324,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         for (int it = g; it < n_it; it += 2) {
             const int s = it % S, use = it / S, r = it % R;
             const uint32_t xh = lane_base + (uint32_t)(s * stage_cols), xl = xh + (uint32_t)KP;
-            mbar_wait(&raw_full[r], (uint32_t)(it / R) & 1u);
+            tcp_wait(&raw_full[r], (uint32_t)(it / R) & 1u, P.spin);
             if (use > 0) {  // the MMAs of the tile that used these operand columns last have completed
-                mbar_wait(&acc_full[s], (uint32_t)(use - 1) & 1u);
+                tcp_wait(&acc_full[s], (uint32_t)(use - 1) & 1u, P.spin);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             const float* rowp = raw + (size_t)r * stage_floats + (size_t)row * d;
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
             const int s = it % S, use = it / S;
             const uint32_t acc = lane_base + (uint32_t)(s * stage_cols + 2 * KP);
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TCP_ROWS;
-            mbar_wait(&acc_full[s], (uint32_t)use & 1u);
+            tcp_wait(&acc_full[s], (uint32_t)use & 1u, P.spin);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             typename Epi::State st;
             Epi::begin(st);

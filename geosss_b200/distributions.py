@@ -215,6 +215,18 @@ class Bingham(Distribution):
     def _fisher(self):
         return None
 
+    def device_eigenrows(self, device=None):
+        """Eigenvector rows ``W`` of the coordinates ``y = W x`` in which the float32 kernels evaluate and sample a DENSE
+        ``A`` (d <= 64), or None (diagonal ``A``, larger d).  Chains started from the same seed use the seed's normal
+        draws in those coordinates, i.e. the direction ``W.T @ z`` in the caller's."""
+        dev = _device.resolve_device(device)
+        W = np.empty((self.d, self.d))
+        with torch.cuda.device(dev):
+            rc = _lib.lib().geosss_target_bingham_eigenrows(self._handle(dev), _lib.dptr(W))
+        if rc < 0:
+            _lib.check(rc)
+        return W if rc == 1 else None
+
     def _create_handle(self, lib):
         A = np.ascontiguousarray(self.A)
         b = self._fisher()

@@ -63,13 +63,21 @@ class Sampler:
                  chain_offset=0):
         self.target = distribution
         self._torch_io = isinstance(initial_state, torch.Tensor)
-        x0 = initial_state.detach().cpu().numpy() if self._torch_io else np.asarray(initial_state)
-        if x0.ndim not in (1, 2):
+        # CUDA initial states stay on the device: no host round trip on the way into the sampler
+        self._cuda_state0 = initial_state.detach() if self._torch_io and initial_state.is_cuda else None
+        if not self._torch_io:
+            initial_state = np.asarray(initial_state)
+        if initial_state.ndim not in (1, 2):
             raise ValueError("initial_state must have shape (d,) or (N, d)")
-        self._single = x0.ndim == 1
-        # as upstream, the array is stored, not copied (mcmc.py:43); it is only ever replaced, never written to
-        self._host_state = np.asarray(x0, dtype=float).reshape(-1, x0.shape[-1])
-        self.N, self.d = self._host_state.shape
+        self._single = initial_state.ndim == 1
+        if self._cuda_state0 is not None:
+            self._host_state = None  # fetched from the device on demand (``state``)
+            self.N, self.d = (1, initial_state.shape[0]) if self._single else tuple(initial_state.shape)
+        else:
+            x0 = initial_state.detach().numpy() if self._torch_io else np.asarray(initial_state)
+            # as upstream, the array is stored, not copied (mcmc.py:43); it is only ever replaced, never written to
+            self._host_state = np.asarray(x0, dtype=float).reshape(-1, x0.shape[-1])
+            self.N, self.d = self._host_state.shape
         if distribution.d is not None and self.d != distribution.d:
             raise ValueError(f"initial_state has dimension {self.d}, target has {distribution.d}")
         self._code, self._tdtype, self._npdtype = _device.dtype_code(dtype)
@@ -103,8 +111,22 @@ class Sampler:
                     self.path = "literal"
                 _lib.check(rc)
                 self._h = h
-                _lib.check(lib.geosss_sampler_set_state_host(h, _lib.dptr(np.ascontiguousarray(self._host_state))))
+                if self._cuda_state0 is not None:
+                    x0 = self._cuda_state0.to(device=self.device, dtype=self._tdtype).reshape(self.N, self.d).contiguous()
+                    _lib.check(lib.geosss_sampler_set_state(h, x0.data_ptr(), _device.stream_ptr(self.device)))
+                    torch.cuda.current_stream(self.device).synchronize()  # x0 may be a temporary
+                    self._cuda_state0 = None
+                else:
+                    _lib.check(lib.geosss_sampler_set_state_host(h, _lib.dptr(np.ascontiguousarray(self._host_state))))
         return self._h
+
+    def _state_device(self):
+        """(N, d) CUDA tensor of the current positions in the sampler's dtype (device-to-device copy)."""
+        h = self._sampler()
+        x = torch.empty((self.N, self.d), dtype=self._tdtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_get_state(h, x.data_ptr(), None, _device.stream_ptr(self.device)))
+        return x
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -119,6 +141,8 @@ class Sampler:
     @property
     def state(self):
         """Current state(s), float64 on the host: (d,) for one chain, (N, d) otherwise."""
+        if self._h is None and self._host_state is None:
+            self._host_state = self._cuda_state0.detach().cpu().numpy().astype(float).reshape(self.N, self.d)
         if self._h is not None:
             buf = np.empty((self.N, self.d))
             with torch.cuda.device(self.device):
@@ -134,6 +158,7 @@ class Sampler:
     def state(self, value):
         value = np.array(value, dtype=float).reshape(self.N, self.d)
         self._host_state = value
+        self._cuda_state0 = None
         if self._h is not None:
             with torch.cuda.device(self.device):
                 _lib.check(_lib.lib().geosss_sampler_set_state_host(self._h, _lib.dptr(np.ascontiguousarray(value))))
@@ -153,10 +178,17 @@ class Sampler:
         self._sync_counters()
         return self._n_reject
 
+    def _reject_total(self):
+        """Sum of the per-chain counters, reduced on the device (one scalar crosses to the host)."""
+        cnt = torch.empty(self.N, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_sampler_get_state(self._h, None, cnt.data_ptr(), _device.stream_ptr(self.device)))
+        return int(cnt.sum().item())
+
     def _sync_counters(self):
         if self._h is None:
             return
-        total = int(self.n_reject_per_chain.sum())
+        total = self._reject_total()
         steps = self.rng.steps_done
         # the reference evaluates log_prob 2 + r times per transition (mcmc.py:364-371,389-397)
         calls = 2 * (steps - self._steps_counted) * self.N + (total - self._rej_seen)
@@ -246,7 +278,7 @@ class Sampler:
         if on_device:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, device=self.device)
             if keeps_current:
-                buf[:, 0] = torch.as_tensor(self._positions(), dtype=self._tdtype, device=self.device)
+                buf[:, 0] = self._state_device()
             if n_skip:
                 self._run_device(n_skip, None)
             if n_new:  # every chain appends its rows behind its own slot 0: (N, n_out, d) chain-major
@@ -255,7 +287,7 @@ class Sampler:
         else:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)
             if keeps_current:
-                cur = self._host_state if self.rng.steps_done == 0 else self._positions()
+                cur = self._host_state if (self.rng.steps_done == 0 and self._host_state is not None) else self._positions()
                 np.copyto(buf[0].numpy(), cur, casting="same_kind")  # one pass, float64 -> sampler dtype
             dst = buf[1:] if keeps_current else buf
             with torch.cuda.device(self.device):
@@ -387,7 +419,7 @@ class MetropolisHastings(Sampler):
     def _sync_counters(self):
         if self._h is None:
             return
-        self._n_accept = int(self.n_reject_per_chain.sum())
+        self._n_accept = self._reject_total()
         steps = self.rng.steps_done
         new = (steps - self._steps_counted) * self.N
         # upstream evaluates log_prob twice per transition (mcmc.py:149-153,287-289) and, for HMC,

@@ -107,6 +107,10 @@ int geosss_target_cpd_set_translation(geosss_target_t t, const double* translati
  * GEOSSS_CPD_DENSE=1 in the environment forces the dense pair sum. */
 int geosss_target_cpd_grid_info(geosss_target_t t, double* cutoff, double* mean_candidates, int* n_cells, int* n_entries);
 int geosss_target_dim(geosss_target_t t); /* ambient dimension d of the state */
+/* Dense Bingham targets (d <= 64) hold the eigenvector rows W of A (reference: Bingham.U, geosss/distributions.py:67-76): the
+ * float32 throughput kernels evaluate x^T A x and run the chains in the coordinates y = W x.  Returns 1 and fills rows_out
+ * ((d, d) row-major, may be NULL) when that system is in use, 0 when not (diagonal A, d > 64, GEOSSS_NO_EIG). */
+int geosss_target_bingham_eigenrows(geosss_target_t t, double* rows_out);
 int geosss_target_destroy(geosss_target_t t);
 
 /* x: (N, d) device, out: (N) device, both of `dtype`. */

@@ -396,8 +396,13 @@ def test_tape_many_chains_ragged_block(golden):
 
 
 # ------------------------------------------------------------------ own Philox stream
-def oracle_chain(pdf_oracle, kind, x0, seed, chain, n, d, dtype, first_step=0):
+def oracle_chain(pdf_oracle, kind, x0, seed, chain, n, d, dtype, first_step=0, normals_to_caller=None):
+    """The float64 reference algorithm fed the device's Philox draws.  ``normals_to_caller`` (d, d): the device used the
+    normal draws in rotated coordinates y = W x (dense Bingham in its eigenbasis); the reference then gets z = W.T @ draws."""
     rng = philox.PhiloxChainRNG(seed=seed, chain=chain, kind=kind, d=d, dtype=dtype, first_step=first_step)
+    if normals_to_caller is not None:
+        draw = rng.standard_normal
+        rng.standard_normal = lambda m: normals_to_caller @ np.asarray(draw(m), dtype=float)
     smp = samplers.SliceSampler(kind, pdf_oracle.log_prob, np.array(x0, float), rng)
     return smp.sample(n + 1)[1:], np.array(smp.rejects_per_step)
 
@@ -512,9 +517,12 @@ def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, c
     smp = cls(pdf, x0, seed, dtype="float32", path="fast")
     got, nrej = run_with_rejections(smp, n)
     assert smp.path == "fast" and got.dtype == F32 and got.shape == (N, n, d)
+    # dense Bingham chains live in the eigenbasis of A on the device: the same draws are normals in those coordinates
+    W = pdf.device_eigenrows() if isinstance(pdf, gs.Bingham) else None
+    assert (W is not None) == (cfg in ("c4dense", "d10", "bf"))  # the dense matrices of the fixtures
     fc = FlipCount(f"k_gc_fast_{cfg}_{'shrink' if kind == samplers.SHRINK else 'reject'}")
     for c in range(N):
-        want, rej = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32)
+        want, rej = oracle_chain(ora, kind, x0[c], seed, c, n, d, F32, normals_to_caller=None if W is None else W.T)
         fc.add(got[c], nrej[c], want, rej)
     fc.check(1.0)
 
