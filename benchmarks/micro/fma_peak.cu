@@ -3,6 +3,35 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
+// packed FP32 pair (sm_100: fma.rn.f32x2 -> FFMA2, two FMAs per lane in one instruction)
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k2(float* out, int iters, float a, float b) {
+    unsigned long long x0 = pack2(threadIdx.x, 1.f), x1 = pack2(threadIdx.x + 1, 2.f), x2 = pack2(threadIdx.x + 2, 3.f), x3 = pack2(threadIdx.x + 3, 4.f);
+    unsigned long long x4 = pack2(threadIdx.x + 4, 1.f), x5 = pack2(threadIdx.x + 5, 2.f), x6 = pack2(threadIdx.x + 6, 3.f), x7 = pack2(threadIdx.x + 7, 4.f);
+    const unsigned long long y0 = pack2(a, a), y1 = pack2(b, b), y2 = pack2(a + b, a), y3 = pack2(a - b, b);
+    unsigned u0 = threadIdx.x, u1 = u0 * 3, u2 = u0 * 5, u3 = u0 * 7;
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 0) {  // 8 independent FFMA2 chains
+            x0 = ffma2(x0, y0, y1); x1 = ffma2(x1, y1, y2); x2 = ffma2(x2, y2, y3); x3 = ffma2(x3, y3, y0);
+            x4 = ffma2(x4, y0, y2); x5 = ffma2(x5, y1, y3); x6 = ffma2(x6, y2, y0); x7 = ffma2(x7, y3, y1);
+        } else {  // 4 FFMA2 + 8 integer ops
+            x0 = ffma2(x0, y0, y1); x1 = ffma2(x1, y1, y2); x2 = ffma2(x2, y2, y3); x3 = ffma2(x3, y3, y0);
+            u0 = (u0 ^ u1) + i; u1 = (u1 ^ u2) + i; u2 = (u2 ^ u3) + i; u3 = (u3 ^ u0) + i;
+        }
+    }
+    const unsigned long long s = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float((unsigned)s ^ (unsigned)(s >> 32) ^ u0 ^ u1 ^ u2 ^ u3);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -29,14 +58,14 @@ __global__ void __launch_bounds__(256) k(float* out, int iters, float a, float b
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
-template <int MODE> double run(const char* name, double ops_per_iter_thread) {
+template <int MODE, bool PACKED = false> double run(const char* name, double ops_per_iter_thread) {
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int blocks = sms * 8, threads = 256, iters = 20000;
     float* out; cudaMalloc(&out, (size_t)blocks * threads * 4);
-    k<MODE><<<blocks, threads>>>(out, 100, 1.0001f, 0.5f);
+    if (PACKED) k2<MODE><<<blocks, threads>>>(out, 100, 1.0001f, 0.5f); else k<MODE><<<blocks, threads>>>(out, 100, 1.0001f, 0.5f);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    k<MODE><<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
+    if (PACKED) k2<MODE><<<blocks, threads>>>(out, iters, 1.0001f, 0.5f); else k<MODE><<<blocks, threads>>>(out, iters, 1.0001f, 0.5f);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double ops = ops_per_iter_thread * iters * (double)blocks * threads;
@@ -52,5 +81,8 @@ int main() {
     run<1>("ffma_imm", 8);
     run<2>("mufu_ex2", 8);
     run<3>("ffma4_plus_alu8", 12);
+    // packed pairs: ops counted as warp INSTRUCTIONS per thread and iteration (an FFMA2 is one instruction, two FMAs per lane)
+    run<0, true>("ffma2_x8 (instructions)", 8);
+    run<1, true>("ffma2_x4_plus_alu8 (instructions)", 12);
     return 0;
 }
