@@ -221,6 +221,8 @@ struct geosss_sampler {
     double alpha = 0.5;
     int n_leap = 10;
     bool eig = false;                      // dense Bingham on the fast path: the chain lives in the eigenbasis of A
+    void* zbuf = nullptr;                  // great-circle kernels without stored normals: (ceil(d/4), N) float4 scratch (kernels_gc.cuh)
+    size_t zbuf_bytes = 0;
     size_t state_bytes = 0, ws_bytes = 0;  // sizes of the pooled blocks (g_pool)
     int device = 0;                        // device the blocks live on (current device at creation)
     bool is_mh() const { return kind >= GEOSSS_RWMH; }
@@ -940,6 +942,7 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     g_pool.put(s->state, s->state_bytes);
     g_pool.put(s->ws, s->ws_bytes);
     g_pool.put(s->n_reject, (size_t)s->N * sizeof(unsigned long long));
+    if (s->zbuf) cudaFree(s->zbuf);
     if (s->stepsize) cudaFree(s->stepsize);
     if (s->adapt_count) cudaFree(s->adapt_count);
     if (s->n_walk) cudaFree(s->n_walk);
@@ -1072,6 +1075,13 @@ extern "C" int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, in
         if (a.ss_chain < n_keep * (int64_t)s->t->d || a.sl_chain < n_keep) return fail(GEOSSS_E_INVALID, "run: chain stride smaller than a chain's output");
     }
     a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
+    // wide rows on the great-circle kernels (d >= 64, normals not kept in shared memory): scratch for the transition's normals
+    if (s->path == GEOSSS_PATH_FAST && s->t->kind != TGT_CPD && !s->zbuf && !gc_store_normals(s->t) && !std::getenv("GEOSSS_GC_REGEN") &&
+        !(s->t->kind == TGT_VMF_MIX && !fast_supported(s->t->kind, s->t->d, s->t->K, s->t->single))) {
+        s->zbuf_bytes = (size_t)((s->t->d + 3) / 4) * (size_t)s->N * 16;
+        if (cudaMalloc(&s->zbuf, s->zbuf_bytes) != cudaSuccess) { cudaGetLastError(); s->zbuf = nullptr; }  // fall back to regeneration
+    }
+    a.zbuf = s->zbuf;
     int rc = s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
     if (rc) return rc;
     if (s->eig && samples_out) {  // retained samples back into the caller's coordinates, in place

@@ -333,6 +333,12 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
     int since_keep = 0;
     int64_t kept = 0;
 
+    // Normals of the current transition for the accepted move x' = alpha x + beta z when they are not kept in shared memory:
+    // column layout (block b, chain c) -> zb[b * N], so that a warp's 32 lanes store / load 512 contiguous bytes.  Half of an
+    // on-the-fly transition was Philox + Box-Muller because the normals were drawn twice; 2 x 4 d bytes of (mostly L2 / HBM)
+    // traffic per transition replace the second draw (C3: 800 B x 2e9 /s = 1.6 TB/s, a quarter of the HBM bandwidth).
+    float4* zb = (!STORE && a.zbuf && live) ? static_cast<float4*>(a.zbuf) + c : nullptr;
+
     typename Policy::Coef co;
     pol.begin(co);
     float lo = 0.f, hi = 2.f, lnu = 0.f, dl_acc = 0.f, lp_x = 0.f;
@@ -354,11 +360,16 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
             if (STORE) {
                 for (int j = 0; j < d; ++j) { const float v = fmaf(alpha, xs[j], beta * us[j]); xs[j] = v; xx = fmaf(v, v, xx); }
             } else {
-                for (int b = 0; b < nbn; ++b) {  // dr still holds the counters of the transition being finished
-                    const U4 w = dr.block(b);
+                for (int b = 0; b < nbn; ++b) {
                     float n0, n1, n2, n3;
-                    box_muller_fast(w.x, w.y, n0, n1);
-                    box_muller_fast(w.z, w.w, n2, n3);
+                    if (zb) {  // the normals of this transition, parked in global memory by the prologue (coalesced 16-byte loads)
+                        const float4 n4 = zb[(size_t)b * a.N];
+                        n0 = n4.x; n1 = n4.y; n2 = n4.z; n3 = n4.w;
+                    } else {   // regenerated: dr still holds the counters of the transition being finished
+                        const U4 w = dr.block(b);
+                        box_muller_fast(w.x, w.y, n0, n1);
+                        box_muller_fast(w.z, w.w, n2, n3);
+                    }
                     const int j = 4 * b;
                     float v = fmaf(alpha, xs[j], beta * n0); xs[j] = v; xx = fmaf(v, v, xx);
                     if (j + 1 < d) { v = fmaf(alpha, xs[j + 1], beta * n1); xs[j + 1] = v; xx = fmaf(v, v, xx); }
@@ -435,6 +446,7 @@ __global__ void __launch_bounds__(gc_block(STORE)) k_gc_fast(GcParams P, RunArgs
                     float n0, n1, n2, n3;
                     box_muller_fast(w.x, w.y, n0, n1);
                     box_muller_fast(w.z, w.w, n2, n3);
+                    if (!STORE && zb) zb[(size_t)b * a.N] = make_float4(n0, n1, n2, n3);
                     const int j = 4 * b;
                     take(j, n0);
                     if (j + 1 < d) take(j + 1, n1);

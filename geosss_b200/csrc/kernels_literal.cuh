@@ -70,6 +70,8 @@ struct RunArgs {
     void* samples;        // (n_keep, N, d) or null
     void* logp;           // (n_keep, N) or null
     uint32_t* nrej;       // (n_keep, N) rejections of each kept transition (thin == 1) or null
+    void* zbuf;           // great-circle kernels with on-the-fly scores: (ceil(d/4), N) float4 scratch holding the transition's normals
+                          // between the prologue and the accepted move (null: they are regenerated from the Philox counter)
     const void* fdir;     // (d) direction v of the scalar test function f(x) = x . v, sampler dtype, or null
     void* fout;           // (n_keep, N) trace of f at the kept states (scalar layout like logp) or null
     unsigned long long* n_reject;  // (N) running totals
