@@ -199,7 +199,11 @@ template <int QUADS, bool EXACT> struct CurvedGcT {
             const float gb = fmaf(cs, c.gx[m], sn * c.gu[m]);
             const float p2 = (gb - ga * ca[m - 1]) * isa[m - 1];
             const bool inside = p2 >= 0.f && fmaf(ga, sa[m - 1], -p2 * ca[m - 1]) >= 0.f;
-            const float dot = inside ? fast_sqrt(fmaf(ga, ga, p2 * p2)) : (p2 < 0.f ? ga : gb);
+            // branch-free: the square root is one MUFU instruction; as a branch the compiler ran it at 7-10 active lanes per segment
+            // (profiles/r2_ncu_full_k_gc_fast_c3_2e20.txt; C3 1.76 -> 1.85e9 samples/s)
+            const float hyp = fast_sqrt(fmaf(ga, ga, p2 * p2));
+            const float end = p2 < 0.f ? ga : gb;
+            const float dot = inside ? hyp : end;
             // the reference ranks segments by arccos(clip(dot, -1, 1)) (spherical_curve.py:32,102): dots above
             // 1 (|x| > 1) tie at distance 0 and the first such segment wins, but its unclipped dot is returned
             const float dc = fminf(dot, 1.f);
