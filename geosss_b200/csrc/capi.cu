@@ -1006,10 +1006,22 @@ extern "C" int64_t geosss_sampler_steps_done(geosss_sampler_t s) { return s ? (i
 template <typename T, int KIND, bool TAPE> static int launch_literal(geosss_sampler* s, const RunArgs& a, cudaStream_t st) {
     geosss_target* t = s->t;
     const unsigned grid = (unsigned)((a.N + LANE_BLOCK - 1) / LANE_BLOCK);
+    RunArgs b = a;
+    const size_t lsm = t->kind == TGT_CPD ? 0 : lane_scratch_smem<T>(3, t->d);  // x / u / y in shared memory when they fit
+    b.ws_smem = lsm ? 1 : 0;
     switch (t->kind) {
-        case TGT_VMF_MIX: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->vmf<T>(), a); break;
-        case TGT_BINGHAM: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->bingham<T>(), a); break;
-        case TGT_CURVED_VMF: k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, 0, st>>>(t->curved<T>(), a); break;
+        case TGT_VMF_MIX:
+            if (lsm > 48 * 1024) CU(cudaFuncSetAttribute(k_sampler_lane<T, KIND, TAPE, VmfMixP<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, lsm, st>>>(t->vmf<T>(), b);
+            break;
+        case TGT_BINGHAM:
+            if (lsm > 48 * 1024) CU(cudaFuncSetAttribute(k_sampler_lane<T, KIND, TAPE, BinghamP<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, lsm, st>>>(t->bingham<T>(), b);
+            break;
+        case TGT_CURVED_VMF:
+            if (lsm > 48 * 1024) CU(cudaFuncSetAttribute(k_sampler_lane<T, KIND, TAPE, CurvedP<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+            k_sampler_lane<T, KIND, TAPE><<<grid, LANE_BLOCK, lsm, st>>>(t->curved<T>(), b);
+            break;
         case TGT_CPD: {
             const size_t smem = (size_t)CPD_WARPS * 3 * t->ns * sizeof(T);
             if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "cpd: source cloud too large for shared memory");

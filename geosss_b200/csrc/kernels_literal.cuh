@@ -67,6 +67,7 @@ struct RunArgs {
     const int64_t* tape_off;  // ... and (N+1) offsets into it
     void* state;          // (N, d) row-major, in/out
     void* ws;             // (3, d, N) column-major scratch
+    int ws_smem;          // 1: the lane kernels keep that scratch in shared memory instead ((planes, d, block) columns; set at launch when it fits)
     void* samples;        // (n_keep, N, d) or null
     void* logp;           // (n_keep, N) or null
     uint32_t* nrej;       // (n_keep, N) rejections of each kept transition (thin == 1) or null
@@ -91,6 +92,13 @@ struct RunArgs {
     int n_leap;                    // HMC leapfrog steps
 };
 
+// dynamic shared memory for the lane kernels' scratch: `planes` vectors of d elements per lane; 0 when that would leave fewer than
+// two blocks per SM (the kernels then use the global scratch)
+template <typename T> inline size_t lane_scratch_smem(int planes, int d) {
+    const size_t bytes = (size_t)planes * d * LANE_BLOCK * sizeof(T);
+    return bytes <= 100 * 1024 ? bytes : 0;
+}
+
 template <typename T, int KIND, bool TAPE> struct DrawsOf;
 template <typename T, int KIND> struct DrawsOf<T, KIND, false> {
     using type = PhiloxDraws<T>;
@@ -112,8 +120,11 @@ __global__ void __launch_bounds__(LANE_BLOCK) k_sampler_lane(P p, RunArgs a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.N) return;
     const int d = p.d;
-    T* ws = static_cast<T*>(a.ws);
-    SVec<T> x{ws + c, a.N}, u{ws + (int64_t)d * a.N + c, a.N}, y{ws + 2 * (int64_t)d * a.N + c, a.N};
+    // x / u / y of a lane: column layout, in shared memory when the launch found room for it (the global (3, d, N) scratch otherwise)
+    extern __shared__ __align__(16) unsigned char lane_smem_raw[];
+    T* ws = a.ws_smem ? reinterpret_cast<T*>(lane_smem_raw) + threadIdx.x : static_cast<T*>(a.ws) + c;
+    const int64_t stride = a.ws_smem ? (int64_t)blockDim.x : a.N, plane = (int64_t)d * stride;
+    SVec<T> x{ws, stride}, u{ws + plane, stride}, y{ws + 2 * plane, stride};
     T* st = static_cast<T*>(a.state) + c * d;
     for (int j = 0; j < d; ++j) x[j] = st[j];
 

@@ -38,9 +38,10 @@ __global__ void __launch_bounds__(LANE_BLOCK) k_mh_lane(P p, int kind, RunArgs a
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.N) return;
     const int d = p.d;
-    T* ws = static_cast<T*>(a.ws);
-    const int64_t plane = (int64_t)d * a.N;
-    SVec<T> x{ws + c, a.N}, v{ws + plane + c, a.N}, xp{ws + 2 * plane + c, a.N}, vp{ws + 3 * plane + c, a.N}, g{ws + 4 * plane + c, a.N};
+    extern __shared__ __align__(16) unsigned char lane_smem_raw[];  // the five vectors of a lane, when the launch found room (RunArgs::ws_smem)
+    T* ws = a.ws_smem ? reinterpret_cast<T*>(lane_smem_raw) + threadIdx.x : static_cast<T*>(a.ws) + c;
+    const int64_t stride = a.ws_smem ? (int64_t)blockDim.x : a.N, plane = (int64_t)d * stride;
+    SVec<T> x{ws, stride}, v{ws + plane, stride}, xp{ws + 2 * plane, stride}, vp{ws + 3 * plane, stride}, g{ws + 4 * plane, stride};
     T* st = static_cast<T*>(a.state) + c * d;
     T* mom = static_cast<T*>(a.momentum) + c * d;
     for (int j = 0; j < d; ++j) { x[j] = st[j]; v[j] = mom[j]; }

@@ -26,8 +26,19 @@ template <typename T, class P> int launch_mh(const P& p, int kind, bool tape, co
         }
     } else {
         const unsigned grid = (unsigned)((a.N + LANE_BLOCK - 1) / LANE_BLOCK);
-        if (tape) k_mh_lane<T, true><<<grid, LANE_BLOCK, 0, st>>>(p, kind, a);
-        else k_mh_lane<T, false><<<grid, LANE_BLOCK, 0, st>>>(p, kind, a);
+        RunArgs b = a;
+        const size_t smem = lane_scratch_smem<T>(5, p.d);  // x, v, proposal x / v, gradient in shared memory when they fit
+        b.ws_smem = smem ? 1 : 0;
+        cudaError_t e = cudaSuccess;
+        if (tape) {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_mh_lane<T, true, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            k_mh_lane<T, true><<<grid, LANE_BLOCK, smem, st>>>(p, kind, b);
+        } else {
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k_mh_lane<T, false, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            k_mh_lane<T, false><<<grid, LANE_BLOCK, smem, st>>>(p, kind, b);
+        }
     }
     return (int)cudaGetLastError();
 }
