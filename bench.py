@@ -306,6 +306,14 @@ def run_extras(a, gs, dev, rank, world, barrier, max_over_ranks, hbm_peak, fp32_
                               "ess_per_sec": rel * value, "chains_used": n_ess * world, "draws": draws,
                               "estimator": "rank-normalised split bulk ESS"}
                 del se, tr
+                if testfn != "logp":
+                    # the same figure from streaming accumulators: 2000 transitions folded in chunks of 250, nothing retained
+                    # (csrc/diag.cuh:k_ess_stream_update; plain multi-chain autocovariance estimator, lags < 250)
+                    ss = cls(pdf, torch.as_tensor(x0[:n_ess]).to(dev), 48385, chain_offset=e_off)
+                    _, rel_s = diagnostics.streaming_ess(ss, 2000, direction, burnin=200, chunk=250, max_lag=250)
+                    rec["ess_streaming"] = {"relative_ess": rel_s, "ess_per_sec": rel_s * value, "draws": 2000, "chunk": 250, "max_lag": 250,
+                                            "estimator": "multi-chain autocovariance ESS from streaming per-chain sums"}
+                    del ss
             except Exception as exc:
                 rec["ess"] = {"error": str(exc)}
         except Exception as exc:  # one failing configuration must not take the bench line down

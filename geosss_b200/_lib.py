@@ -50,6 +50,8 @@ SIGNATURES = {
     "geosss_sampler_get_state_host": (_i, [_p, _pd, _p]),
     "geosss_sampler_run_host": (_i, [_p, _i64, _i64, _p]),
     "geosss_diag_ess_partials": (_i, [_p, _i, _i, _i64, _i64, _i, _p, _i, _p, _p]),
+    "geosss_diag_stream_update": (_i, [_p, _i, _i, _i64, _i64, _i64, _i, _p, _p]),
+    "geosss_diag_stream_finish": (_i, [_p, _i64, _i64, _i, _p, _p]),
     "geosss_sampler_mh_configure": (_i, [_p, C.c_double, C.c_double, _i]),
     "geosss_sampler_mh_reset": (_i, [_p, _i64]),
     "geosss_sampler_mh_momenta_out": (_i, [_p, _p]),

@@ -1440,6 +1440,36 @@ extern "C" int geosss_diag_ess_partials(const void* samples, int dtype, int layo
     return 0;
 }
 
+extern "C" int geosss_diag_stream_update(const void* trace, int dtype, int layout, int64_t n_new, int64_t n_chains, int64_t n_before,
+                                         int max_lag, double* acc, void* stream) {
+    if (layout != GEOSSS_STEP_MAJOR && layout != GEOSSS_CHAIN_MAJOR) return fail(GEOSSS_E_INVALID, "diag_stream_update: unknown layout");
+    if (!trace || !acc || n_new < 1 || n_chains < 1 || n_before < 0 || max_lag < 1) return fail(GEOSSS_E_INVALID, "diag_stream_update: bad arguments");
+    const size_t smem = (size_t)(max_lag + n_new) * sizeof(float);
+    if (smem > 200 * 1024) return fail(GEOSSS_E_UNSUPPORTED, "diag_stream_update: max_lag + chunk length must stay below 51200");
+    const int64_t step_stride = layout == GEOSSS_STEP_MAJOR ? n_chains : 1, chain_stride = layout == GEOSSS_STEP_MAJOR ? 1 : n_new;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == GEOSSS_F64) {
+        CU(cudaFuncSetAttribute(k_ess_stream_update<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ess_stream_update<double><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const double*>(trace), n_new, step_stride, chain_stride,
+                                                                                  n_before, max_lag, acc);
+    } else {
+        CU(cudaFuncSetAttribute(k_ess_stream_update<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ess_stream_update<float><<<(unsigned)n_chains, DIAG_BLOCK, smem, st>>>(static_cast<const float*>(trace), n_new, step_stride, chain_stride,
+                                                                                 n_before, max_lag, acc);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int geosss_diag_stream_finish(const double* acc, int64_t n_chains, int64_t n_total, int max_lag, double* out, void* stream) {
+    if (!acc || !out || n_chains < 1 || n_total < 2 || max_lag < 1) return fail(GEOSSS_E_INVALID, "diag_stream_finish: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(cudaMemsetAsync(out, 0, (size_t)(max_lag + 2) * sizeof(double), st));
+    k_ess_stream_finish<<<(unsigned)((n_chains + DIAG_BLOCK - 1) / DIAG_BLOCK), DIAG_BLOCK, 0, st>>>(acc, n_chains, n_total, max_lag, out);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int geosss_diag_path_stats(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
                                       const double* modes, int n_modes, int sign_labels, double* out, void* stream) {
     if (layout != GEOSSS_STEP_MAJOR && layout != GEOSSS_CHAIN_MAJOR) return fail(GEOSSS_E_INVALID, "diag_path_stats: unknown layout");

@@ -57,6 +57,74 @@ __global__ void __launch_bounds__(DIAG_BLOCK) k_ess_partials(const T* __restrict
     }
 }
 
+// Streaming form of the same estimator: a run of any length is folded in, chunk by chunk, without ever being retained
+// (C3 at 2^20 chains keeps "last state + moments").  The sampler kernels write the scalar test function of a
+// chunk of transitions (RunArgs::fout, 4 bytes per kept transition), k_ess_stream_update folds the chunk into per-chain
+// accumulators and the chunk buffer is reused:
+//   acc[c] = { S = sum f,  P[l] = sum_{t >= l} f_t f_{t-l} (l < L),  head[i] = f_i (i < L),  tail[i] = the last L values }
+// (1 + 3 L doubles per chain).  k_ess_stream_finish turns them into the partial sums k_ess_partials produces
+// (autocovariance about the chain mean, biased 1/n):  n acov(l) = P[l] - m (2 S - last_l - first_l) + (n - l) m^2  with
+// last_l / first_l the sums of the last / first l values.  Products are accumulated in double.
+template <typename T>
+__global__ void __launch_bounds__(DIAG_BLOCK) k_ess_stream_update(const T* __restrict__ trace, int64_t n_new, int64_t step_stride,
+                                                                  int64_t chain_stride, int64_t n_before, int L, double* __restrict__ acc) {
+    extern __shared__ float ext[];  // L values carried from earlier chunks, then the n_new values of this one
+    __shared__ double red[DIAG_BLOCK / 32];
+    const int64_t c = blockIdx.x;
+    double* a = acc + c * (1 + 3 * (int64_t)L);
+    double *P = a + 1, *head = a + 1 + L, *tail = a + 1 + 2 * (int64_t)L;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) ext[i] = (float)tail[i];
+    double part = 0.0;
+    for (int64_t t = threadIdx.x; t < n_new; t += blockDim.x) {
+        const float f = (float)trace[t * step_stride + c * chain_stride];
+        ext[L + t] = f;
+        part += (double)f;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    // lagged products of the new values with everything before them (a partner older than the run does not exist)
+    const int64_t valid_before = n_before < L ? n_before : L;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        double s = 0.0;
+        int64_t t0 = l - valid_before;  // first new index whose partner exists
+        if (t0 < 0) t0 = 0;
+        for (int64_t t = t0; t < n_new; ++t) s += (double)ext[L + t] * (double)ext[L + t - l];
+        P[l] += s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < DIAG_BLOCK / 32; ++w) s += red[w];
+        a[0] += s;
+    }
+    // the first L values of the run, and the new last L values
+    for (int64_t i = threadIdx.x; i < L; i += blockDim.x) {
+        if (i >= n_before && i - n_before < n_new) head[i] = (double)ext[L + i - n_before];
+        const int64_t src = n_new + i;  // position in ext of the i-th of the last L values (ext holds L + n_new values)
+        tail[i] = (double)ext[src];
+    }
+}
+
+// out: max_lag + 2 doubles as for k_ess_partials, zeroed by the caller; one thread per chain
+static __global__ void __launch_bounds__(DIAG_BLOCK) k_ess_stream_finish(const double* __restrict__ acc, int64_t n_chains, int64_t n, int L,
+                                                                         double* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const double* a = acc + c * (1 + 3 * (int64_t)L);
+    const double *P = a + 1, *head = a + 1 + L, *tail = a + 1 + 2 * (int64_t)L;
+    const double S = a[0], m = S / (double)n;
+    atomicAdd(out + L, m);
+    atomicAdd(out + L + 1, m * m);
+    double first = 0.0, last = 0.0;
+    for (int l = 0; l < L && l < n; ++l) {
+        if (l > 0) { first += head[l - 1]; last += tail[L - l]; }  // sums of the first / last l values
+        const double cov = (P[l] - m * (2.0 * S - last - first) + (double)(n - l) * m * m) / (double)n;
+        atomicAdd(out + l, cov);
+    }
+}
+
 // Path statistics of the retained draws: mode populations (argmax_k x . mode_k,
 // scripts/vMF_diagnostics.py:333-342), hops between labels of successive draws of a chain
 // (np.diff(np.sign(x . mode)) != 0, scripts/bingham.py:23-25, when sign_labels; label changes otherwise)

@@ -180,6 +180,75 @@ def bulk_ess(trace, group=None, relative=False):
     return 1.0 / tau if relative else m_total * half / tau
 
 
+class StreamingESS:
+    """Multi-chain autocovariance ESS of a scalar trace that is never retained: chunks of the trace (as the sampler
+    kernels write them, ``Sampler.sample_trace``) are folded into per-chain accumulators on the GPU
+    (``csrc/diag.cuh:k_ess_stream_update``: running sum, lagged products for lags < ``max_lag``, first and last values),
+    so a run of any length costs ``n_chains x (1 + 3 max_lag)`` doubles.  ``result()`` equals ``ess()`` of the whole
+    retained trace with the same ``max_lag`` (tested to 1e-9 against the float64 oracle); with torch.distributed the
+    partial sums are all-reduced, so every rank gets the ESS of all chains."""
+
+    def __init__(self, n_chains, max_lag, device=None):
+        self.device = _device.resolve_device(device)
+        self.n_chains, self.max_lag, self.n = int(n_chains), int(max_lag), 0
+        self.acc = torch.zeros((self.n_chains, 1 + 3 * self.max_lag), dtype=torch.float64, device=self.device)
+
+    def update(self, trace):
+        """``trace``: CUDA tensor ``(n_chains, n_new)``, contiguous."""
+        if not (isinstance(trace, torch.Tensor) and trace.is_cuda and trace.dim() == 2 and trace.shape[0] == self.n_chains):
+            raise ValueError("update needs a CUDA tensor (n_chains, n_new)")
+        trace = trace.contiguous()
+        code, _, _ = _device.dtype_code(trace.dtype)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_diag_stream_update(trace.data_ptr(), code, _lib.CHAIN_MAJOR, trace.shape[1], self.n_chains, self.n,
+                                                            self.max_lag, self.acc.data_ptr(), _device.stream_ptr(self.device)))
+        self.n += int(trace.shape[1])
+        return self
+
+    def partials(self):
+        out = torch.empty(self.max_lag + 2, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().geosss_diag_stream_finish(self.acc.data_ptr(), self.n_chains, self.n, self.max_lag, out.data_ptr(),
+                                                            _device.stream_ptr(self.device)))
+        return out
+
+    def result(self, group=None):
+        """(ESS, relative ESS) over all chains (of all ranks)."""
+        import torch.distributed as dist
+        part = self.partials()
+        total = torch.tensor([float(self.n_chains)], dtype=torch.float64, device=self.device)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(part, group=group)
+            dist.all_reduce(total, group=group)
+        return ess_from_partials(part.cpu().numpy(), self.n, int(total.item()))
+
+
+def streaming_ess(sampler, n_samples, direction=None, burnin=0, chunk=500, max_lag=250, group=None):
+    """ESS of ``x . direction`` over ``n_samples`` transitions of every chain of ``sampler`` without retaining states or
+    trace: the run is cut into chunks of ``chunk`` transitions whose scalar trace (4 bytes per transition and chain) is
+    folded into a ``StreamingESS`` and overwritten by the next chunk.  Returns (ESS, relative ESS)."""
+    n_samples, chunk = int(n_samples), int(min(chunk, n_samples))
+    if burnin:
+        sampler._run_device(determine_burnin_count(n_samples, burnin), None)
+    sampler._sampler()
+    acc = StreamingESS(sampler.N, min(max_lag, n_samples), sampler.device)
+    buf = None
+    done = 0
+    while done < n_samples:
+        n = min(chunk, n_samples - done)
+        if buf is None or buf.shape[1] != n:
+            buf = torch.empty((sampler.N, n), dtype=sampler._tdtype, device=acc.device)
+        tr = sampler.sample_trace(n, direction, out=buf)
+        acc.update(tr.reshape(sampler.N, n))
+        done += n
+    return acc.result(group)
+
+
+def determine_burnin_count(n_samples, burnin):
+    from .mcmc import determine_burnin
+    return determine_burnin(n_samples, burnin)
+
+
 def path_stats(samples, modes=None, sign_labels=False, group=None, chain_major=True):
     """One pass over retained draws on the GPU: label populations, hops and geodesic steps.
 

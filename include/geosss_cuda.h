@@ -229,6 +229,15 @@ int geosss_exact_bingham(int d, const double* v_host, const double* U_host, doub
 int geosss_diag_ess_partials(const void* samples, int dtype, int layout, int64_t n_draws, int64_t n_chains, int d,
                              const void* direction, int max_lag, double* out, void* stream);
 
+/* Streaming form of geosss_diag_ess_partials for runs that are never retained: a scalar trace (geosss_sampler_trace_out)
+ * is produced chunk by chunk and folded into per-chain accumulators acc ((n_chains, 1 + 3 max_lag) device doubles, zeroed
+ * by the caller before the first chunk); trace: (n_new, n_chains) or, CHAIN_MAJOR, (n_chains, n_new) of `dtype`; n_before:
+ * draws already folded in.  _finish writes the same max_lag + 2 partial sums as geosss_diag_ess_partials for the n_total
+ * draws seen.  Replaces keeping whole chains for `arviz.ess` / `acf` (scripts/ess_curve_vMF.py:97-130, utils.py:91-112). */
+int geosss_diag_stream_update(const void* trace, int dtype, int layout, int64_t n_new, int64_t n_chains, int64_t n_before,
+                              int max_lag, double* acc, void* stream);
+int geosss_diag_stream_finish(const double* acc, int64_t n_chains, int64_t n_total, int max_lag, double* out, void* stream);
+
 /* Path statistics of retained draws, same layouts as above.  modes: (n_modes, d) device doubles (NULL
  * when n_modes = 0).  out (device doubles, additive over chain shards):
  *   out[0 .. L-1]  draws per label; label = argmax_k x . mode_k, L = n_modes (mode populations of

@@ -733,6 +733,44 @@ def test_device_bulk_ess_matches_independent_restatement():
     assert abs(diagnostics.bulk_ess(torch.as_tensor(x, dtype=torch.float32).cuda(), relative=True) - 0.25 / 1.75) < 0.01
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_streaming_ess_equals_retained_trace_estimate(golden, dtype):
+    """Chunks of a scalar trace folded into per-chain accumulators on the device (never retained) give the estimator of the
+    whole trace: against the float64 oracle on AR(1) traces cut into ragged chunks (shorter than, equal to and longer than
+    max_lag), and for a real run -- streaming_ess(sampler) against ess() of the same chain's retained trace."""
+    from geosss_b200 import diagnostics
+    from oracle import ess as E
+    gen = np.random.default_rng(7)
+    N, n, L = 37, 1500, 64
+    x = np.zeros((N, n))
+    e = gen.standard_normal((N, n))
+    for t in range(1, n):
+        x[:, t] = 0.8 * x[:, t - 1] + e[:, t]
+    x += 3.0  # a mean far from zero: the raw lagged sums must cancel it
+    x = x.astype(np.float32).astype(float)  # the accumulators stage the trace in float32 (as k_ess_partials does), products in double
+    want = E.ess_multichain(x, L)
+    for cuts in ([n], [10, 40, 64, 65, 300, 7, 1014], [1] * 5 + [n - 5]):
+        acc = diagnostics.StreamingESS(N, L)
+        pos = 0
+        for m in cuts:
+            acc.update(torch.as_tensor(x[:, pos:pos + m], dtype=dtype).cuda())
+            pos += m
+        assert pos == n and acc.n == n
+        got, rel = acc.result()
+        assert abs(got - want) <= 1e-9 * want, (cuts[:3], got, want)
+        assert abs(rel - want / (N * n)) <= 1e-12
+    # a real run: the same seed gives the same chain with and without retaining the trace
+    g = golden("traj_c2")
+    pdf = mixture(100.0 * g["modes"])
+    x0 = torch.as_tensor(gs.sample_sphere(9, 300, seed=4)).cuda()
+    v = gs.sample_sphere(9, seed=5)
+    kw = dict(dtype="float32" if dtype == torch.float32 else "float64")
+    full = gs.ShrinkageSphericalSliceSampler(pdf, x0, 12, **kw).sample_trace(700, v, burnin=50)
+    want2, _ = diagnostics.ess(full.unsqueeze(-1), np.ones(1), 100)
+    got2, _ = diagnostics.streaming_ess(gs.ShrinkageSphericalSliceSampler(pdf, x0, 12, **kw), 700, v, burnin=50, chunk=128, max_lag=100)
+    assert abs(got2 - want2) <= 1e-6 * want2, (got2, want2)
+
+
 def test_sample_trace_equals_projection_of_retained_samples(golden):
     """The scalar test-function trace written by the sampler kernels (4 bytes per kept transition) equals
     x . direction of the fully retained chain, for the register-resident, the shared-memory and the literal kernels."""
