@@ -53,9 +53,16 @@ def main():
         x = x0(pdf, count)
         pdf.log_prob(x)   # float64: literal kernels
         pdf.gradient(x.float())
+    # tensor-core log_prob at the shapes it is tuned on, retained dense-Bingham samples (rotation kernel)
+    big = gs.MixtureModel([gs.VonMisesFisher(100.0 * m) for m in gs.sample_sphere(99, 8, seed=5)])
+    for pdf, count in ((big, 1 << 20), (curved, 1 << 20), (dense, 1 << 21)):
+        pdf.log_prob(x0(pdf, count).float())
+    gs.ShrinkageSphericalSliceSampler(dense, x0(dense, 1 << 14), 17).sample(8)
     # diagnostics and exact samplers
     chains = gs.ShrinkageSphericalSliceSampler(c2, x0(c2, 4096), 16).sample(500)
     dg.ess(chains)
+    dg.bulk_ess(chains[:, :, 0])
+    dg.streaming_ess(gs.ShrinkageSphericalSliceSampler(c2, x0(c2, 4096), 18), 400, chunk=100, max_lag=50)
     dg.mode_kl(chains, c2)
     gs.sample_vMF(c2.pdfs[0], 1 << 18, seed=1, as_torch=True)
     gs.sample_bingham(dense.A, 1 << 18, seed=2, as_torch=True)

@@ -107,21 +107,26 @@ __global__ void __launch_bounds__(DIAG_BLOCK) k_ess_stream_update(const T* __res
     }
 }
 
-// out: max_lag + 2 doubles as for k_ess_partials, zeroed by the caller; one thread per chain
+// out: max_lag + 2 doubles as for k_ess_partials, zeroed by the caller; one thread per chain, sums reduced over the warp first
 static __global__ void __launch_bounds__(DIAG_BLOCK) k_ess_stream_finish(const double* __restrict__ acc, int64_t n_chains, int64_t n, int L,
                                                                          double* __restrict__ out) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_chains) return;
-    const double* a = acc + c * (1 + 3 * (int64_t)L);
+    const bool live = c < n_chains;
+    const double* a = acc + (live ? c : 0) * (1 + 3 * (int64_t)L);
     const double *P = a + 1, *head = a + 1 + L, *tail = a + 1 + 2 * (int64_t)L;
-    const double S = a[0], m = S / (double)n;
-    atomicAdd(out + L, m);
-    atomicAdd(out + L + 1, m * m);
+    const double S = live ? a[0] : 0.0, m = S / (double)n;
+    auto warp_add = [&](double v, double* dst) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(dst, v);
+    };
+    warp_add(live ? m : 0.0, out + L);
+    warp_add(live ? m * m : 0.0, out + L + 1);
     double first = 0.0, last = 0.0;
     for (int l = 0; l < L && l < n; ++l) {
-        if (l > 0) { first += head[l - 1]; last += tail[L - l]; }  // sums of the first / last l values
+        if (l > 0 && live) { first += head[l - 1]; last += tail[L - l]; }  // sums of the first / last l values
         const double cov = (P[l] - m * (2.0 * S - last - first) + (double)(n - l) * m * m) / (double)n;
-        atomicAdd(out + l, cov);
+        warp_add(live ? cov : 0.0, out + l);
     }
 }
 
