@@ -396,10 +396,10 @@ def main_ours(a):
     algo_bytes = N * T * d * 4
     achieved = algo_bytes / avg_launch_s / 1e9
 
-    # DRAM traffic of this launch from the committed ncu capture (profiles/r1_traffic.json), when the workload matches
+    # DRAM traffic of this launch from the committed ncu capture (profiles/r2_traffic.json), when the workload matches
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tr = json.load(f)["k_vmf_fast<5,10,SHRINK>"]
         if a.sampler == "shrink" and tr["chains"] == N and tr["transitions_per_step"] == T and a.kappa == 100.0:
             traffic = tr["chain_major_quorum_22_default"]["dram_read"] + tr["chain_major_quorum_22_default"]["dram_write"]
