@@ -41,6 +41,7 @@ SIGNATURES = {
     "geosss_sampler_get_state": (_i, [_p, _p, _p, _p]),
     "geosss_sampler_run": (_i, [_p, _i64, _i64, _p, _p, _p, _p]),
     "geosss_sampler_run_layout": (_i, [_p, _i64, _i64, _i, _i64, _i64, _p, _p, _p, _p]),
+    "geosss_sampler_run_block": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "geosss_sampler_run_tape": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     "geosss_sampler_steps_done": (_i64, [_p]),
     "geosss_sampler_trace_out": (_i, [_p, _pd, _p]),

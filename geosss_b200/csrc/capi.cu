@@ -167,6 +167,7 @@ struct geosss_target {
     Arr A, b, Adiag;
     Arr eig_rows, eig_vals;  // dense A, d <= 64: eigenvectors as rows (+ b as row d when it fits), eigenvalues (kernels_logp_tc.cuh)
     Arr eig_b;               // the Fisher vector in the eigenbasis (W b)
+    Arr eig_cols;            // W transposed (rows = columns of W): the B operand of the rotation back, x = W^T y
     std::vector<double> h_eig_rows;  // host copy of the d eigenvector rows (direction of the test function, tests)
     int has_b = 0, diag = 0, eig_n_out = 0;
     // curved vMF
@@ -195,7 +196,7 @@ struct geosss_target {
                 (T)log_outlier, (T)beta, nt, ns, k, outlier, {(T)shift[0], (T)shift[1], (T)shift[2]}, dim};
     }
     void release() {
-        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &eig_rows, &eig_vals, &eig_b, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
+        for (Arr* a : {&mu, &logw, &logi0, &consts, &A, &b, &Adiag, &eig_rows, &eig_vals, &eig_b, &eig_cols, &knots, &ang, &cosang, &sinang, &tgt, &wt, &src, &logws}) a->release();
         for (void** q : {&d_cell, &d_entry, &d_tgt4}) { if (*q) cudaFree(*q); *q = nullptr; }
         has_grid = 0;
     }
@@ -221,6 +222,7 @@ struct geosss_sampler {
     double alpha = 0.5;
     int n_leap = 10;
     bool eig = false;                      // dense Bingham on the fast path: the chain lives in the eigenbasis of A
+    void* rot_tmp = nullptr;               // one 128-row tile of scratch for the ragged tail of a tensor-core rotation
     void* zbuf = nullptr;                  // great-circle kernels without stored normals: (ceil(d/4), N) float4 scratch (kernels_gc.cuh)
     size_t zbuf_bytes = 0;
     size_t state_bytes = 0, ws_bytes = 0;  // sizes of the pooled blocks (g_pool)
@@ -230,38 +232,83 @@ struct geosss_sampler {
 };
 
 // Rows of a strided (n_outer, n_inner, d) float array rotated in place: y = W x (to_eig) or x = W^T y; W (d, d) row-major,
-// rows = eigenvectors, staged in shared memory; one thread per row, the row in registers (d <= 64).
-static __global__ void __launch_bounds__(128) k_rotate_rows(const float* __restrict__ W, int d, int to_eig, float* __restrict__ data,
+// rows = eigenvectors.  A register-tiled FP32 GEMM: a block takes 128 consecutive rows, stages them TRANSPOSED in shared memory
+// (Xt[k][row], coalesced global reads), W as Ws[k][out]; thread (row group ri, output group oi = its warp) accumulates a 4 x 4 tile:
+// per k one 16-byte load of four rows' x_k, one 16-byte broadcast load of four outputs' weights, 16 FMAs.  Every output is the
+// sequential fmaf chain over k = 0..d-1, so a row's result does not depend on where it sits in the array (the continuation
+// "first sample of the next call == last sample of this one" stays bit-exact).  First versions (thread per row, 64 row values in
+// registers, one shared load per 1-4 FMAs) ran at 1.0-1.7e9 rows/s, load/store-unit bound.
+constexpr int ROT_ROWS = 128, ROT_RS = ROT_ROWS + 4;
+static __global__ void __launch_bounds__(512) k_rotate_rows(const float* __restrict__ W, int d, int to_eig, float* __restrict__ data,
                                                             int64_t n_outer, int64_t n_inner, int64_t s_outer, int64_t s_inner) {
-    __shared__ float Ws[TC_MAX_D * TC_MAX_D];
-    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
-        const int r = i / d, c = i - r * d;
-        Ws[to_eig ? c * d + r : i] = W[i];  // Ws[j * d + i] multiplies input j into output i
+    extern __shared__ __align__(16) float rot_smem[];
+    const int dp = (d + 3) & ~3;
+    float* Ws = rot_smem;             // d x dp:      Ws[k * dp + o] multiplies input k into output o
+    float* Xt = rot_smem + d * dp;    // dp x ROT_RS: Xt[k * ROT_RS + r], reused for the outputs
+    {
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5, n_warps_ = blockDim.x >> 5;
+        for (int k = warp_; k < d; k += n_warps_)
+            for (int o = lane_; o < dp; o += 32) Ws[k * dp + o] = o < d ? (to_eig ? W[o * d + k] : W[k * d + o]) : 0.f;
+    }
+    __shared__ float* row_base[ROT_ROWS];
+    const int64_t n_rows = n_outer * n_inner, row0 = (int64_t)blockIdx.x * ROT_ROWS;
+    const int rows_here = (int)(n_rows - row0 < ROT_ROWS ? n_rows - row0 : ROT_ROWS);
+    for (int r = threadIdx.x; r < ROT_ROWS; r += blockDim.x) {  // one 64-bit division per row, not per element
+        const int64_t idx = row0 + r;
+        row_base[r] = r < rows_here ? data + (idx / n_inner) * s_outer + (idx % n_inner) * s_inner : nullptr;
     }
     __syncthreads();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_outer * n_inner) return;
-    float* row = data + (idx / n_inner) * s_outer + (idx % n_inner) * s_inner;
-    float v[TC_MAX_D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int r = warp; r < ROT_ROWS; r += n_warps) {  // a warp per row: d contiguous floats
+        const float* src = row_base[r];
+        for (int c = lane; c < d; c += 32) Xt[c * ROT_RS + r] = src ? src[c] : 0.f;
+    }
+    __syncthreads();
+    const int ri = threadIdx.x & 31, oi = threadIdx.x >> 5;  // rows 4 ri .. 4 ri + 3, outputs 4 oi .. 4 oi + 3 (one output group per warp)
+    float acc[4][4];
 #pragma unroll
-    for (int j = 0; j < TC_MAX_D; ++j) v[j] = j < d ? row[j] : 0.f;
-    for (int i = 0; i < d; ++i) {
-        float a0 = 0.f, a1 = 0.f;
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int j = 0; j < TC_MAX_D; j += 2) {
-            if (j < d) a0 = fmaf(Ws[j * d + i], v[j], a0);
-            if (j + 1 < d) a1 = fmaf(Ws[(j + 1) * d + i], v[j + 1], a1);
-        }
-        row[i] = a0 + a1;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(Xt + k * ROT_RS + 4 * ri);
+        const float4 wv = *reinterpret_cast<const float4*>(Ws + k * dp + 4 * oi);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, wb[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(wb[b], xa[a], acc[a][b]);
+    }
+    __syncthreads();  // every warp has read the inputs: the tile now takes the outputs
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        *reinterpret_cast<float4*>(Xt + (4 * oi + b) * ROT_RS + 4 * ri) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
+    __syncthreads();
+    for (int r = warp; r < rows_here; r += n_warps) {
+        float* dst = row_base[r];
+        for (int c = lane; c < d; c += 32) dst[c] = Xt[c * ROT_RS + r];
     }
 }
 
-static int rotate_rows(const geosss_sampler* s, bool to_eig, void* data, int64_t n_outer, int64_t n_inner, int64_t s_outer, int64_t s_inner,
+// contiguous rows on the tensor cores (defined below, next to the other tcgen05 launches); returns 1 when it does not apply
+static int rotate_rows_tc(geosss_sampler* s, bool to_eig, float* data, int64_t rows, cudaStream_t st);
+
+static int rotate_rows(geosss_sampler* s, bool to_eig, void* data, int64_t n_outer, int64_t n_inner, int64_t s_outer, int64_t s_inner,
                        cudaStream_t st) {
     const int64_t rows = n_outer * n_inner;
     if (rows <= 0) return 0;
-    k_rotate_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(s->t->eig_rows.f, s->t->d, to_eig ? 1 : 0, static_cast<float*>(data), n_outer,
-                                                                    n_inner, s_outer, s_inner);
+    const int d = s->t->d, dp = (d + 3) & ~3;
+    // one dense (rows, d) matrix: 3xTF32 GEMM on tcgen05 (HBM-bound); strided layouts stay on the FP32 kernel below
+    const bool dense_rows = (n_inner == 1 ? s_outer == d : (s_inner == d && (n_outer == 1 || s_outer == n_inner * (int64_t)d)));
+    if (dense_rows) {
+        const int rc = rotate_rows_tc(s, to_eig, static_cast<float*>(data), rows, st);
+        if (rc <= 0) return rc;
+    }
+    const size_t smem = ((size_t)d * dp + (size_t)dp * ROT_RS) * sizeof(float);
+    CU(cudaFuncSetAttribute(k_rotate_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rotate_rows<<<(unsigned)((rows + ROT_ROWS - 1) / ROT_ROWS), 32 * (dp / 4), smem, st>>>(s->t->eig_rows.f, d, to_eig ? 1 : 0,
+                                                                                            static_cast<float*>(data), n_outer, n_inner, s_outer, s_inner);
     CU(cudaGetLastError());
     return 0;
 }
@@ -489,6 +536,12 @@ extern "C" int geosss_target_create_bingham(int d, const double* A, const double
         t->h_eig_rows.assign(rows.begin(), rows.begin() + (size_t)d * d);
         rc = t->eig_rows.upload(rows.data(), rows.size());
         if (!rc) rc = t->eig_vals.upload(w.data(), d);
+        if (!rc) {
+            std::vector<double> cols((size_t)d * d);
+            for (int j = 0; j < d; ++j)
+                for (int k = 0; k < d; ++k) cols[(size_t)k * d + j] = rows[(size_t)j * d + k];
+            rc = t->eig_cols.upload(cols.data(), cols.size());
+        }
         if (!rc && b) {
             std::vector<double> wb(d, 0.0);
             for (int j = 0; j < d; ++j)
@@ -796,6 +849,39 @@ static int logp_tc(const TcpParams& tp, const float* x, float* out, int64_t N, c
 static bool tc_enabled() { return !std::getenv("GEOSSS_NO_TC"); }
 static int tc_spin() { const char* e = std::getenv("GEOSSS_TC_SPIN"); return e ? std::atoi(e) : 0; }
 
+static int rotate_rows_tc(geosss_sampler* s, bool to_eig, float* data, int64_t rows, cudaStream_t st) {
+    const geosss_target* t = s->t;
+    const int d = t->d;
+    if (!tc_enabled() || d < 8 || !tcp_fits<TcRotateEpi>(d, d) || (reinterpret_cast<uintptr_t>(data) & 15) != 0 || !t->eig_cols.f) return 1;
+    if (!g_sm_count) {
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    TcpParams tp{to_eig ? t->eig_rows.f : t->eig_cols.f, nullptr, nullptr, 0.f, d, d, tcp_np(d), tc_spin(), data};
+    const int R = tcp_stages(d, tp.np, TcRotateEpi::AUX);
+    const size_t smem = tcp_smem_bytes(d, tp.np, TcRotateEpi::AUX, R);
+    CU(cudaFuncSetAttribute(k_logp_tc<TcRotateEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t full = rows / TCP_ROWS, tail = rows - full * TCP_ROWS;
+    if (full > 0) {
+        const int64_t grid = full < g_sm_count ? full : g_sm_count;
+        k_logp_tc<TcRotateEpi><<<(unsigned)grid, TCP_THREADS, smem, st>>>(tp, data, nullptr, full, R);
+        CU(cudaGetLastError());
+    }
+    if (tail > 0) {  // the ragged tail goes through one zero-padded scratch tile, so that every row sees the same arithmetic
+        const size_t tile_bytes = (size_t)TCP_ROWS * d * sizeof(float);
+        if (!s->rot_tmp) CU(cudaMalloc(&s->rot_tmp, tile_bytes));
+        float* tmp = static_cast<float*>(s->rot_tmp);
+        CU(cudaMemsetAsync(tmp, 0, tile_bytes, st));
+        CU(cudaMemcpyAsync(tmp, data + full * TCP_ROWS * d, (size_t)tail * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        tp.rows_out = tmp;
+        k_logp_tc<TcRotateEpi><<<1, TCP_THREADS, smem, st>>>(tp, tmp, nullptr, 1, R);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(data + full * TCP_ROWS * d, tmp, (size_t)tail * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
 static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cudaStream_t st) {
     LpParams p{};
     p.d = t->d;
@@ -811,7 +897,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
                 return t->K <= LP_MAX_K ? launch_logp_tiled<VmfLp>(p, xs, os, n, st) : logp_literal<float>(t, xs, os, n, st);
             };
             if (tc_enabled() && t->d >= 24 && tcp_fits<TcVmfEpi>(t->d, t->K)) {
-                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K, tcp_np(t->K), tc_spin()};
+                const TcpParams tp{t->mu.f, t->consts.f, nullptr, 0.f, t->d, t->K, tcp_np(t->K), tc_spin(), nullptr};
                 return logp_tc<TcVmfEpi>(tp, xi, o, N, st, simt);
             }
             if (t->K > LP_MAX_K) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast vMF kernel handles K <= %d", LP_MAX_K);
@@ -821,7 +907,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             // dense A, 8 <= d <= 64: Y = X A on the tensor cores (tcgen05, 3xTF32), kernels_tc.cuh
             if (!t->diag && t->d >= 8 && t->eig_n_out > 0 && tcp_fits<TcBinghamEpi>(t->d, t->eig_n_out) && tc_enabled() && !std::getenv("GEOSSS_TC_V1")) {
                 p.diag = 0; p.a0 = t->A.f; p.a1 = t->has_b ? t->b.f : nullptr;
-                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out, tcp_np(t->eig_n_out), tc_spin()};
+                const TcpParams tp{t->eig_rows.f, t->eig_vals.f, nullptr, 0.f, t->d, t->eig_n_out, tcp_np(t->eig_n_out), tc_spin(), nullptr};
                 return logp_tc<TcBinghamEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<BinghamLp>(p, xs, os, n, st); });
             }
             // round-1 kernel (one block-wide phase at a time), kept selectable for A/B runs: GEOSSS_TC_V1=1
@@ -852,7 +938,7 @@ static int logp_fast(geosss_target* t, const void* x, void* out, int64_t N, cuda
             if (t->M > GC_MAX_KNOTS) return fail(GEOSSS_E_UNSUPPORTED, "log_prob: fast curved kernel handles <= %d knots", GC_MAX_KNOTS);
             p.M = t->M; p.kappa = (float)t->kappa; p.a0 = t->knots.f; p.a1 = t->cosang.f; p.a2 = t->sinang.f;
             if (tc_enabled() && t->d >= 24 && tcp_fits<TcCurvedEpi>(t->d, t->M)) {  // G = X knots^T on the tensor cores
-                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M, tcp_np(t->M), tc_spin()};
+                const TcpParams tp{t->knots.f, t->cosang.f, t->sinang.f, (float)t->kappa, t->d, t->M, tcp_np(t->M), tc_spin(), nullptr};
                 return logp_tc<TcCurvedEpi>(tp, xi, o, N, st, [&](const float* xs, float* os, int64_t n) { return launch_logp_tiled<CurvedLp>(p, xs, os, n, st); });
             }
             return launch_logp_tiled<CurvedLp>(p, xi, o, N, st);
@@ -946,6 +1032,7 @@ extern "C" int geosss_sampler_destroy(geosss_sampler_t s) {
     g_pool.put(s->ws, s->ws_bytes);
     g_pool.put(s->n_reject, (size_t)s->N * sizeof(unsigned long long));
     if (s->zbuf) cudaFree(s->zbuf);
+    if (s->rot_tmp) cudaFree(s->rot_tmp);
     if (s->stepsize) cudaFree(s->stepsize);
     if (s->adapt_count) cudaFree(s->adapt_count);
     if (s->n_walk) cudaFree(s->n_walk);
@@ -1070,6 +1157,45 @@ static RunArgs base_args(geosss_sampler* s, int64_t n_steps, int64_t thin) {
     return a;
 }
 
+// the launch itself: scratch of the great-circle kernels, then the fast or the literal kernels
+static int run_launch(geosss_sampler* s, RunArgs& a, cudaStream_t st) {
+    // wide rows on the great-circle kernels (d >= 64, normals not kept in shared memory): scratch for the transition's normals
+    if (s->path == GEOSSS_PATH_FAST && s->t->kind != TGT_CPD && !s->zbuf && !gc_store_normals(s->t) && !std::getenv("GEOSSS_GC_REGEN") &&
+        !(s->t->kind == TGT_VMF_MIX && !fast_supported(s->t->kind, s->t->d, s->t->K, s->t->single))) {
+        s->zbuf_bytes = (size_t)((s->t->d + 3) / 4) * (size_t)s->N * 16;
+        if (cudaMalloc(&s->zbuf, s->zbuf_bytes) != cudaSuccess) { cudaGetLastError(); s->zbuf = nullptr; }  // fall back to regeneration
+    }
+    a.zbuf = s->zbuf;
+    return s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
+}
+
+// Sampler.sample on device buffers (mcmc.py:55-77): block_out is one contiguous (N, head_rows + n_steps / thin, d) array; with
+// head_rows = 1 row 0 of every chain is its current state -- "the first retained sample is the current state" -- and the kept
+// states follow.  Dense-Bingham chains (eigenbasis of A) rotate the whole block on the tensor cores afterwards, the head rows
+// included, so that they carry the same arithmetic as the last row of the previous call.
+extern "C" int geosss_sampler_run_block(geosss_sampler_t s, int64_t n_steps, int64_t thin, int64_t head_rows, void* block_out, void* stream) {
+    if (!s || n_steps < 0 || thin < 1 || head_rows < 0 || head_rows > 1 || !block_out) return fail(GEOSSS_E_INVALID, "run_block: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n_keep = n_steps / thin, rows = head_rows + n_keep, d = s->t->d;
+    const size_t es = s->esize();
+    if (rows == 0) return 0;
+    if (head_rows)
+        CU(cudaMemcpy2DAsync(block_out, (size_t)rows * d * es, s->state, (size_t)d * es, (size_t)d * es, (size_t)s->N, cudaMemcpyDeviceToDevice, st));
+    if (n_steps > 0) {
+        RunArgs a = base_args(s, n_steps, thin);
+        a.ss_step = d; a.ss_chain = rows * d; a.sl_step = 1; a.sl_chain = n_keep;
+        a.samples = n_keep > 0 ? static_cast<unsigned char*>(block_out) + (size_t)head_rows * d * es : nullptr;
+        const int rc = run_launch(s, a, st);
+        if (rc) return rc;
+    }
+    if (s->eig) {
+        const int rc = rotate_rows(s, false, block_out, s->N * rows, 1, d, 0, st);
+        if (rc) return rc;
+    }
+    s->step += (uint64_t)n_steps;
+    return 0;
+}
+
 extern "C" int geosss_sampler_run(geosss_sampler_t s, int64_t n_steps, int64_t thin, void* samples_out, void* logp_out,
                                   uint32_t* nrej_out, void* stream) {
     return geosss_sampler_run_layout(s, n_steps, thin, GEOSSS_STEP_MAJOR, 0, 0, samples_out, logp_out, nrej_out, stream);
@@ -1090,17 +1216,12 @@ extern "C" int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, in
         if (a.ss_chain < n_keep * (int64_t)s->t->d || a.sl_chain < n_keep) return fail(GEOSSS_E_INVALID, "run: chain stride smaller than a chain's output");
     }
     a.samples = samples_out; a.logp = logp_out; a.nrej = nrej_out;
-    // wide rows on the great-circle kernels (d >= 64, normals not kept in shared memory): scratch for the transition's normals
-    if (s->path == GEOSSS_PATH_FAST && s->t->kind != TGT_CPD && !s->zbuf && !gc_store_normals(s->t) && !std::getenv("GEOSSS_GC_REGEN") &&
-        !(s->t->kind == TGT_VMF_MIX && !fast_supported(s->t->kind, s->t->d, s->t->K, s->t->single))) {
-        s->zbuf_bytes = (size_t)((s->t->d + 3) / 4) * (size_t)s->N * 16;
-        if (cudaMalloc(&s->zbuf, s->zbuf_bytes) != cudaSuccess) { cudaGetLastError(); s->zbuf = nullptr; }  // fall back to regeneration
-    }
-    a.zbuf = s->zbuf;
-    int rc = s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
+    int rc = run_launch(s, a, st);
     if (rc) return rc;
     if (s->eig && samples_out) {  // retained samples back into the caller's coordinates, in place
-        rc = rotate_rows(s, false, samples_out, n_steps / thin, s->N, a.ss_step, a.ss_chain, st);
+        // rows in memory order: the smaller stride is the inner index, so that a block's 128 rows are neighbours
+        rc = a.ss_step <= a.ss_chain ? rotate_rows(s, false, samples_out, s->N, n_steps / thin, a.ss_chain, a.ss_step, st)
+                                     : rotate_rows(s, false, samples_out, n_steps / thin, s->N, a.ss_step, a.ss_chain, st);
         if (rc) return rc;
     }
     s->step += (uint64_t)n_steps;

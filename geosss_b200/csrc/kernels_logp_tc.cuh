@@ -50,6 +50,7 @@ struct TcpParams {
     int d, n_out;
     int np;           // accumulator columns per half: n_out rounded up to 16 (UMMA N is a multiple of 16 at M = 128)
     int spin;         // 1: barrier waits poll with mbarrier.test_wait, 0 (default): mbarrier.try_wait
+    float* rows_out;  // TcRotateEpi: (N, d) output rows (may be the input array: a tile is consumed before it is written)
 };
 
 // Waits of the role warps: mbarrier.try_wait (may suspend the warp for a time slice) or, with GEOSSS_TC_SPIN=1, polling with
@@ -102,7 +103,8 @@ struct TcBinghamEpi {
         for (int i = threadIdx.x; i < AUX; i += blockDim.x) aux[i] = i < P.d ? P.v0[i] : 0.f;
     }
     static __device__ __forceinline__ float scale() { return 1.f; }
-    static __device__ __forceinline__ void begin(State& st) { st.q0 = st.q1 = st.q2 = st.q3 = 0.f; }
+    static constexpr bool SCALAR_OUT = true;
+    static __device__ __forceinline__ void begin(State& st, int64_t) { st.q0 = st.q1 = st.q2 = st.q3 = 0.f; }
     // sum_j v_j s_j^2 (+ s_d = b . x)
     static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float* aux, int c0, const float (&s)[16]) {
 #pragma unroll
@@ -127,7 +129,8 @@ struct TcVmfEpi {
         for (int i = threadIdx.x; i < AUX; i += blockDim.x) aux[i] = i < P.n_out ? P.v0[i] * 1.4426950408889634f : -INFINITY;
     }
     static __device__ __forceinline__ float scale() { return 1.4426950408889634f; }  // W = mu log2(e)
-    static __device__ __forceinline__ void begin(State& st) { st.v = 0.f; }
+    static constexpr bool SCALAR_OUT = true;
+    static __device__ __forceinline__ void begin(State& st, int64_t) { st.v = 0.f; }
     static __device__ __forceinline__ void consume(State& st, const TcpParams&, const float* aux, int, const float (&s)[16]) {
         float e[16], m = -INFINITY;
 #pragma unroll
@@ -154,7 +157,8 @@ struct TcCurvedEpi {
         }
     }
     static __device__ __forceinline__ float scale() { return 1.f; }
-    static __device__ __forceinline__ void begin(State& st) { st.v = 0.f; }
+    static constexpr bool SCALAR_OUT = true;
+    static __device__ __forceinline__ void begin(State& st, int64_t) { st.v = 0.f; }
     // max over segments of x . nearest point, first segment wins ties: CurvedGcT::best_dot (kernels_gc.cuh) at theta = 0
     static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float* aux, int, const float (&g)[16]) {
         float ga = g[0], best = 0.f, best_clipped = -INFINITY;
@@ -171,6 +175,30 @@ struct TcCurvedEpi {
         st.v = P.kappa * best;
     }
     static __device__ __forceinline__ float result(const State& st, const TcpParams&) { return st.v; }
+};
+
+// Rotation of rows, Y = X W^T with all d outputs kept (dense Bingham chains live in the eigenbasis of A: states and retained
+// samples are rotated at the C-ABI boundary, capi.cu).  Every thread stores its own row's columns; rows are contiguous, so a
+// warp fills a 32 d float span.
+struct TcRotateEpi {
+    static constexpr int NP_MAX = 64;
+    static constexpr int AUX = 4;
+    static constexpr bool SCALAR_OUT = false;
+    struct State { float* o; int64_t row; };
+    static __device__ void stage(const TcpParams&, float*) {}
+    static __device__ __forceinline__ float scale() { return 1.f; }
+    static __device__ __forceinline__ void begin(State& st, int64_t row) { st.o = nullptr; st.row = row; }
+    static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float*, int c0, const float (&s)[16]) {
+        float* o = P.rows_out + st.row * P.d + c0;
+        if ((P.d & 1) == 0) {  // rows start on 8-byte boundaries
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) if (c0 + j < P.d) *reinterpret_cast<float2*>(o + j) = make_float2(s[j], s[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (c0 + j < P.d) o[j] = s[j];
+        }
+    }
+    static __device__ __forceinline__ float result(const State&, const TcpParams&) { return 0.f; }
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -367,7 +395,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
             tcp_wait(&acc_full[s], (uint32_t)use & 1u, P.spin);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             typename Epi::State st;
-            Epi::begin(st);
+            Epi::begin(st, row0 + row);
             for (int c0 = 0; c0 < NP; c0 += 16) {
                 float a0[8], a1[8], b0[8], b1[8], sc[16];
                 tmem_ld8(acc + (uint32_t)c0, a0);
@@ -384,7 +412,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                 for (int q = 0; q < 8; ++q) { sc[q] = a0[q] + b0[q]; sc[8 + q] = a1[q] + b1[q]; }
                 Epi::consume(st, P, aux, c0, sc);
             }
-            out[row0 + row] = Epi::result(st, P);
+            if (Epi::SCALAR_OUT) out[row0 + row] = Epi::result(st, P);
         }
     }
 

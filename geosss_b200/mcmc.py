@@ -277,12 +277,12 @@ class Sampler:
             raise ValueError(f"out must be a contiguous {self._tdtype} tensor of shape {shape}")
         if on_device:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, device=self.device)
-            if keeps_current:
-                buf[:, 0] = self._state_device()
             if n_skip:
                 self._run_device(n_skip, None)
-            if n_new:  # every chain appends its rows behind its own slot 0: (N, n_out, d) chain-major
-                self._run_device(n_new, buf[:, 1:] if keeps_current else buf, chain_major=True, chain_stride=n_out * self.d)
+            # one contiguous (N, n_out, d) block: slot 0 of every chain is its current state when it is kept, its new states follow
+            with torch.cuda.device(self.device):
+                _lib.check(lib.geosss_sampler_run_block(h, n_new, 1, 1 if keeps_current else 0, buf.data_ptr(), _device.stream_ptr(self.device)))
+            self.rng.steps_done += n_new
             res = buf
         else:
             buf = out if out is not None else torch.empty(shape, dtype=self._tdtype, pin_memory=True)

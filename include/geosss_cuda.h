@@ -143,6 +143,10 @@ int geosss_sampler_run_layout(geosss_sampler_t s, int64_t n_steps, int64_t thin,
  * ESS of a coordinate / of x . mode (reference: scripts/ess_mixture_vMF.py:233, scripts/ess_curve_vMF.py:267,
  * scripts/bingham.py:50-52, where the full chains are kept and sliced afterwards). */
 int geosss_sampler_trace_out(geosss_sampler_t s, const double* direction_host, void* trace_out);
+/* Sampler.sample on device buffers (geosss/mcmc.py:55-77): block_out is ONE contiguous (N, head_rows + n_steps / thin, d) array
+ * of the sampler's dtype; with head_rows = 1 row 0 of every chain holds its state before the run ("the first retained sample
+ * is the current state", mcmc.py:67-68), the kept states follow.  head_rows is 0 or 1. */
+int geosss_sampler_run_block(geosss_sampler_t s, int64_t n_steps, int64_t thin, int64_t head_rows, void* block_out, void* stream);
 /* Parity mode: draws come from a flat float64 tape per chain, in the order the reference consumes
  * them (d normals, level uniform, [bracket uniform,] one uniform per proposal; next transition).
  * tape_offsets: (N + 1) int64.  status: (N) 0 ok / 1 tape exhausted early, or NULL. */

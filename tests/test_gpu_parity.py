@@ -527,6 +527,44 @@ def test_great_circle_fast_kernels_follow_reference_under_shared_draws(golden, c
     fc.check(1.0)
 
 
+def test_dense_bingham_chains_live_in_the_eigenbasis(golden, monkeypatch):
+    """Dense A on the float32 path: the chain runs as y = W x on the diagonal kernel and states / samples are rotated at the
+    C-ABI boundary (tensor cores for dense blocks, one scratch tile for the ragged tail).  W is an eigen-system of A; the
+    first retained sample is the current state; a second call continues bit-exactly from the last sample of the first; shards
+    reproduce the full run bit for bit (the rotation of a row does not depend on where the row sits); the dense matrix-vector
+    kernel (GEOSSS_NO_EIG) has the same law."""
+    A = golden("logprob_bingham")["c4dense_A"]
+    pdf = gs.Bingham(A)
+    W = pdf.device_eigenrows()
+    assert W is not None and np.max(np.abs(W @ W.T - np.eye(50))) < 1e-12
+    assert np.max(np.abs(W @ A @ W.T - np.diag(np.diag(W @ A @ W.T)))) < 1e-9 * np.abs(A).max()
+    N = 300  # two full 128-row tiles and a ragged tail in every rotation
+    x0 = torch.as_tensor(gs.sample_sphere(49, N, seed=8), dtype=torch.float32).cuda()
+    smp = gs.ShrinkageSphericalSliceSampler(pdf, x0, 5)
+    first = smp.sample(7)
+    assert smp.path == "fast" and tuple(first.shape) == (N, 7, 50)
+    assert torch.max(torch.abs(first[:, 0] - x0)) < 2e-6                      # W^T (W x0) in 3xTF32 / float32
+    assert torch.max(torch.abs(first.double().norm(dim=-1) - 1.0)) < 1e-5
+    second = smp.sample(5)
+    assert torch.equal(second[:, 0], first[:, -1])                             # continuation, bit for bit
+    assert np.array_equal(smp.state.astype(np.float32), second[:, -1].cpu().numpy())
+    full = torch.cat([first, second[:, 1:]], dim=1)
+    part = gs.ShrinkageSphericalSliceSampler(pdf, x0[100:200], 5, chain_offset=100).sample(11)
+    assert torch.equal(part[:, 1:], full[100:200, 1:])                         # shard invariance through the rotations
+    lp = pdf.log_prob(full[:, -1])
+    assert rel_err(lp.cpu().numpy(), oracle_of(pdf).log_prob(full[:, -1].double().cpu().numpy())) <= 1e-5
+    # host-buffer entry point (step-major staging buffers are rotated too)
+    host = gs.ShrinkageSphericalSliceSampler(pdf, x0.cpu().numpy(), 5).sample(11)
+    assert np.max(np.abs(host - full.cpu().numpy())) < 1e-6
+    # same law on the dense matrix-vector kernel: mean log-density after burn-in
+    many = torch.as_tensor(gs.sample_sphere(49, 4096, seed=9), dtype=torch.float32).cuda()
+    a = pdf.log_prob(gs.ShrinkageSphericalSliceSampler(pdf, many, 6).sample(1, 150)[:, 0]).double().mean().item()
+    monkeypatch.setenv("GEOSSS_NO_EIG", "1")
+    b = pdf.log_prob(gs.ShrinkageSphericalSliceSampler(gs.Bingham(A), many, 7).sample(1, 150)[:, 0]).double().mean().item()
+    monkeypatch.delenv("GEOSSS_NO_EIG")
+    assert abs(a - b) < 1.0, (a, b)  # log p ~ 280 +- 5 per chain: means of 4096 chains agree to a fraction of a unit
+
+
 @pytest.mark.parametrize("cls,kind", [(gs.ShrinkageSphericalSliceSampler, samplers.SHRINK),
                                       (gs.RejectionSphericalSliceSampler, samplers.REJECT)])
 @pytest.mark.parametrize("d,K,kappa", [(40, 12, 60.0), (17, 3, 200.0), (100, 16, 30.0)])
