@@ -118,7 +118,7 @@ def _tau_bulk(acov_sum, mean_sum, mean_sq_sum, n_draws, n_chains):
     return max(tau, 1.0 / math.log10(m * n)), exhausted
 
 
-def bulk_ess(trace, group=None, relative=False):
+def bulk_ess(trace, group=None, relative=False, local_only=False):
     """Rank-normalised split bulk-ESS of a scalar trace, the estimator the upstream scripts obtain from
     ``arviz.ess`` (default method "bulk"; scripts/bingham.py:28-70, scripts/ess_curve_vMF.py:97-130,
     scripts/vMF_diagnostics.py:451-492), after Vehtari et al. (2021): every chain is split in two halves, the
@@ -129,7 +129,8 @@ def bulk_ess(trace, group=None, relative=False):
     ``trace``: CUDA tensor ``(n_chains, n_draws)`` -- e.g. ``sampler.sample_trace(...)`` or
     ``samples[..., 0]``.  With ``torch.distributed`` initialised the ranks are taken over the chains of all
     processes (all_gather of the scalar traces) and the partial sums are all-reduced, so every process
-    returns the ESS of all chains.  Returns ESS, or ESS / (chains x draws) with ``relative``."""
+    returns the ESS of all chains (``local_only`` keeps the call to this process's chains).  Returns ESS, or
+    ESS / (chains x draws) with ``relative``."""
     import torch.distributed as dist
     if not (isinstance(trace, torch.Tensor) and trace.is_cuda and trace.dim() == 2):
         raise ValueError("bulk_ess needs a CUDA tensor (n_chains, n_draws); there is no CPU fallback")
@@ -138,7 +139,7 @@ def bulk_ess(trace, group=None, relative=False):
     if half < 4:
         raise ValueError("bulk_ess needs at least 8 draws per chain")
     local = torch.cat([trace[:, :half], trace[:, n - half:]], dim=0).to(torch.float32).contiguous()  # (2N, half)
-    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    distributed = not local_only and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     if distributed:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         counts = torch.zeros(world, dtype=torch.int64, device=trace.device)
