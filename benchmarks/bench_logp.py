@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 22)
     ap.add_argument("--only", default="")
     ap.add_argument("--sweep", action="store_true", help="tensor-core kernel tuning knobs (landing stages, TMEM rings, stacked W) instead of the standard variants")
+    ap.add_argument("--modes", default="", help="comma-separated landing-ring depths (GEOSSS_TC_STAGES) to compare")
     a = ap.parse_args()
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -70,6 +71,9 @@ def main():
     if a.sweep:  # tuning knobs of the tensor-core kernel
         knobs = [("default", {}), ("2 landing stages", {"GEOSSS_TC_STAGES": "2"}), ("3 landing stages", {"GEOSSS_TC_STAGES": "3"}),
                  ("polling waits", {"GEOSSS_TC_SPIN": "1"})]
+        cases = [(n, p, knobs) for n, p, v in cases if "SIMT" not in v[0][0]]
+    if a.modes:
+        knobs = [(f"stages {m}", {"GEOSSS_TC_STAGES": m}) for m in a.modes.split(",")]
         cases = [(n, p, knobs) for n, p, v in cases if "SIMT" not in v[0][0]]
     for name, pdf, variants in cases:
         if a.only and a.only not in name:

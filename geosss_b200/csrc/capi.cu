@@ -1617,3 +1617,13 @@ extern "C" int geosss_diag_path_stats(const void* samples, int dtype, int layout
     CU(cudaGetLastError());
     return 0;
 }
+
+#ifdef TCP_TIMERS
+extern "C" int geosss_debug_tc_timers(unsigned long long* out) {  // experiment builds only: read and clear the phase timers
+    unsigned long long z[32] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, geosss::tcp_timers, sizeof(z));
+    cudaMemcpyToSymbol(geosss::tcp_timers, z, sizeof(z));
+    return 0;
+}
+#endif

@@ -37,7 +37,10 @@
 namespace geosss {
 
 constexpr int TCP_ROWS = 128;                       // UMMA M = TMEM lanes
-constexpr int TCP_THREADS = (2 + 8 + 8) * 32;       // producer, MMA, 2 x 4 split warps, 2 x 4 epilogue warps
+constexpr int TCP_ROLE_WARPS = 4;                   // producer, MMA issuer of the even tiles, of the odd tiles, one idle
+constexpr int TCP_SPLIT_GROUPS = 2;                 // split groups of 4 warps, tiles dealt round-robin (3 groups measured no faster: r2_logp_tc_v9.md)
+constexpr int TCP_SPLIT_WARPS = 4 * TCP_SPLIT_GROUPS;
+constexpr int TCP_THREADS = (TCP_ROLE_WARPS + TCP_SPLIT_WARPS + 8) * 32;  // + 2 x 4 epilogue warps
 constexpr int TCP_MAX_STAGES = 4;
 constexpr int TCP_TMEM_COLS = 512;
 constexpr int TCP_TMEM_STAGES = 4;                  // at most; as many (hi | lo | accumulator) column groups as fit the 512 columns
@@ -56,7 +59,7 @@ struct TcpParams {
 // Waits of the role warps: mbarrier.try_wait (may suspend the warp for a time slice) or, with GEOSSS_TC_SPIN=1, polling with
 // mbarrier.test_wait.  Measured on B200 (r2 sweep): polling is 2-7 % SLOWER on every shape, so try_wait is the default.
 __device__ __forceinline__ void tcp_wait(uint64_t* bar, uint32_t parity, int spin) {
-    if (!spin) { mbar_wait(bar, parity); return; }
+    if (!(spin & 1)) { mbar_wait(bar, parity); return; }
     uint32_t done = 0;
     for (uint32_t n = 0; !done; ++n) {
         asm volatile(
@@ -91,6 +94,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// wider shapes of the same accesses: a tcgen05.st / ld costs the issuing warp its latency whatever the width (phase timers:
+// ~100 cycles per x8 store pair in the split loop), so the split stores 32 columns and the epilogue loads 16 per instruction
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31])) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- epilogue policies ---------------------------------------------------------------------------
 // NP: accumulator columns (n_out padded; UMMA N, a multiple of 16 for M = 128).
 // Every policy consumes the accumulator row in chunks of 16 columns (begin / consume / result), so that the
@@ -104,6 +122,8 @@ struct TcBinghamEpi {
     }
     static __device__ __forceinline__ float scale() { return 1.f; }
     static constexpr bool SCALAR_OUT = true;
+    static constexpr bool ROUND_SPLIT = false;
+    static constexpr bool ONE_ACC = true;  // wide accumulator: all three products land on the same NP columns
     static __device__ __forceinline__ void begin(State& st, int64_t) { st.q0 = st.q1 = st.q2 = st.q3 = 0.f; }
     // sum_j v_j s_j^2 (+ s_d = b . x)
     static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float* aux, int c0, const float (&s)[16]) {
@@ -130,15 +150,21 @@ struct TcVmfEpi {
     }
     static __device__ __forceinline__ float scale() { return 1.4426950408889634f; }  // W = mu log2(e)
     static constexpr bool SCALAR_OUT = true;
+    static constexpr bool ROUND_SPLIT = false;
+    static constexpr bool ONE_ACC = false;
     static __device__ __forceinline__ void begin(State& st, int64_t) { st.v = 0.f; }
-    static __device__ __forceinline__ void consume(State& st, const TcpParams&, const float* aux, int, const float (&s)[16]) {
-        float e[16], m = -INFINITY;
+    static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float* aux, int, const float (&s)[16]) {
+        if (P.n_out <= 8) { lse<8>(st, aux, s); } else { lse<16>(st, aux, s); }  // uniform branch: half the exponentials for K <= 8
+    }
+    template <int KN>
+    static __device__ __forceinline__ void lse(State& st, const float* aux, const float (&s)[16]) {
+        float e[KN], m = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { e[k] = s[k] + aux[k]; m = fmaxf(m, e[k]); }
+        for (int k = 0; k < KN; ++k) { e[k] = s[k] + aux[k]; m = fmaxf(m, e[k]); }
         if (!(m > -INFINITY)) { st.v = m; return; }  // i0 overflow: every component is -inf, like the reference
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc += fast_ex2(e[k] - m);
+        for (int k = 0; k < KN; ++k) acc += fast_ex2(e[k] - m);
         st.v = (m + fast_lg2(acc)) * 0.6931471805599453f;
     }
     static __device__ __forceinline__ float result(const State& st, const TcpParams&) { return st.v; }
@@ -158,6 +184,8 @@ struct TcCurvedEpi {
     }
     static __device__ __forceinline__ float scale() { return 1.f; }
     static constexpr bool SCALAR_OUT = true;
+    static constexpr bool ROUND_SPLIT = false;
+    static constexpr bool ONE_ACC = false;
     static __device__ __forceinline__ void begin(State& st, int64_t) { st.v = 0.f; }
     // max over segments of x . nearest point, first segment wins ties: CurvedGcT::best_dot (kernels_gc.cuh) at theta = 0
     static __device__ __forceinline__ void consume(State& st, const TcpParams& P, const float* aux, int, const float (&g)[16]) {
@@ -184,6 +212,8 @@ struct TcRotateEpi {
     static constexpr int NP_MAX = 64;
     static constexpr int AUX = 4;
     static constexpr bool SCALAR_OUT = false;
+    static constexpr bool ROUND_SPLIT = true;
+    static constexpr bool ONE_ACC = true;
     struct State { float* o; int64_t row; };
     static __device__ void stage(const TcpParams&, float*) {}
     static __device__ __forceinline__ float scale() { return 1.f; }
@@ -207,46 +237,95 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// Split 8 row values into TF32 hi / lo and store them to this thread's TMEM lane, columns col .. col + 7 of the hi and lo blocks.
-// hi = x rounded to 11 significant bits (bit pattern + half an ulp, low 13 bits cleared: round-to-nearest in magnitude, 2 integer
-// instructions instead of the ~6 of cvt.rna.tf32 with its inf / nan handling -- rows are finite); lo = x - hi is exact in fp32 and
-// goes to tensor memory as it is: the tensor core ignores its low 13 mantissa bits, an error of 2^-11 |lo| <= 2^-23 |x|.
-__device__ __forceinline__ void tcp_split_store(uint32_t xh, uint32_t xl, int col, const float (&v)[8]) {
-    float h[8], l[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        h[c] = __uint_as_float((__float_as_uint(v[c]) + 0x1000u) & 0xFFFFE000u);
-        l[c] = v[c] - h[c];
-    }
-    tmem_st8(xh + (uint32_t)col, h);
-    tmem_st8(xl + (uint32_t)col, l);
-}
+// TF32 hi / lo split of the row values (tcp_split_block below).  The tensor core reads an fp32 word as TF32 by dropping its low
+// 13 mantissa bits (measured: the 3xTF32 error stays at 1e-6 with this split, r2 mode sweep), so hi is the row value as it is
+// and lo = x - trunc(x) (exact in fp32, one AND + one FADD per element).  lo loses its own low bits the same way: an error of
+// 2^-10 |lo| < 2^-20 |x| per element, inside the 1e-5 the fp32 log_prob states.
 
-// 8 values of a row starting at column k0 (k0 % 8 == 0), zero beyond d; widest loads the row stride allows
-__device__ __forceinline__ void tcp_load8(const float* __restrict__ row, int k0, int d, float (&v)[8]) {
-    if (k0 + 8 <= d) {
-        if ((d & 3) == 0) {
-            const float4 a = *reinterpret_cast<const float4*>(row + k0), b = *reinterpret_cast<const float4*>(row + k0 + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else if ((d & 1) == 0) {
+// N (8, 16 or 32) row values from column k0 on, split and stored with one tcgen05.st per half.  ROT (d % 16 == 0, N >= 16): the
+// 16-byte pieces of each group of 16 columns are read in the order (p + lane) mod 4 and rotated back in registers.
+// LW: floats per shared-memory load the row stride allows (4, 2, 1); CHECK: columns beyond d read as zero (the last block only).
+// TRUNC = false (the rotation of rows, whose output is sample coordinates): hi is rounded to TF32 first -- bit pattern + half an
+// ulp, low 13 bits cleared -- one more integer instruction per element for half the split error.
+template <int N, bool ROT, int LW = 4, bool CHECK = false, bool TRUNC = true>
+__device__ __forceinline__ void tcp_split_block(const float* __restrict__ rowp, int k0, int d, int rl, uint32_t xh, uint32_t xl) {
+    float v[N], l[N];
+    if constexpr (ROT) {
 #pragma unroll
-            for (int q = 0; q < 8; q += 2) { const float2 a = *reinterpret_cast<const float2*>(row + k0 + q); v[q] = a.x; v[q + 1] = a.y; }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = row[k0 + q];
+        for (int g = 0; g < N; g += 16) {
+            const float4* base = reinterpret_cast<const float4*>(rowp + k0 + g);
+            float4 t0 = base[rl], t1 = base[(rl + 1) & 3], t2 = base[(rl + 2) & 3], t3 = base[(rl + 3) & 3];
+            // t_i = piece (i + rl) mod 4; rotate right by rl: stage 1 by (rl & 1), stage 2 by (rl & 2)
+            const bool b0 = rl & 1, b1 = rl & 2;
+            float4 u0 = b0 ? t3 : t0, u1 = b0 ? t0 : t1, u2 = b0 ? t1 : t2, u3 = b0 ? t2 : t3;
+            float4 p0 = b1 ? u2 : u0, p1 = b1 ? u3 : u1, p2 = b1 ? u0 : u2, p3 = b1 ? u1 : u3;
+            v[g + 0] = p0.x; v[g + 1] = p0.y; v[g + 2] = p0.z; v[g + 3] = p0.w; v[g + 4] = p1.x; v[g + 5] = p1.y; v[g + 6] = p1.z; v[g + 7] = p1.w;
+            v[g + 8] = p2.x; v[g + 9] = p2.y; v[g + 10] = p2.z; v[g + 11] = p2.w; v[g + 12] = p3.x; v[g + 13] = p3.y; v[g + 14] = p3.z; v[g + 15] = p3.w;
         }
     } else {
+        const float* src = rowp + k0;
+        if constexpr (CHECK) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = k0 + q < d ? row[k0 + q] : 0.f;
+            for (int q = 0; q < N; ++q) v[q] = k0 + q < d ? src[q] : 0.f;
+        } else if constexpr (LW == 4) {
+#pragma unroll
+            for (int q = 0; q < N; q += 4) { const float4 a = *reinterpret_cast<const float4*>(src + q); v[q] = a.x; v[q + 1] = a.y; v[q + 2] = a.z; v[q + 3] = a.w; }
+        } else if constexpr (LW == 2) {
+#pragma unroll
+            for (int q = 0; q < N; q += 2) { const float2 a = *reinterpret_cast<const float2*>(src + q); v[q] = a.x; v[q + 1] = a.y; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[q] = src[q];
+        }
     }
+    // hi = the value as it is (the tensor core drops the low 13 bits), lo = x - trunc(x)
+    if constexpr (TRUNC) {
+#pragma unroll
+        for (int c = 0; c < N; ++c) l[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xFFFFE000u);
+    } else {
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            const float h = __uint_as_float((__float_as_uint(v[c]) + 0x1000u) & 0xFFFFE000u);
+            l[c] = v[c] - h;
+            v[c] = h;
+        }
+    }
+    if constexpr (N == 32) { tmem_st32(xh + (uint32_t)k0, v); tmem_st32(xl + (uint32_t)k0, l); }
+    else if constexpr (N == 16) { tmem_st16(xh + (uint32_t)k0, v); tmem_st16(xl + (uint32_t)k0, l); }
+    else { tmem_st8(xh + (uint32_t)k0, *reinterpret_cast<const float(*)[8]>(v)); tmem_st8(xl + (uint32_t)k0, *reinterpret_cast<const float(*)[8]>(l)); }
 }
+
+// one row of a tile: whole blocks of 32 / 16 / 8 columns without bound checks, then the ragged last K step
+template <int LW, bool TRUNC>
+__device__ __forceinline__ void tcp_split_row(const float* __restrict__ rowp, int d, int KP, uint32_t xh, uint32_t xl) {
+    int k0 = 0;
+    for (; k0 + 32 <= d; k0 += 32) tcp_split_block<32, false, LW, false, TRUNC>(rowp, k0, d, 0, xh, xl);
+    if (k0 + 16 <= d) { tcp_split_block<16, false, LW, false, TRUNC>(rowp, k0, d, 0, xh, xl); k0 += 16; }
+    if (k0 + 8 <= d) { tcp_split_block<8, false, LW, false, TRUNC>(rowp, k0, d, 0, xh, xl); k0 += 8; }
+    if (k0 < KP) tcp_split_block<8, false, 1, true, TRUNC>(rowp, k0, d, 0, xh, xl);
+}
+
+#ifdef TCP_TIMERS
+__device__ unsigned long long tcp_timers[32];
+#define TCP_T0() long long t_prev = clock64(), t_acc[6] = {0, 0, 0, 0, 0, 0}
+#define TCP_TICK(i) { const long long t_now = clock64(); t_acc[i] += t_now - t_prev; t_prev = t_now; }
+#define TCP_DUMP(base, n) if (blockIdx.x == 0 && lane == 0) for (int q = 0; q < n; ++q) atomicAdd(&tcp_timers[base + q], (unsigned long long)t_acc[q])
+#else
+#define TCP_T0()
+#define TCP_TICK(i)
+#define TCP_DUMP(base, n)
+#endif
 
 template <class Epi>
 __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const float* __restrict__ x, float* __restrict__ out,
                                                              int64_t n_tiles, int R) {
     extern __shared__ __align__(128) unsigned char tcp_smem[];
-    __shared__ __align__(8) uint64_t raw_full[TCP_MAX_STAGES], raw_empty[TCP_MAX_STAGES], op_full[TCP_TMEM_STAGES], acc_full[TCP_TMEM_STAGES],
-        acc_empty[TCP_TMEM_STAGES];
+    // Every barrier has ONE waiting role instance and one arriving one: the first index is the parity of the WAITER's tile
+    // (even tiles: issuer warp 1, split / epilogue group 0; odd tiles: warp 2, group 1).  With an odd ring depth the users of a
+    // stage alternate between the two instances, and a parity wait by the instance that runs ahead would take the previous
+    // phase for its own (mbarrier waits only know the parity); per-parity barriers keep each one's phases in a single order.
+    __shared__ __align__(8) uint64_t raw_full[TCP_SPLIT_GROUPS][TCP_MAX_STAGES], raw_empty[TCP_MAX_STAGES], op_full[2][TCP_TMEM_STAGES],
+        op_empty[TCP_SPLIT_GROUPS][TCP_TMEM_STAGES], acc_full[2][TCP_TMEM_STAGES], acc_empty[2][TCP_TMEM_STAGES];
     __shared__ uint32_t tmem_base_s;
     const int NP = P.np, NS = 2 * NP;  // W is stacked: rows 0..NP-1 of a K block hold Wh, rows NP..2NP-1 hold Wl
     const int d = P.d, ksteps = (d + 7) >> 3, KP = ksteps << 3;
@@ -262,8 +341,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < TCP_MAX_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 4); }
-        for (int i = 0; i < TCP_TMEM_STAGES; ++i) { mbar_init(&op_full[i], 4); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < TCP_MAX_STAGES; ++i) {
+            for (int q = 0; q < TCP_SPLIT_GROUPS; ++q) mbar_init(&raw_full[q][i], 1);
+            mbar_init(&raw_empty[i], 4);
+        }
+        for (int q = 0; q < TCP_SPLIT_GROUPS; ++q)
+            for (int i = 0; i < TCP_TMEM_STAGES; ++i) mbar_init(&op_empty[q][i], 1);
+        for (int q = 0; q < 2; ++q)
+            for (int i = 0; i < TCP_TMEM_STAGES; ++i) {
+                mbar_init(&op_full[q][i], 4); mbar_init(&acc_full[q][i], 1); mbar_init(&acc_empty[q][i], 4);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -283,10 +370,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
-    const int stage_cols = 2 * KP + NS;  // per TMEM stage: Xh | Xl | accumulator (Xh Wh + Xl Wh | Xh Wl)
-    // S TMEM stages; tile `it` uses stage it mod S.  The two warp groups take alternate tiles, so with S = 4 a group's next
-    // split does not have to wait for the MMAs of its previous tile.
-    const int S = min(TCP_TMEM_STAGES, TCP_TMEM_COLS / stage_cols) >= 4 ? 4 : 2;
+    constexpr bool one_acc = Epi::ONE_ACC;
+    // Tensor memory: a ring of SA operand stages (Xh | Xl, 2 KP columns each) followed by a ring of SD accumulator stages
+    // (ACCW columns each); tile `it` uses operand stage it mod SA and accumulator stage it mod SD.  Decoupled, so that the
+    // split of a later tile overlaps the MMAs of this one even where only two whole (operand + accumulator) groups would fit.
+    const int ACCW = one_acc ? NP : NS;
+    int SA = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - 2 * ACCW) / (2 * KP)));
+    int SD = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - SA * 2 * KP) / ACCW));
+    {  // experiment knobs: ring depths from GEOSSS_TC_SPIN bits 8-11 (operands) and 12-15 (accumulators), ignored unless they fit
+        const int ka = (P.spin >> 8) & 15, kd = (P.spin >> 12) & 15;
+        const int sa2 = ka ? ka : SA, sd2 = kd ? kd : SD;
+        if (sa2 >= 2 && sd2 >= 2 && sa2 <= TCP_TMEM_STAGES && sd2 <= TCP_TMEM_STAGES && sa2 * 2 * KP + sd2 * ACCW <= TCP_TMEM_COLS) { SA = sa2; SD = sd2; }
+    }
+    const int acc_col0 = SA * 2 * KP;
     const int n_it = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const size_t tile_floats = (size_t)TCP_ROWS * d;
     const int quad = warp & 3;  // the TMEM lane quadrant this warp may access
@@ -295,19 +391,25 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
 
     if (warp == 0) {
         // ===== producer
-        for (int it = 0; it < n_it; ++it) {
-            const int r = it % R, use = it / R;
+        TCP_T0();
+        for (int it = 0, r = 0, use = 0; it < n_it; ++it, r = r + 1 == R ? 0 : r + 1, use += r == 0) {
+            TCP_TICK(1);
             if (use > 0) tcp_wait(&raw_empty[r], (uint32_t)(use - 1) & 1u, P.spin);
+            TCP_TICK(0);
             if (lane == 0) {
                 const float* src = x + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)tile_floats;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&raw_full[r], (uint32_t)(tile_floats * sizeof(float)));
-                bulk_g2s(raw + (size_t)r * stage_floats, src, (uint32_t)(tile_floats * sizeof(float)), &raw_full[r]);
+                mbar_expect_tx(&raw_full[it % TCP_SPLIT_GROUPS][r], (uint32_t)(tile_floats * sizeof(float)));
+                bulk_g2s(raw + (size_t)r * stage_floats, src, (uint32_t)(tile_floats * sizeof(float)), &raw_full[it % TCP_SPLIT_GROUPS][r]);
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer.  The whole warp walks the loop (descriptor arithmetic stays in uniform registers: a tcgen05.mma
+        TCP_TICK(1);
+        TCP_DUMP(0, 2);
+    } else if (warp == 1 || warp == 2) {
+        // ===== MMA issuers: warp 1 takes the even tiles, warp 2 the odd ones (phase timers: issuing one tile's MMAs costs the
+        // warp 50-70 cycles per tcgen05.mma in uniform-datapath bookkeeping, 600-1100 cycles per tile -- with a single issuer that
+        // was the period of a narrow tile; the tiles of the two warps use different TMEM stages, so their MMAs interleave freely).  The whole warp walks the loop (descriptor arithmetic stays in uniform registers: a tcgen05.mma
         // costs ~8-32 tensor-pipe cycles at these shapes, so the issue loop itself must not be a chain of vector->uniform moves)
         // and one elected lane issues.  Two passes per tile: Xh [Wh; Wl] (N = 2 NP) and Xl Wh (N = NP) accumulated onto the
         // first NP columns; the epilogue adds the Xh Wl half.
@@ -316,13 +418,41 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         const bool elected = elect_one();
         const uint64_t wdesc = umma_smem_desc(Ws, NS * 16, 128);
         const uint32_t kdesc = (uint32_t)(NS * 8 * 4) >> 4;  // one K block further, in descriptor address units (16 bytes)
-        for (int it = 0; it < n_it; ++it) {
-            const int s = it % S, use = it / S;
-            tcp_wait(&op_full[s], (uint32_t)use & 1u, P.spin);
-            if (use > 0) tcp_wait(&acc_empty[s], (uint32_t)(use - 1) & 1u, P.spin);
+        // Two issuers where the operand ring is at least 3 deep; with 2 stages (d >= 88) the interleaved chains only lengthen
+        // the stage cycle (measured -3 % at d = 100), so warp 1 issues every tile there and warp 2 idles.
+        const bool two = (P.spin & 48) ? (P.spin & 32) != 0 : SA >= 3;
+        const int step = two ? 2 : 1;
+        uint32_t ph_op = 0, ph_acc = 0;  // parity this warp expects next, one bit per (tile parity, stage)
+        TCP_T0();
+        // ring positions by counters, not runtime modulo (depths are at least 2)
+        for (int it = two ? warp - 1 : (warp == 1 ? 0 : n_it), sa = it % SA, sd = it % SD; it < n_it;
+             it += step, sa = sa + step >= SA ? sa + step - SA : sa + step, sd = sd + step >= SD ? sd + step - SD : sd + step) {
+            const int par = it & 1;
+            TCP_TICK(2);
+            tcp_wait(&op_full[par][sa], (ph_op >> (4 * par + sa)) & 1u, P.spin);
+            ph_op ^= 1u << (4 * par + sa);
+            TCP_TICK(0);
+            if (it >= SD) { tcp_wait(&acc_empty[par][sd], (ph_acc >> (4 * par + sd)) & 1u, P.spin); ph_acc ^= 1u << (4 * par + sd); }
+            TCP_TICK(1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t xh = tmem + (uint32_t)(s * stage_cols), xl = xh + (uint32_t)KP, acc = xl + (uint32_t)KP;
+            const uint32_t xh = tmem + (uint32_t)(sa * 2 * KP), xl = xh + (uint32_t)KP, acc = tmem + (uint32_t)(acc_col0 + sd * ACCW);
             if (elected) {
+                if (one_acc) {  // three N = NP passes onto the same columns: Xh Wh, Xh Wl, Xl Wh
+#pragma unroll 4
+                    for (int kk = 0; kk < ksteps; ++kk)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                            ::"r"(acc), "r"(xh + (uint32_t)(kk << 3)), "l"(wdesc + (uint64_t)(kk * kdesc)), "r"(idesc_b), "r"(kk > 0 ? 1u : 0u)
+                            : "memory");
+#pragma unroll 4
+                    for (int kk = 0; kk < ksteps; ++kk)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                            ::"r"(acc), "r"(xh + (uint32_t)(kk << 3)), "l"(wdesc + (uint64_t)(kk * kdesc + NP)), "r"(idesc_b), "r"(1u)
+                            : "memory");
+                } else {
 #pragma unroll 4
                 for (int kk = 0; kk < ksteps; ++kk)
                     asm volatile(
@@ -330,6 +460,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                         ::"r"(acc), "r"(xh + (uint32_t)(kk << 3)), "l"(wdesc + (uint64_t)(kk * kdesc)), "r"(idesc_a), "r"(kk > 0 ? 1u : 0u)
                         : "memory");
+                }
 #pragma unroll 4
                 for (int kk = 0; kk < ksteps; ++kk)
                     asm volatile(
@@ -337,83 +468,103 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                         ::"r"(acc), "r"(xl + (uint32_t)(kk << 3)), "l"(wdesc + (uint64_t)(kk * kdesc)), "r"(idesc_b), "r"(1u)
                         : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[s])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&op_empty[(it + SA) % TCP_SPLIT_GROUPS][sa])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[par][sd])) : "memory");
             }
             __syncwarp();
         }
-    } else if (warp < 10) {
+        TCP_TICK(2);
+        if (warp == 1) TCP_DUMP(4, 3);
+    } else if (warp == 3) {
+        // idle role slot (keeps the split / epilogue warps on whole TMEM lane quadrants: quadrant = warp & 3)
+    } else if (warp < TCP_ROLE_WARPS + TCP_SPLIT_WARPS) {
         // ===== split warps of stage g: tiles g, g + 2, ...
-        const int g = (warp - 2) >> 2;
+        const int g = (warp - TCP_ROLE_WARPS) >> 2;
         // Row stride d floats.  d % 16 == 0: the same 16-byte piece of neighbouring rows falls on the same banks (8-way conflict for
         // d % 32 == 0), so a thread reads the four pieces of a pair of K steps in the order (p + lane) mod 4 and rotates them back
         // in registers (two select stages): 2-way conflicts at worst.  Other d: at most 2-way as they are.
         const bool rot = (d & 15) == 0;
         const int rl = lane & 3;
-        for (int it = g; it < n_it; it += 2) {
-            const int s = it % S, use = it / S, r = it % R;
-            const uint32_t xh = lane_base + (uint32_t)(s * stage_cols), xl = xh + (uint32_t)KP;
-            tcp_wait(&raw_full[r], (uint32_t)(it / R) & 1u, P.spin);
-            if (use > 0) {  // the MMAs of the tile that used these operand columns last have completed
-                tcp_wait(&acc_full[s], (uint32_t)(use - 1) & 1u, P.spin);
+        constexpr bool TR = !Epi::ROUND_SPLIT;
+        uint32_t ph_raw = 0, ph_op = 0;
+        TCP_T0();
+        for (int it = g, sa = g % SA, r = g % R; it < n_it; it += TCP_SPLIT_GROUPS) {
+            const uint32_t xh = lane_base + (uint32_t)(sa * 2 * KP), xl = xh + (uint32_t)KP;
+            TCP_TICK(4);
+            tcp_wait(&raw_full[g][r], (ph_raw >> r) & 1u, P.spin);
+            ph_raw ^= 1u << r;
+            TCP_TICK(0);
+            if (it >= SA) {  // the MMAs of the tile that used these operand columns last have completed
+                tcp_wait(&op_empty[g][sa], (ph_op >> sa) & 1u, P.spin);
+                ph_op ^= 1u << sa;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
+            TCP_TICK(1);
             const float* rowp = raw + (size_t)r * stage_floats + (size_t)row * d;
+            int k0 = 0;
             if (rot) {
-                for (int kk = 0; kk < ksteps; kk += 2) {
-                    const float4* base = reinterpret_cast<const float4*>(rowp + (kk << 3));
-                    float4 t0 = base[rl], t1 = base[(rl + 1) & 3], t2 = base[(rl + 2) & 3], t3 = base[(rl + 3) & 3];
-                    // t_i = piece (i + rl) mod 4; rotate right by rl: stage 1 by (rl & 1), stage 2 by (rl & 2)
-                    const bool b0 = rl & 1, b1 = rl & 2;
-                    float4 u0 = b0 ? t3 : t0, u1 = b0 ? t0 : t1, u2 = b0 ? t1 : t2, u3 = b0 ? t2 : t3;
-                    float4 p0 = b1 ? u2 : u0, p1 = b1 ? u3 : u1, p2 = b1 ? u0 : u2, p3 = b1 ? u1 : u3;
-                    const float va[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    const float vb[8] = {p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
-                    tcp_split_store(xh, xl, kk << 3, va);
-                    tcp_split_store(xh, xl, (kk + 1) << 3, vb);
-                }
+                for (; k0 + 32 <= KP; k0 += 32) tcp_split_block<32, true, 4, false, TR>(rowp, k0, d, rl, xh, xl);
+                if (k0 < KP) tcp_split_block<16, true, 4, false, TR>(rowp, k0, d, rl, xh, xl);
+            } else if ((d & 3) == 0) {
+                tcp_split_row<4, TR>(rowp, d, KP, xh, xl);
+            } else if ((d & 1) == 0) {
+                tcp_split_row<2, TR>(rowp, d, KP, xh, xl);
             } else {
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    float v[8];
-                    tcp_load8(rowp, kk << 3, d, v);
-                    tcp_split_store(xh, xl, kk << 3, v);
-                }
+                tcp_split_row<1, TR>(rowp, d, KP, xh, xl);
             }
             __syncwarp();
+            TCP_TICK(2);
             if (lane == 0) mbar_arrive(&raw_empty[r]);  // the landing stage may be refilled
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TCP_TICK(3);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&op_full[s]);
+            if (lane == 0) mbar_arrive(&op_full[it & 1][sa]);
+            sa += TCP_SPLIT_GROUPS; while (sa >= SA) sa -= SA;  // ring positions by counters, not runtime modulo
+            r += TCP_SPLIT_GROUPS; while (r >= R) r -= R;
         }
+        TCP_TICK(4);
+        if (warp == TCP_ROLE_WARPS) TCP_DUMP(8, 5);
     } else {
         // ===== epilogue warps of stage e
-        const int e = (warp - 10) >> 2;
-        for (int it = e; it < n_it; it += 2) {
-            const int s = it % S, use = it / S;
-            const uint32_t acc = lane_base + (uint32_t)(s * stage_cols + 2 * KP);
+        const int e = (warp - TCP_ROLE_WARPS - TCP_SPLIT_WARPS) >> 2;
+        uint32_t ph_acc = 0;
+        TCP_T0();
+        for (int it = e, sd = e % SD; it < n_it; it += 2, sd = sd + 2 >= SD ? sd + 2 - SD : sd + 2) {
+            const uint32_t acc = lane_base + (uint32_t)(acc_col0 + sd * ACCW);
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TCP_ROWS;
-            tcp_wait(&acc_full[s], (uint32_t)use & 1u, P.spin);
+            TCP_TICK(3);
+            tcp_wait(&acc_full[e][sd], (ph_acc >> sd) & 1u, P.spin);
+            ph_acc ^= 1u << sd;
+            TCP_TICK(0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             typename Epi::State st;
             Epi::begin(st, row0 + row);
             for (int c0 = 0; c0 < NP; c0 += 16) {
-                float a0[8], a1[8], b0[8], b1[8], sc[16];
-                tmem_ld8(acc + (uint32_t)c0, a0);
-                tmem_ld8(acc + (uint32_t)(c0 + 8), a1);
-                tmem_ld8(acc + (uint32_t)(NP + c0), b0);
-                tmem_ld8(acc + (uint32_t)(NP + c0 + 8), b1);
+                float sc[16], sb[16];
+                tmem_ld16(acc + (uint32_t)c0, sc);
+                if (!one_acc) tmem_ld16(acc + (uint32_t)(NP + c0), sb);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                TCP_TICK(1);
                 if (c0 + 16 >= NP) {  // the accumulator row sits in registers now
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[s]);
+                    if (lane == 0) mbar_arrive(&acc_empty[(it + SD) & 1][sd]);
                 }
+                if (!one_acc) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { sc[q] = a0[q] + b0[q]; sc[8 + q] = a1[q] + b1[q]; }
+                    for (int q = 0; q < 16; ++q) sc[q] += sb[q];
+                }
                 Epi::consume(st, P, aux, c0, sc);
+                TCP_TICK(2);
             }
             if (Epi::SCALAR_OUT) out[row0 + row] = Epi::result(st, P);
         }
+        TCP_TICK(3);
+        if (warp == TCP_ROLE_WARPS + TCP_SPLIT_WARPS) TCP_DUMP(16, 4);
+#ifdef TCP_TIMERS
+        if (warp == TCP_ROLE_WARPS + TCP_SPLIT_WARPS && blockIdx.x == 0 && lane == 0) atomicAdd(&tcp_timers[24], (unsigned long long)n_it);
+#endif
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
