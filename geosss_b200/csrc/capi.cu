@@ -986,7 +986,9 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     if (!t || !out || N < 1) return fail(GEOSSS_E_INVALID, "sampler_create: bad arguments");
     if (kind < GEOSSS_REJECT || kind > GEOSSS_HMC) return fail(GEOSSS_E_INVALID, "sampler_create: unknown sampler kind");
     const bool mh = kind >= GEOSSS_RWMH;
-    if (mh && path == GEOSSS_PATH_FAST) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the baseline samplers run on the literal path");
+    // the baseline samplers run on the literal kernels, except the gradient-free ones on a registration target with cutoff lists
+    const bool mh_cell = mh && path == GEOSSS_PATH_FAST && dtype == GEOSSS_F32 && kind != GEOSSS_HMC && t->kind == TGT_CPD && cpd_use_grid(t);
+    if (mh && path == GEOSSS_PATH_FAST && !mh_cell) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: this baseline sampler runs on the literal path");
     if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "sampler_create: dtype must be f32 or f64");
     if (path == GEOSSS_PATH_FAST) {
         if (dtype != GEOSSS_F32) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: the fast path is float32 only");
@@ -1166,6 +1168,16 @@ static int run_launch(geosss_sampler* s, RunArgs& a, cudaStream_t st) {
         if (cudaMalloc(&s->zbuf, s->zbuf_bytes) != cudaSuccess) { cudaGetLastError(); s->zbuf = nullptr; }  // fall back to regeneration
     }
     a.zbuf = s->zbuf;
+    if (s->path == GEOSSS_PATH_FAST && s->is_mh()) {  // random-walk / independence / mixture MH on the registration cutoff lists
+        const CpdCellGrid g = cpd_grid_now(s->t);
+        const size_t smem = g.smem_bytes();
+        const unsigned grid = (unsigned)((a.N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS);
+        auto kern = g.k > 0 ? k_mh_cpd_cell<true> : k_mh_cpd_cell<false>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, s->kind, a);
+        CU(cudaGetLastError());
+        return 0;
+    }
     return s->path == GEOSSS_PATH_FAST ? target_launch_fast(s->t, s->kind, a, st) : dispatch_literal<false>(s, a, st);
 }
 

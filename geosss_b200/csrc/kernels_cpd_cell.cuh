@@ -27,6 +27,7 @@
 #include "philox.cuh"
 #include "targets.cuh"
 #include "transition.cuh"
+#include "transition_mh.cuh"
 
 namespace geosss {
 
@@ -214,6 +215,64 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_logp_cpd_cell(CpdCel
         SVec<const float> v{q + i * 4, 1};
         const float val = f(v);
         if ((threadIdx.x & 31) == 0) out[i] = val;
+    }
+}
+
+
+// Baseline samplers on the cutoff lists (random-walk MH, independence and their mixture: mcmc.py:115-234; no gradient, so HMC
+// stays on the dense literal kernel): the loop of k_mh_cpd with the cell-list log-density of the slice-sampler kernel above.
+template <bool KNN> struct CpdCellMhTarget {
+    CpdWarpLogPCell<KNN> f;
+    template <class Vec> __device__ __forceinline__ float logp(Vec q) const { return f(q); }
+    template <class Vec, class Out> __device__ __forceinline__ void grad(Vec, Out) const {}  // never called: kind != MH_HMC
+};
+
+template <bool KNN>
+__global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellGrid g, int kind, RunArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CpdCellMhTarget<KNN> f;
+    f.f.g = g;
+    f.f.s = cpd_cell_stage(g, smem_raw);
+    const int64_t c = (int64_t)blockIdx.x * CPD_CELL_WARPS + warp;
+    if (c >= a.N) return;
+    float xs[4], vs[4], xps[4], vps[4], gs[4];
+    Reg4<float> x{xs}, v{vs}, xp{xps}, vp{vps}, gr{gs};
+    float* st = static_cast<float*>(a.state) + c * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { xs[j] = st[j]; vs[j] = 0.f; }
+    PhiloxSeq<float> dr;
+    dr.init(a.seed, a.chain0 + (uint64_t)c);
+    MhChain ch{a.stepsize[c], a.adapt_count[c], a.n_walk[c]};
+    const MhParams mp{a.alpha, a.n_leap, a.adapt_total};
+    unsigned long long acc_total = a.n_reject[c];
+    unsigned int acc_window = 0;
+    float lp = f.logp(x);
+    float* samples = static_cast<float*>(a.samples);
+    float* lpo = static_cast<float*>(a.logp);
+    int64_t since_keep = 0, kept = 0;
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+        dr.begin_step(a.step0 + (uint64_t)t);
+        const bool ok = mh_transition<float>(kind, 4, x, v, xp, vp, gr, dr, f, ch, mp, lp);
+        acc_total += ok ? 1u : 0u;
+        acc_window += ok ? 1u : 0u;
+        if (++since_keep == a.thin) {
+            const int64_t k = kept++;
+            since_keep = 0;
+            if (lane == 0) {
+                if (samples) *reinterpret_cast<float4*>(samples + (k * a.ss_step + c * a.ss_chain)) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
+                if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = acc_window;
+            }
+            acc_window = 0;
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st[j] = xs[j];
+        a.n_reject[c] = acc_total;
+        a.stepsize[c] = ch.stepsize; a.adapt_count[c] = ch.adapt_count; a.n_walk[c] = ch.n_walk;
+        if (a.status) a.status[c] = 0;
     }
 }
 

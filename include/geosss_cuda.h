@@ -184,7 +184,8 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
                        uint64_t* n_reject_host);
 
 /* ---- baseline samplers of the reference's comparison ("next" row f3) ------------------------ */
-/* Kinds GEOSSS_RWMH .. GEOSSS_HMC are created with geosss_sampler_create (literal path) and driven by
+/* Kinds GEOSSS_RWMH .. GEOSSS_HMC are created with geosss_sampler_create (literal path; the gradient-free
+ * kinds also on the fast path for a float32 registration target with cutoff lists: k_mh_cpd_cell) and driven by
  * the same run / run_layout / run_tape / run_host / sample_host entry points.  For them the counter
  * reported as n_reject counts ACCEPTED proposals (MetropolisHastings.n_accept, mcmc.py:133,158) and
  * the per-transition output of run() is 1 if the transition accepted.  Tape order per transition:

@@ -169,3 +169,36 @@ def test_shard_invariance(golden):
     lo = gs.SphericalHMC(pdf, x0[:4], 21, stepsize=0.02, dtype="float64").sample(30, 10)
     hi = gs.SphericalHMC(pdf, x0[4:], 21, stepsize=0.02, dtype="float64", chain_offset=4).sample(30, 10)
     assert np.array_equal(whole, np.concatenate([lo, hi]))
+
+
+@pytest.mark.parametrize("cls,kw", [(gs.MetropolisHastings, dict(stepsize=0.05)),
+                                    (gs.MixtureRWMHIndependenceSampler, dict(stepsize=0.05, mixing_probability=0.7))])
+def test_gradient_free_baselines_on_the_registration_cutoff_lists(golden, cls, kw):
+    """float32 random-walk MH (and its mixture with the independence proposal) on the registration target runs on the cutoff-list
+    kernel (k_mh_cpd_cell, path 'fast'): same Philox draws, same proposals, a log-density that differs from the dense float32
+    sum only by the terms below float32 resolution -- so the chains follow the literal float32 kernel step for step (an
+    accept / reject decision within 1e-4 of the threshold may flip; none does at this size), the adapted step sizes and the
+    acceptance counts agree, and HMC (which needs the gradient) stays on the literal path."""
+    g = golden("logprob_cpd")
+    n = len(g["c5_source"])
+    pdf = gs.CoherentPointDrift(gs.PointCloud(g["c5_target"]), gs.PointCloud(g["c5_source"], np.ones(n) / n), sigma=1.0, k=20, omega=0.4)
+    N, steps = 64, 60
+    x0 = gs.sample_sphere(3, N, seed=31)
+    fast = cls(pdf, x0.copy(), 77, dtype="float32", **kw)
+    a = fast.sample(steps, burnin=20, return_all_samples=True)
+    lit = cls(pdf, x0.copy(), 77, dtype="float32", path="literal", **kw)
+    b = lit.sample(steps, burnin=20, return_all_samples=True)
+    assert fast.path == "fast" and lit.path == "literal"
+    same = np.max(np.abs(a - b), axis=(1, 2)) <= 1e-5
+    assert same.mean() >= 0.95, same.mean()
+    assert np.allclose(fast.stepsize[same], lit.stepsize[same], rtol=1e-6)
+    assert np.array_equal(np.asarray(fast.n_accept_per_chain)[same], np.asarray(lit.n_accept_per_chain)[same])
+    assert 0.05 < fast.n_accept / (N * (steps + 20 - 1)) < 0.95
+    # continuation and shard invariance on the fast path
+    more = fast.sample(5)
+    assert np.array_equal(more[:, 0], a[:, -1])
+    part = cls(pdf, x0[16:32].copy(), 77, dtype="float32", chain_offset=16, **kw)
+    assert np.array_equal(part.sample(steps, burnin=20, return_all_samples=True), a[16:32]) and part.path == "fast"
+    hmc = gs.SphericalHMC(pdf, x0[:4].copy(), 5, stepsize=1e-3, n_steps=3, dtype="float32")
+    hmc.sample(3)
+    assert hmc.path == "literal"
