@@ -45,6 +45,7 @@ def main():
     gs.MetropolisHastings(c2, x0(c2, N), 13)._run_device(50, None)
     gs.SphericalHMC(c2, x0(c2, N), 14, stepsize=0.02)._run_device(5, None)
     gs.SphericalHMC(cpd_knn, x0(cpd_knn, 1024), 15)._run_device(1, None)
+    gs.MetropolisHastings(cpd_knn, x0(cpd_knn, 16384), 16, stepsize=0.05)._run_device(10, None)  # cutoff lists: k_mh_cpd_cell
     # log_prob / gradient
     for pdf, count in ((c2, 1 << 22), (hi, 1 << 20), (curved, 1 << 19), (diag, 1 << 20), (dense, 1 << 20), (cpd_dense, 1 << 13)):
         x = x0(pdf, count).float()
