@@ -67,8 +67,8 @@ def main():
 
 
 def registration(a):
-    """C5: slice samplers and random-walk MH on the cutoff-list kernels (path 'fast'), RWMH and HMC on the dense literal float32
-    kernels beside them (fewer chains: they are 30x slower)."""
+    """C5: slice samplers, random-walk MH and HMC (10 leapfrog steps) on the cutoff-list kernels (path 'fast'), RWMH and HMC on the
+    dense literal float32 kernels beside them (fewer chains: they are 50-90x slower)."""
     dev = torch.device("cuda", 0)
     g = np.load(os.path.join(ROOT, "tests", "golden", "logprob_cpd.npz"))
     n = len(g["c5_source"])
@@ -78,7 +78,8 @@ def registration(a):
         ("sss-shrink", a.chains, lambda x0: gs.ShrinkageSphericalSliceSampler(pdf, x0, 7)),
         ("rwmh", a.chains, lambda x0: gs.MetropolisHastings(pdf, x0, 7, stepsize=0.05)),
         ("rwmh (literal float32, dense sum)", a.chains // 16, lambda x0: gs.MetropolisHastings(pdf, x0, 7, stepsize=0.05, path="literal")),
-        ("hmc (literal float32, dense sum)", a.chains // 16, lambda x0: gs.SphericalHMC(pdf, x0, 7, stepsize=1e-3, n_steps=10)),
+        ("hmc", a.chains, lambda x0: gs.SphericalHMC(pdf, x0, 7, stepsize=1e-3, n_steps=10)),
+        ("hmc (literal float32, dense sum)", a.chains // 16, lambda x0: gs.SphericalHMC(pdf, x0, 7, stepsize=1e-3, n_steps=10, path="literal")),
     ]
     for name, N, make in cases:
         x0 = torch.as_tensor(gs.sample_sphere(3, N, seed=4), dtype=torch.float32, device=dev)

@@ -986,8 +986,8 @@ extern "C" int geosss_sampler_create(geosss_target_t t, int kind, int dtype, int
     if (!t || !out || N < 1) return fail(GEOSSS_E_INVALID, "sampler_create: bad arguments");
     if (kind < GEOSSS_REJECT || kind > GEOSSS_HMC) return fail(GEOSSS_E_INVALID, "sampler_create: unknown sampler kind");
     const bool mh = kind >= GEOSSS_RWMH;
-    // the baseline samplers run on the literal kernels, except the gradient-free ones on a registration target with cutoff lists
-    const bool mh_cell = mh && path == GEOSSS_PATH_FAST && dtype == GEOSSS_F32 && kind != GEOSSS_HMC && t->kind == TGT_CPD && cpd_use_grid(t);
+    // the baseline samplers run on the literal kernels, except on a float32 registration target with cutoff lists (k_mh_cpd_cell)
+    const bool mh_cell = mh && path == GEOSSS_PATH_FAST && dtype == GEOSSS_F32 && t->kind == TGT_CPD && cpd_use_grid(t);
     if (mh && path == GEOSSS_PATH_FAST && !mh_cell) return fail(GEOSSS_E_UNSUPPORTED, "sampler_create: this baseline sampler runs on the literal path");
     if (dtype != GEOSSS_F32 && dtype != GEOSSS_F64) return fail(GEOSSS_E_INVALID, "sampler_create: dtype must be f32 or f64");
     if (path == GEOSSS_PATH_FAST) {
@@ -1168,11 +1168,12 @@ static int run_launch(geosss_sampler* s, RunArgs& a, cudaStream_t st) {
         if (cudaMalloc(&s->zbuf, s->zbuf_bytes) != cudaSuccess) { cudaGetLastError(); s->zbuf = nullptr; }  // fall back to regeneration
     }
     a.zbuf = s->zbuf;
-    if (s->path == GEOSSS_PATH_FAST && s->is_mh()) {  // random-walk / independence / mixture MH on the registration cutoff lists
+    if (s->path == GEOSSS_PATH_FAST && s->is_mh()) {  // random-walk / independence / mixture MH and HMC on the registration cutoff lists
         const CpdCellGrid g = cpd_grid_now(s->t);
         const size_t smem = g.smem_bytes();
         const unsigned grid = (unsigned)((a.N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS);
-        auto kern = g.k > 0 ? k_mh_cpd_cell<true> : k_mh_cpd_cell<false>;
+        auto kern = s->kind == GEOSSS_HMC ? (g.k > 0 ? k_mh_cpd_cell<true, true> : k_mh_cpd_cell<false, true>)
+                                          : (g.k > 0 ? k_mh_cpd_cell<true, false> : k_mh_cpd_cell<false, false>);
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, CPD_CELL_WARPS * 32, smem, st>>>(g, s->kind, a);
         CU(cudaGetLastError());
@@ -1454,6 +1455,20 @@ template <typename T> static int gradient_any(geosss_target* t, const void* x, v
     const T* xi = static_cast<const T*>(x);
     T* o = static_cast<T*>(out);
     int rc;
+    if (sizeof(T) == 4 && t->kind == TGT_CPD && cpd_use_grid(t) && !std::getenv("GEOSSS_GRAD_DENSE")) {  // float32: cutoff lists
+        const CpdCellGrid g = cpd_grid_now(t);
+        const size_t gsmem = g.smem_bytes();
+        int dev = 0, sms = 148;
+        CU(cudaGetDevice(&dev));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t want = (N + CPD_CELL_WARPS - 1) / CPD_CELL_WARPS;
+        const int64_t cap = (int64_t)sms * (gsmem <= 110 * 1024 ? 2 : 1);
+        auto kern = g.k > 0 ? k_grad_cpd_cell<true> : k_grad_cpd_cell<false>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        kern<<<(unsigned)(want < cap ? want : cap), CPD_CELL_WARPS * 32, gsmem, st>>>(g, reinterpret_cast<const float*>(xi), reinterpret_cast<float*>(o), N);
+        CU(cudaGetLastError());
+        return 0;
+    }
     switch (t->kind) {
         case TGT_VMF_MIX: rc = launch_grad<T>(t->vmf<T>(), xi, o, N, st); break;
         case TGT_BINGHAM: rc = launch_grad<T>(t->bingham<T>(), xi, o, N, st); break;

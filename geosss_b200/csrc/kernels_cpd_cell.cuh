@@ -154,6 +154,116 @@ template <bool KNN> struct CpdWarpLogPCell {
         const float probe = R[0] + R[4] + R[8];
         return probe == probe ? g.beta * (float)acc : probe;  // NaN quaternion -> NaN, as the dense sum gives
     }
+
+    // Gradient with respect to the quaternion (registration.py:261-293) on the same lists.  With e = t_l - (R x_k + shift) =
+    // h R (f - m) and x_k = org + h m (m: list entry, f: the row in cell units) the 3 x 3 matrix of cpd_row_grad is
+    //   G = sum_l sum_k c_lk e x_k^T = h R (V org^T + h W),  V = sum c (f - m),  W = sum c (f - m) m^T,
+    // c_lk = w_l gamma_lk / sigma^2 with the responsibilities gamma_lk = term_k / (outlier + sum of the row's terms): 12
+    // accumulators per lane.  Candidates beyond the cutoff carry responsibilities below float32 resolution (upstream clips
+    // them at e^-20; their share of G is ~1e-7 relative).  The quotient-rule Jacobian of R(q) is cpd_grad_finish's.
+    template <class Vec, class Out> __device__ __forceinline__ void grad(Vec q, Out out) const {
+        const int lane = threadIdx.x & 31;
+        const int grp = lane >> 2, sub = lane & 3;
+        float R[9];
+        quat_to_matrix<float>(q[0], q[1], q[2], q[3], R);
+        float M[9], c[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) M[3 * i + jj] = R[3 * jj + i] * g.inv_h;
+            c[i] = -fmaf(M[3 * i], g.shift[0], fmaf(M[3 * i + 1], g.shift[1], fmaf(M[3 * i + 2], g.shift[2], g.org[i] * g.inv_h)));
+        }
+        const float hx = (float)g.n[0] - 1.f, hy = (float)g.n[1] - 1.f, hz = (float)g.n[2] - 1.f;
+        float V[3] = {0.f, 0.f, 0.f}, W[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int l0 = 0; l0 < g.nt; l0 += 8) {
+            const int l = l0 + grp;
+            const float4 y = s.tgt4[l < g.nt ? l : g.nt - 1];
+            const float fx = fmaf(M[0], y.x, fmaf(M[1], y.y, fmaf(M[2], y.z, c[0])));
+            const float fy = fmaf(M[3], y.x, fmaf(M[4], y.y, fmaf(M[5], y.z, c[1])));
+            const float fz = fmaf(M[6], y.x, fmaf(M[7], y.y, fmaf(M[8], y.z, c[2])));
+            const int cx = (int)fminf(fmaxf(fx, 0.f), hx), cy = (int)fminf(fmaxf(fy, 0.f), hy), cz = (int)fminf(fmaxf(fz, 0.f), hz);
+            const uint32_t cw = s.cell[(cz * g.n[1] + cy) * g.n[0] + cx];
+            const int cnt = (int)(cw >> CPD_CELL_COUNT_SHIFT);
+            const float4* e = s.entry + (cw & ((1u << CPD_CELL_COUNT_SHIFT) - 1u));
+            float sum = 0.f, v[3] = {0.f, 0.f, 0.f}, w[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int inside = 0;
+            for (int k = sub; k < cnt; k += 4) {
+                const float4 m = e[k];
+                const float e0 = fx - m.x, e1 = fy - m.y, e2 = fz - m.z;
+                const float d2 = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+                if (KNN) inside += d2 < g.rc2 ? 1 : 0;
+                const float tk = fast_ex2(fmaf(d2, g.q2, m.w));
+                sum += tk;
+                const float a0 = tk * e0, a1 = tk * e1, a2 = tk * e2;
+                v[0] += a0; v[1] += a1; v[2] += a2;
+                w[0] = fmaf(a0, m.x, w[0]); w[1] = fmaf(a0, m.y, w[1]); w[2] = fmaf(a0, m.z, w[2]);
+                w[3] = fmaf(a1, m.x, w[3]); w[4] = fmaf(a1, m.y, w[4]); w[5] = fmaf(a1, m.z, w[5]);
+                w[6] = fmaf(a2, m.x, w[6]); w[7] = fmaf(a2, m.y, w[7]); w[8] = fmaf(a2, m.z, w[8]);
+            }
+            if (KNN) {  // more than k candidates inside the cutoff: keep exactly the k nearest, as operator() does
+                inside += __shfl_xor_sync(0xffffffffu, inside, 1);
+                inside += __shfl_xor_sync(0xffffffffu, inside, 2);
+                const bool crowded = inside > g.k;
+                if (__any_sync(0xffffffffu, crowded)) {
+                    const int n = crowded ? cnt : 0;
+                    if (crowded) { sum = 0.f; v[0] = v[1] = v[2] = 0.f; for (int i = 0; i < 9; ++i) w[i] = 0.f; }
+                    for (int i = sub; i < n; i += 4) {
+                        const float4 mi = e[i];
+                        const float e0 = fx - mi.x, e1 = fy - mi.y, e2 = fz - mi.z;
+                        const float di = fmaf(e0, e0, fmaf(e1, e1, e2 * e2));
+                        int rank = 0;
+                        for (int j = 0; j < n; ++j) {
+                            const float4 mj = e[j];
+                            const float b0 = fx - mj.x, b1 = fy - mj.y, b2 = fz - mj.z;
+                            const float dj = fmaf(b0, b0, fmaf(b1, b1, b2 * b2));
+                            rank += (dj < di || (dj == di && j < i)) ? 1 : 0;
+                        }
+                        if (rank < g.k) {
+                            const float tk = fast_ex2(fmaf(di, g.q2, mi.w));
+                            sum += tk;
+                            const float a0 = tk * e0, a1 = tk * e1, a2 = tk * e2;
+                            v[0] += a0; v[1] += a1; v[2] += a2;
+                            w[0] = fmaf(a0, mi.x, w[0]); w[1] = fmaf(a0, mi.y, w[1]); w[2] = fmaf(a0, mi.z, w[2]);
+                            w[3] = fmaf(a1, mi.x, w[3]); w[4] = fmaf(a1, mi.y, w[4]); w[5] = fmaf(a1, mi.z, w[5]);
+                            w[6] = fmaf(a2, mi.x, w[6]); w[7] = fmaf(a2, mi.y, w[7]); w[8] = fmaf(a2, mi.z, w[8]);
+                        }
+                    }
+                }
+            }
+            float tot = sum;
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            const float sc = l < g.nt ? y.w / (g.base + tot) : 0.f;  // w_l / (outlier + sum): this lane's terms become responsibilities
+#pragma unroll
+            for (int i = 0; i < 3; ++i) V[i] = fmaf(sc, v[i], V[i]);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) W[i] = fmaf(sc, w[i], W[i]);
+        }
+        // Q = V org^T + h W, reduced over the warp in double like the dense kernel, then G = (h / sigma^2) R Q
+        const float h = 1.0f / g.inv_h;
+        const float inv_s2 = -2.0f * g.q2 * g.inv_h * g.inv_h * 0.6931471805599453f;  // q2 = -0.5 log2(e) h^2 / sigma^2
+        float Q[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                double t = (double)fmaf(V[i], g.org[jj], h * W[3 * i + jj]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                Q[3 * i + jj] = (float)t;
+            }
+        float G[9];
+        const float k0 = h * inv_s2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+                G[3 * i + jj] = k0 * fmaf(R[3 * i], Q[jj], fmaf(R[3 * i + 1], Q[3 + jj], R[3 * i + 2] * Q[6 + jj]));
+        CpdP<float> pb{};
+        pb.beta = g.beta;
+        cpd_grad_finish<float>(pb, q[0], q[1], q[2], q[3], G, out);
+    }
 };
 
 template <int KIND, bool KNN>
@@ -219,19 +329,22 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_logp_cpd_cell(CpdCel
 }
 
 
-// Baseline samplers on the cutoff lists (random-walk MH, independence and their mixture: mcmc.py:115-234; no gradient, so HMC
-// stays on the dense literal kernel): the loop of k_mh_cpd with the cell-list log-density of the slice-sampler kernel above.
-template <bool KNN> struct CpdCellMhTarget {
+// Baseline samplers on the cutoff lists (random-walk MH, independence, their mixture and spherical HMC: mcmc.py:115-332): the
+// loop of k_mh_cpd with the cell-list log-density and gradient above.
+// GRAD = false (the gradient-free kinds): the gradient code is left out and two blocks fit an SM.
+template <bool KNN, bool GRAD> struct CpdCellMhTarget {
     CpdWarpLogPCell<KNN> f;
     template <class Vec> __device__ __forceinline__ float logp(Vec q) const { return f(q); }
-    template <class Vec, class Out> __device__ __forceinline__ void grad(Vec, Out) const {}  // never called: kind != MH_HMC
+    template <class Vec, class Out> __device__ __forceinline__ void grad(Vec q, Out o) const {
+        if constexpr (GRAD) f.grad(q, o);
+    }
 };
 
-template <bool KNN>
-__global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellGrid g, int kind, RunArgs a) {
+template <bool KNN, bool GRAD>
+__global__ void __launch_bounds__(CPD_CELL_WARPS * 32, GRAD ? 1 : 2) k_mh_cpd_cell(CpdCellGrid g, int kind, RunArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    CpdCellMhTarget<KNN> f;
+    CpdCellMhTarget<KNN, GRAD> f;
     f.f.g = g;
     f.f.s = cpd_cell_stage(g, smem_raw);
     const int64_t c = (int64_t)blockIdx.x * CPD_CELL_WARPS + warp;
@@ -239,8 +352,9 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellG
     float xs[4], vs[4], xps[4], vps[4], gs[4];
     Reg4<float> x{xs}, v{vs}, xp{xps}, vp{vps}, gr{gs};
     float* st = static_cast<float*>(a.state) + c * 4;
+    float* mom = static_cast<float*>(a.momentum) + c * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { xs[j] = st[j]; vs[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { xs[j] = st[j]; vs[j] = mom[j]; }
     PhiloxSeq<float> dr;
     dr.init(a.seed, a.chain0 + (uint64_t)c);
     MhChain ch{a.stepsize[c], a.adapt_count[c], a.n_walk[c]};
@@ -250,6 +364,7 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellG
     float lp = f.logp(x);
     float* samples = static_cast<float*>(a.samples);
     float* lpo = static_cast<float*>(a.logp);
+    float* momenta = static_cast<float*>(a.momenta_out);
     int64_t since_keep = 0, kept = 0;
     for (int64_t t = 0; t < a.n_steps; ++t) {
         dr.begin_step(a.step0 + (uint64_t)t);
@@ -261,6 +376,7 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellG
             since_keep = 0;
             if (lane == 0) {
                 if (samples) *reinterpret_cast<float4*>(samples + (k * a.ss_step + c * a.ss_chain)) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                if (momenta) *reinterpret_cast<float4*>(momenta + (k * a.ss_step + c * a.ss_chain)) = make_float4(vs[0], vs[1], vs[2], vs[3]);
                 if (lpo) lpo[k * a.sl_step + c * a.sl_chain] = lp;
                 if (a.nrej) a.nrej[k * a.sl_step + c * a.sl_chain] = acc_window;
             }
@@ -269,10 +385,28 @@ __global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_mh_cpd_cell(CpdCellG
     }
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) st[j] = xs[j];
+        for (int j = 0; j < 4; ++j) { st[j] = xs[j]; mom[j] = vs[j]; }
         a.n_reject[c] = acc_total;
         a.stepsize[c] = ch.stepsize; a.adapt_count[c] = ch.adapt_count; a.n_walk[c] = ch.n_walk;
         if (a.status) a.status[c] = 0;
+    }
+}
+
+// batched gradient, persistent over points like k_logp_cpd_cell
+template <bool KNN>
+__global__ void __launch_bounds__(CPD_CELL_WARPS * 32, 2) k_grad_cpd_cell(CpdCellGrid g, const float* __restrict__ q,
+                                                                       float* __restrict__ out, int64_t N) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    CpdWarpLogPCell<KNN> f;
+    f.g = g;
+    f.s = cpd_cell_stage(g, smem_raw);
+    for (int64_t i = (int64_t)blockIdx.x * CPD_CELL_WARPS + warp; i < N; i += (int64_t)gridDim.x * CPD_CELL_WARPS) {
+        SVec<const float> v{q + i * 4, 1};
+        float gq[4];
+        Reg4<float> o{gq};
+        f.grad(v, o);
+        if ((threadIdx.x & 31) == 0) *reinterpret_cast<float4*>(out + i * 4) = make_float4(gq[0], gq[1], gq[2], gq[3]);
     }
 }
 

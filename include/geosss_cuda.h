@@ -184,8 +184,8 @@ int geosss_sample_host(geosss_target_t t, int kind, int dtype, int path, int64_t
                        uint64_t* n_reject_host);
 
 /* ---- baseline samplers of the reference's comparison ("next" row f3) ------------------------ */
-/* Kinds GEOSSS_RWMH .. GEOSSS_HMC are created with geosss_sampler_create (literal path; the gradient-free
- * kinds also on the fast path for a float32 registration target with cutoff lists: k_mh_cpd_cell) and driven by
+/* Kinds GEOSSS_RWMH .. GEOSSS_HMC are created with geosss_sampler_create (literal path; also the fast
+ * path for a float32 registration target with cutoff lists: k_mh_cpd_cell) and driven by
  * the same run / run_layout / run_tape / run_host / sample_host entry points.  For them the counter
  * reported as n_reject counts ACCEPTED proposals (MetropolisHastings.n_accept, mcmc.py:133,158) and
  * the per-transition output of run() is 1 if the transition accepted.  Tape order per transition:
@@ -205,7 +205,8 @@ int geosss_sampler_mh_momenta_out(geosss_sampler_t s, void* momenta_out);
 int geosss_sampler_mh_get_host(geosss_sampler_t s, double* stepsize_host, uint64_t* n_walk_host, double* momentum_host);
 
 /* Distribution.gradient(x) for x of shape (N, d) (distributions.py:88-89, :159-160, :223-227, :277-278;
- * registration.py:55-59 with pointcloud.py:135-203).  x, out: (N, d) device, `dtype`. */
+ * registration.py:55-59 with pointcloud.py:135-203).  x, out: (N, d) device, `dtype`.  A float32 registration target with
+ * cutoff lists is evaluated on the lists (k_grad_cpd_cell; GEOSSS_GRAD_DENSE=1 keeps the dense sum). */
 int geosss_gradient(geosss_target_t t, int dtype, const void* x, void* out, int64_t N, void* stream);
 
 /* ---- exact i.i.d. samplers used as ground truth ("next" row f4; geosss/rand.py) ----------------- */
