@@ -63,6 +63,11 @@ def main():
         ("bingham dense d=32", gs.random_bingham(32, 300, 0, False, 6982), [("tcgen05 pipelined", {}), ("tcgen05 round-1 kernel", {"GEOSSS_TC_V1": "1"})]),
         ("vmf mixture d=100 K=8", mix(100, 8, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
         ("vmf mixture d=32 K=8", mix(32, 8, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
+        ("vmf mixture d=24 K=8", mix(24, 8, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
+        ("vmf mixture d=40 K=8", mix(40, 8, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
+        ("vmf mixture d=48 K=8", mix(48, 8, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
+        ("bingham dense d=40", gs.random_bingham(40, 300, 0, False, 6982), [("tcgen05 pipelined", {})]),
+        ("bingham dense d=16", gs.random_bingham(16, 300, 0, False, 6982), [("tcgen05 pipelined", {})]),
         ("vmf mixture d=64 K=12", mix(64, 12, 100.0), [("tcgen05 pipelined", {}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),
         ("curved vmf d=100 10 knots (C3)", gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(10, 100, 0.5, seed=4562)), 500.0),
          [("tcgen05 pipelined", {}), ("tcgen05, 2 landing stages", {"GEOSSS_TC_STAGES": "2"}), ("fp32 SIMT", {"GEOSSS_NO_TC": "1"})]),

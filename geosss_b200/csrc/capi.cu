@@ -828,21 +828,26 @@ static int logp_vmf_const(geosss_target* t, const float* x, float* o, int64_t N,
 // unaligned input) goes to the SIMT tiled kernel passed as `simt`.  GEOSSS_NO_TC=1 keeps everything on the SIMT kernels.
 template <class Epi, class Simt>
 static int logp_tc(const TcpParams& tp, const float* x, float* out, int64_t N, cudaStream_t st, Simt simt) {
-    const int64_t full = N / TCP_ROWS;
+    int64_t full = N / TCP_ROWS;
     if (full == 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return simt(x, out, N);
     if (!g_sm_count) {
         int dev = 0;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    int R = tcp_stages(tp.d, tp.np, Epi::AUX);
+    TcpParams tq = tp;
+    tq.sub = std::getenv("GEOSSS_TC_SUB1") ? 1 : tcp_sub(tp.d, tp.np, Epi::AUX, Epi::ONE_ACC);  // GEOSSS_TC_SUB1=1: 128-row tiles (A/B runs)
+    if (const char* e = std::getenv("GEOSSS_TC_SUBCAP")) { const int v = std::atoi(e); if (v >= 1 && v < tq.sub) tq.sub = v; }
+    while (tq.sub > 1 && full < 2 * (int64_t)g_sm_count * tq.sub) --tq.sub;  // small batches: keep every SM busy
+    full = N / (TCP_ROWS * tq.sub);
+    int R = tcp_stages(tp.d, tp.np, Epi::AUX, tq.sub);
     if (const char* e = std::getenv("GEOSSS_TC_STAGES")) { const int v = std::atoi(e); if (v >= 2 && v <= R) R = v; }
-    const size_t smem = tcp_smem_bytes(tp.d, tp.np, Epi::AUX, R);
+    const size_t smem = tcp_smem_bytes(tp.d, tp.np, Epi::AUX, R, tq.sub);
     CU(cudaFuncSetAttribute(k_logp_tc<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = full < g_sm_count ? full : g_sm_count;  // persistent: one block per SM (all 512 TMEM columns)
-    k_logp_tc<Epi><<<(unsigned)grid, TCP_THREADS, smem, st>>>(tp, x, out, full, R);
+    k_logp_tc<Epi><<<(unsigned)grid, TCP_THREADS, smem, st>>>(tq, x, out, full, R);
     CU(cudaGetLastError());
-    const int64_t done = full * TCP_ROWS;
+    const int64_t done = full * TCP_ROWS * tq.sub;
     return done < N ? simt(x + done * tp.d, out + done, N - done) : 0;
 }
 

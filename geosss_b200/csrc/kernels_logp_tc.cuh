@@ -54,6 +54,7 @@ struct TcpParams {
     int np;           // accumulator columns per half: n_out rounded up to 16 (UMMA N is a multiple of 16 at M = 128)
     int spin;         // 1: barrier waits poll with mbarrier.test_wait, 0 (default): mbarrier.try_wait
     float* rows_out;  // TcRotateEpi: (N, d) output rows (may be the input array: a tile is consumed before it is written)
+    int sub;          // 128-row MMA groups per tile (0 / 1 .. 4): narrow rows take 256-512-row tiles, one hand-off per tile
 };
 
 // Waits of the role warps: mbarrier.try_wait (may suspend the warp for a time slice) or, with GEOSSS_TC_SPIN=1, polling with
@@ -184,7 +185,7 @@ struct TcCurvedEpi {
     }
     static __device__ __forceinline__ float scale() { return 1.f; }
     static constexpr bool SCALAR_OUT = true;
-    static constexpr bool ROUND_SPLIT = false;
+    static constexpr bool ROUND_SPLIT = true;   // the segment maximum amplifies the split error (sqrt of a difference of squares): rounded hi
     static constexpr bool ONE_ACC = false;
     static __device__ __forceinline__ void begin(State& st, int64_t) { st.v = 0.f; }
     // max over segments of x . nearest point, first segment wins ties: CurvedGcT::best_dot (kernels_gc.cuh) at theta = 0
@@ -330,7 +331,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     const int NP = P.np, NS = 2 * NP;  // W is stacked: rows 0..NP-1 of a K block hold Wh, rows NP..2NP-1 hold Wl
     const int d = P.d, ksteps = (d + 7) >> 3, KP = ksteps << 3;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const size_t stage_floats = ((size_t)TCP_ROWS * d + 31) & ~(size_t)31;
+    const int SUBT = P.sub < 1 ? 1 : (P.sub > 4 ? 4 : P.sub), ROWS = TCP_ROWS * SUBT;
+    const size_t stage_floats = ((size_t)ROWS * d + 31) & ~(size_t)31;
     float* raw = reinterpret_cast<float*>(tcp_smem);
     float* Ws = raw + (size_t)R * stage_floats;           // ksteps blocks of NS x 8, canonical K-major / no swizzle
     float* aux = Ws + (size_t)ksteps * NS * 8;
@@ -375,16 +377,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
     // (ACCW columns each); tile `it` uses operand stage it mod SA and accumulator stage it mod SD.  Decoupled, so that the
     // split of a later tile overlaps the MMAs of this one even where only two whole (operand + accumulator) groups would fit.
     const int ACCW = one_acc ? NP : NS;
-    int SA = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - 2 * ACCW) / (2 * KP)));
-    int SD = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - SA * 2 * KP) / ACCW));
+    const int OPW = SUBT * 2 * KP, ACW = SUBT * ACCW;  // columns of one operand / accumulator stage (all sub-tiles)
+    int SA = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - 2 * ACW) / OPW));
+    int SD = max(2, min(TCP_TMEM_STAGES, (TCP_TMEM_COLS - SA * OPW) / ACW));
     {  // experiment knobs: ring depths from GEOSSS_TC_SPIN bits 8-11 (operands) and 12-15 (accumulators), ignored unless they fit
         const int ka = (P.spin >> 8) & 15, kd = (P.spin >> 12) & 15;
         const int sa2 = ka ? ka : SA, sd2 = kd ? kd : SD;
-        if (sa2 >= 2 && sd2 >= 2 && sa2 <= TCP_TMEM_STAGES && sd2 <= TCP_TMEM_STAGES && sa2 * 2 * KP + sd2 * ACCW <= TCP_TMEM_COLS) { SA = sa2; SD = sd2; }
+        if (sa2 >= 2 && sd2 >= 2 && sa2 <= TCP_TMEM_STAGES && sd2 <= TCP_TMEM_STAGES && sa2 * OPW + sd2 * ACW <= TCP_TMEM_COLS) { SA = sa2; SD = sd2; }
     }
-    const int acc_col0 = SA * 2 * KP;
+    const int acc_col0 = SA * OPW;
     const int n_it = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const size_t tile_floats = (size_t)TCP_ROWS * d;
+    const size_t tile_floats = (size_t)ROWS * d;
     const int quad = warp & 3;  // the TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
@@ -435,8 +438,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
             if (it >= SD) { tcp_wait(&acc_empty[par][sd], (ph_acc >> (4 * par + sd)) & 1u, P.spin); ph_acc ^= 1u << (4 * par + sd); }
             TCP_TICK(1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t xh = tmem + (uint32_t)(sa * 2 * KP), xl = xh + (uint32_t)KP, acc = tmem + (uint32_t)(acc_col0 + sd * ACCW);
             if (elected) {
+              for (int sb = 0; sb < SUBT; ++sb) {
+                const uint32_t xh = tmem + (uint32_t)(sa * OPW + sb * 2 * KP), xl = xh + (uint32_t)KP, acc = tmem + (uint32_t)(acc_col0 + sd * ACW + sb * ACCW);
                 if (one_acc) {  // three N = NP passes onto the same columns: Xh Wh, Xh Wl, Xl Wh
 #pragma unroll 4
                     for (int kk = 0; kk < ksteps; ++kk)
@@ -468,6 +472,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
                         ::"r"(acc), "r"(xl + (uint32_t)(kk << 3)), "l"(wdesc + (uint64_t)(kk * kdesc)), "r"(idesc_b), "r"(1u)
                         : "memory");
+              }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&op_empty[(it + SA) % TCP_SPLIT_GROUPS][sa])) : "memory");
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&acc_full[par][sd])) : "memory");
             }
@@ -489,7 +494,6 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         uint32_t ph_raw = 0, ph_op = 0;
         TCP_T0();
         for (int it = g, sa = g % SA, r = g % R; it < n_it; it += TCP_SPLIT_GROUPS) {
-            const uint32_t xh = lane_base + (uint32_t)(sa * 2 * KP), xl = xh + (uint32_t)KP;
             TCP_TICK(4);
             tcp_wait(&raw_full[g][r], (ph_raw >> r) & 1u, P.spin);
             ph_raw ^= 1u << r;
@@ -500,7 +504,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             TCP_TICK(1);
-            const float* rowp = raw + (size_t)r * stage_floats + (size_t)row * d;
+          for (int sb = 0; sb < SUBT; ++sb) {
+            const uint32_t xh = lane_base + (uint32_t)(sa * OPW + sb * 2 * KP), xl = xh + (uint32_t)KP;
+            const float* rowp = raw + (size_t)r * stage_floats + (size_t)(sb * TCP_ROWS + row) * d;
             int k0 = 0;
             if (rot) {
                 for (; k0 + 32 <= KP; k0 += 32) tcp_split_block<32, true, 4, false, TR>(rowp, k0, d, rl, xh, xl);
@@ -512,6 +518,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
             } else {
                 tcp_split_row<1, TR>(rowp, d, KP, xh, xl);
             }
+          }
             __syncwarp();
             TCP_TICK(2);
             if (lane == 0) mbar_arrive(&raw_empty[r]);  // the landing stage may be refilled
@@ -531,13 +538,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
         uint32_t ph_acc = 0;
         TCP_T0();
         for (int it = e, sd = e % SD; it < n_it; it += 2, sd = sd + 2 >= SD ? sd + 2 - SD : sd + 2) {
-            const uint32_t acc = lane_base + (uint32_t)(acc_col0 + sd * ACCW);
-            const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TCP_ROWS;
+            const int64_t tile_row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * ROWS;
             TCP_TICK(3);
             tcp_wait(&acc_full[e][sd], (ph_acc >> sd) & 1u, P.spin);
             ph_acc ^= 1u << sd;
             TCP_TICK(0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int sub_i = 0; sub_i < SUBT; ++sub_i) {
+            const uint32_t acc = lane_base + (uint32_t)(acc_col0 + sd * ACW + sub_i * ACCW);
+            const int64_t row0 = tile_row0 + sub_i * TCP_ROWS;
             typename Epi::State st;
             Epi::begin(st, row0 + row);
             for (int c0 = 0; c0 < NP; c0 += 16) {
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                 if (!one_acc) tmem_ld16(acc + (uint32_t)(NP + c0), sb);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 TCP_TICK(1);
-                if (c0 + 16 >= NP) {  // the accumulator row sits in registers now
+                if (c0 + 16 >= NP && sub_i == SUBT - 1) {  // the accumulator rows sit in registers now
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[(it + SD) & 1][sd]);
@@ -559,6 +568,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
                 TCP_TICK(2);
             }
             if (Epi::SCALAR_OUT) out[row0 + row] = Epi::result(st, P);
+          }
         }
         TCP_TICK(3);
         if (warp == TCP_ROLE_WARPS + TCP_SPLIT_WARPS) TCP_DUMP(16, 4);
@@ -577,15 +587,26 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) k_logp_tc(TcpParams P, const f
 
 // shared memory of one block with R landing stages; R: as many as fit next to the operands (at most TCP_MAX_STAGES)
 inline int tcp_np(int n_out) { return (n_out + 15) / 16 * 16; }
-inline size_t tcp_smem_bytes(int d, int np, int aux, int R) {
+inline size_t tcp_smem_bytes(int d, int np, int aux, int R, int sub = 1) {
     const int ksteps = (d + 7) / 8;
-    const size_t stage = ((size_t)TCP_ROWS * d + 31) & ~(size_t)31;
+    const size_t stage = ((size_t)TCP_ROWS * sub * d + 31) & ~(size_t)31;
     return ((size_t)R * stage + 2 * (size_t)ksteps * np * 8 + aux) * sizeof(float) + 128;  // landing ring + stacked W + constants
 }
-inline int tcp_stages(int d, int np, int aux) {
+inline int tcp_stages(int d, int np, int aux, int sub = 1) {
     int R = TCP_MAX_STAGES;
-    while (R > 2 && tcp_smem_bytes(d, np, aux, R) > 220 * 1024) --R;
-    return tcp_smem_bytes(d, np, aux, R) <= 220 * 1024 ? R : 0;
+    while (R > 2 && tcp_smem_bytes(d, np, aux, R, sub) > 220 * 1024) --R;
+    return tcp_smem_bytes(d, np, aux, R, sub) <= 220 * 1024 ? R : 0;
+}
+// Tiles of 256 rows (2 MMA groups per hand-off) where two operand and two accumulator stages of that size fit tensor memory
+// and four landing stages fit shared memory: narrow rows, whose 16 KB tiles did not amortise the hand-offs between the role
+// warps (measured: vMF d=32 0.67 -> 0.88 of HBM, d=24 0.59 -> 0.77, d=48 0.84 -> 0.89, Bingham d=32 0.62 -> 0.82).  The kernel
+// takes up to 4 groups per tile; 3 (d=24: 0.66) and 4 (Bingham d=16: 0.63 against 0.57) were mixed, so 2 is the rule.
+inline int tcp_sub(int d, int np, int aux, bool one_acc, int dmax = 64) {
+    const int kp = (d + 7) / 8 * 8, accw = one_acc ? np : 2 * np;
+    if (d > dmax) return 1;
+    for (int sub = 2; sub > 1; --sub)
+        if (2 * (sub * 2 * kp) + 2 * (sub * accw) <= TCP_TMEM_COLS && tcp_stages(d, np, aux, sub) >= 4) return sub;
+    return 1;
 }
 // two TMEM stages (hi, lo operand columns + the two accumulator halves each) must fit the 512 columns
 template <class Epi> inline bool tcp_fits(int d, int n_out) {

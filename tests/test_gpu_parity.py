@@ -328,6 +328,29 @@ def test_dense_bingham_logprob_on_tensor_cores():
     assert rel_err(simt, want) <= 1e-5 and not np.array_equal(simt, tc)
 
 
+@pytest.mark.parametrize("d", [24, 32, 48])
+def test_tensor_core_logprob_on_256_row_tiles(d, monkeypatch):
+    """Large batches of narrow rows take 256-row tiles on the tcgen05 kernel (two MMA groups per hand-off; batches below
+    2 x 148 x 256 points keep 128-row tiles, so the small-N tests above never reach this path): vMF mixture, curved vMF and dense
+    Bingham against the float64 oracle on a strided subset and the ragged tail, and bit-equal to the 128-row-tile kernel
+    (GEOSSS_TC_SUB1) -- a row's 3xTF32 arithmetic does not depend on the tile it sits in."""
+    n = 2 * 148 * 256 * 2 + 256 + 77
+    dev = torch.device("cuda", 0)
+    x = torch.nn.functional.normalize(torch.randn(n, d, device=dev, generator=torch.Generator(dev).manual_seed(d)), dim=1)
+    pick = np.r_[0:300, n // 2:n // 2 + 300, n - 400:n]
+    pdfs = [gs.MixtureModel([gs.VonMisesFisher(60.0 * m) for m in gs.sample_sphere(d - 1, 6, seed=2)]),
+            gs.CurvedVonMisesFisher(gs.SlerpCurve(gs.brownian_curve(9, d, 0.5, seed=4)), 200.0),
+            gs.random_bingham(d, 100.0, 0, False, 5)]
+    for pdf in pdfs:
+        got = pdf.log_prob(x)
+        want = oracle_of(pdf).log_prob(x[pick].double().cpu().numpy())
+        assert rel_err(got[pick].cpu().numpy(), want) <= 1e-5, type(pdf).__name__
+        monkeypatch.setenv("GEOSSS_TC_SUB1", "1")
+        small_tiles = pdf.log_prob(x)
+        monkeypatch.delenv("GEOSSS_TC_SUB1")
+        assert torch.equal(got, small_tiles), type(pdf).__name__
+
+
 # ------------------------------------------------------------------ trajectories under the reference's draws
 def tape_cases(golden):
     g = golden("traj_c1")
